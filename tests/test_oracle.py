@@ -1,0 +1,115 @@
+"""Pins the plain-C restatement (oracle/zopfli_oracle.c) against the UNMODIFIED reference compiled
+from /root/reference (oracle/_ref), at the seams of SURVEY.md section 4:
+  seam 3: per-position ZopfliFindLongestMatch (length, dist, sublen[3..length]) + hash state
+  seam 2: ZopfliLZ77Store out of ZopfliLZ77Greedy / ZopfliLZ77Optimal / ZopfliLZ77OptimalFixed
+plus the integer helpers the iterate loop drags in (katajainen.c, tree.c, deflate.c estimators).
+Bit-exact everywhere (integer/byte work; the fp64 entropy must match to the last bit too).
+"""
+import numpy as np
+import pytest
+
+import zref
+from zopfli_b200 import corpus
+
+TXT = corpus.synth_text(300000, 2)
+CASES = [
+    ("text-head", TXT, 0, 20000),
+    ("text-mid", TXT, 100000, 125000),            # 32 KiB history in play
+    ("collide", corpus.adv_collide(), 40000, 52000),  # chain cap + hash collisions
+    ("chain", corpus.adv_chain(), 30000, 42000),
+    ("runs", corpus.adv_runs(), 0, 40000),        # chain-2 switch, long-run shortcut
+    ("longrun", corpus.adv_longrun(), 0, 150000),  # `same` saturates at 65535
+    ("longrun-cut", corpus.adv_longrun(), 1000, 68000),  # block boundary inside a byte run
+    ("random", corpus.random_bytes(3000), 0, 3000),
+    ("foobar", corpus.go_case_foobar(), 0, 7013),
+    ("binary", corpus.synth_binary(200000), 60000, 100000),
+    ("tiny3", b"abcabcabc", 0, 9),
+    ("tiny1", b"a", 0, 1),
+    ("tail-repeat", b"xyz" * 200 + b"aaaa", 100, 604),
+]
+
+
+@pytest.mark.parametrize("name,data,s,e", CASES, ids=[c[0] for c in CASES])
+def test_match_table_seam(ref, oracle, name, data, s, e):
+    e2 = min(e, s + 12000)  # python-side loop over positions; keep it quick
+    a = ref.match_table(data, s, e2)
+    b = oracle.match_table(data, s, e2)
+    for x, y, what in zip(a, b, ("length", "dist", "sublen", "same", "hv", "hv2")):
+        if len(data) < 2 and what in ("hv", "hv2"):
+            continue  # hash.c:139-143 warms up one byte fewer for a 1-byte range; key never used
+        assert np.array_equal(x, y), what
+
+
+@pytest.mark.parametrize("name,data,s,e", CASES[:6], ids=[c[0] for c in CASES[:6]])
+def test_limited_walk_is_table_lookup(ref, oracle, name, data, s, e):
+    """FindLongestMatch(limit=L, sublen=NULL) == (L, sublen_full[L])."""
+    e2 = min(e, s + 6000)
+    ln, ds, sub, *_ = ref.match_table(data, s, e2)
+    rng = np.random.default_rng(5)
+    limits = np.where(ln >= 3, rng.integers(3, 259, len(ln)), 0)
+    limits = np.minimum(limits, ln).astype(np.uint16)
+    limits[limits < 3] = 0
+    rl, rd = ref.limited_match(data, s, e2, limits)
+    ol, od = oracle.limited_match(data, s, e2, limits)
+    assert np.array_equal(rl, ol) and np.array_equal(rd, od)
+    j = np.nonzero(limits >= 3)[0]
+    assert np.array_equal(rl[j], limits[j])
+    assert np.array_equal(rd[j], sub[j, limits[j]])
+
+
+@pytest.mark.parametrize("name,data,s,e", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("mode,iters", [(2, 0), (3, 0), (1, 0), (0, 1), (0, 15)])
+def test_store_seam(ref, oracle, name, data, s, e, mode, iters):
+    a = ref.lz77(data, s, e, mode, iters)
+    b = oracle.lz77(data, s, e, mode, iters)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    if s == 0 and len(a[0]):
+        llc, dc = zref.histogram(*a)
+        assert ref.block_size(data, a[0], a[1], 0, len(a[0]), 2) == oracle.dynamic_block_size(llc, dc)
+
+
+def test_store_seam_50_iterations(ref, oracle):
+    """randomisation + blended statistics active (squeeze.c:505-517)."""
+    a = ref.lz77(TXT, 0, 40000, 0, 50)
+    b = oracle.lz77(TXT, 0, 40000, 0, 50)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_length_limited_code_lengths(ref, oracle):
+    rng = np.random.default_rng(0)
+    for t in range(1500):
+        n = int(rng.choice([19, 32, 288]))
+        mb = 7 if n == 19 else 15
+        k = int(rng.integers(0, n + 1))
+        f = np.zeros(n, dtype=np.uint64)
+        idx = rng.choice(n, k, replace=False)
+        m = t % 5
+        if m == 0:
+            f[idx] = rng.integers(1, 4, k)
+        elif m == 1:
+            f[idx] = rng.integers(1, 100000, k)
+        elif m == 2:
+            f[idx] = (2 ** rng.integers(0, 18, k)).astype(np.uint64)
+        elif m == 3:
+            f[idx] = np.sort(rng.integers(1, 50, k))
+        else:  # forces the 15-bit limit with many ties
+            f[idx] = (1.5 ** rng.integers(0, 34, k)).astype(np.uint64) + rng.integers(0, 2, k).astype(np.uint64)
+        e1, a = ref.length_limited(f, mb)
+        e2, b = oracle.length_limited(f, mb)
+        assert e1 == e2 and np.array_equal(a, b)
+
+
+def test_entropy_and_rle(ref, oracle):
+    rng = np.random.default_rng(1)
+    for t in range(200):
+        c = rng.integers(0, 5000, 288).astype(np.uint64)
+        c[rng.random(288) < 0.3] = 0
+        assert np.array_equal(ref.entropy(c), oracle.entropy(c))
+    assert np.array_equal(ref.entropy(np.zeros(32)), oracle.entropy(np.zeros(32)))
+    for t in range(400):
+        n = int(rng.choice([32, 288]))
+        c = rng.integers(0, 30, n).astype(np.uint64)
+        c[rng.random(n) < 0.4] = 0
+        if t % 3 == 0:
+            c = np.repeat(rng.integers(0, 9, n // 8 + 1), 8)[:n].astype(np.uint64)
+        assert np.array_equal(ref.optimize_rle(c), oracle.optimize_rle(c))
