@@ -1,0 +1,100 @@
+/*
+ * zopfli_b200.h -- additional C-ABI entry points of libzopfli.so.1 (zopfli-b200 build).
+ *
+ * These expose the hot-path seams the reference keeps internal, for parity tests, the bench
+ * harness and multi-GPU sharding.  Plain pointers and sizes only.  Each cites the reference
+ * function whose result it returns (paths relative to /root/reference/src/zopfli/).
+ * All functions return 0 on success; CUDA failures abort (no CPU fallback exists).
+ */
+#ifndef ZOPFLI_B200_EXTRA_H_
+#define ZOPFLI_B200_EXTRA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "zopfli.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* LZ77 parse of in[instart, inend) with in[max(0,instart-32768), instart) as dictionary.
+ * mode 0: ZopfliLZ77Optimal (squeeze.h:41-44) with `numiterations`;
+ * mode 1: ZopfliLZ77OptimalFixed (squeeze.h:56-59);
+ * mode 2: ZopfliLZ77Greedy (lz77.h:136-138).
+ * Writes up to cap symbols (dists[i]==0 => literal litlens[i]) and the symbol count. */
+int ZopfliB200LZ77(const unsigned char* in, size_t insize, size_t instart, size_t inend, int mode,
+                   int numiterations, unsigned short* litlens, unsigned short* dists, size_t cap,
+                   size_t* size);
+
+/* Batched form: n ranges of one input parsed in one device pass.  off[i]/cnt[i] locate the
+ * symbols of range i inside litlens/dists (total capacity cap); cost[i] (may be NULL) receives
+ * the exact dynamic-block bit size of the returned parse (ZopfliCalculateBlockSize btype 2,
+ * deflate.h:79-80) for mode 0. */
+int ZopfliB200LZ77Batch(const unsigned char* in, size_t insize, size_t n, const size_t* instart,
+                        const size_t* inend, int mode, int numiterations, unsigned short* litlens,
+                        unsigned short* dists, size_t cap, size_t* off, size_t* cnt,
+                        uint64_t* cost);
+
+/* ZopfliFindLongestMatch (lz77.h:112-115) for every position of [instart, inend), limit 258,
+ * cache disabled: length[j], distance[j], sublen[j*259 + k] for k in 3..length[j] (0 elsewhere),
+ * plus the per-position hash state same / hashval / hashval2 (hash.h:29-47). Any output may be NULL. */
+int ZopfliB200MatchTable(const unsigned char* in, size_t insize, size_t instart, size_t inend,
+                         unsigned short* length, unsigned short* distance, unsigned short* sublen,
+                         unsigned short* same, unsigned short* hashval, unsigned short* hashval2);
+
+/* ZopfliCalculateBlockSize(btype 2) as a function of the 288+32 symbol histogram
+ * (deflate.c:569-608), evaluated on the device (where=1) or by the host code (where=0). */
+uint64_t ZopfliB200DynamicBlockBits(const uint32_t* hist320, int where);
+
+/* Host logic seams (no GPU needed): ZopfliBlockSplitLZ77 (blocksplitter.h:42-45) and
+ * ZopfliCalculateBlockSize[AutoType] (deflate.h:79-86) over an explicit symbol list whose first
+ * symbol starts at byte 0 of `in`. */
+size_t ZopfliB200HostBlockSplitLZ77(const unsigned char* in, const unsigned short* litlens,
+                                    const unsigned short* dists, size_t n, size_t maxblocks,
+                                    size_t* points, size_t cap);
+double ZopfliB200HostBlockSize(const unsigned char* in, const unsigned short* litlens,
+                               const unsigned short* dists, size_t n, size_t lstart, size_t lend,
+                               int btype /* 0,1,2 or -1 for AutoType */);
+/* AddLZ77Block (deflate.c:682-745) for btype 1/2 at bit offset 0: emits one block into out
+ * (capacity cap bytes), returns the number of bits. */
+uint64_t ZopfliB200HostEmitBlock(const unsigned char* in, const unsigned short* litlens,
+                                 const unsigned short* dists, size_t n, size_t lstart, size_t lend,
+                                 int btype, int final, unsigned char* out, size_t cap);
+/* ZopfliLengthLimitedCodeLengths (katajainen.h:35-36) as restated for host and device. */
+int ZopfliB200HostLengthLimited(const uint32_t* freq, int n, int maxbits, unsigned* bitlengths);
+
+/* Sharding: compress master blocks [mb_begin, mb_end) of `in` (1,000,000-byte
+ * units, util.h:60; deflate.c:912-924) into a position-independent SPAN: a sequence of records
+ *   u8 kind (0 bits, 1 stored) | u8 final | u64 nbits-or-nbytes | payload bytes
+ * Compressed blocks are encoded at bit offset 0; stored blocks carry their raw bytes because
+ * their padding depends on the final bit offset (deflate.c:643-649).  `final` marks the last
+ * block of the last unit.  If dev_in is non-NULL it is a device pointer holding the same bytes
+ * as `in` (16-byte aligned, readable 16 bytes past insize) and no host-to-device copy is made. */
+int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in, size_t insize,
+                          const unsigned char* dev_in, size_t mb_begin, size_t mb_end, int final,
+                          unsigned char** span, size_t* spansize);
+/* Splices a span onto a stream whose last byte has *bp bits in use (bit-offset scan). */
+void ZopfliB200AppendSpan(const unsigned char* span, size_t spansize, unsigned char* bp,
+                          unsigned char** out, size_t* outsize);
+/* ZopfliCompress with the input already resident on the device (bench `value` leg). */
+void ZopfliB200CompressDevice(const ZopfliOptions* options, ZopfliFormat output_type,
+                              const unsigned char* in, size_t insize, const unsigned char* dev_in,
+                              unsigned char** out, size_t* outsize);
+
+/* Engine control / introspection. */
+typedef struct ZopfliB200Stats {
+  double ms_same, ms_keys, ms_scan, ms_scatter, ms_match, ms_greedy, ms_iterate, ms_pack, ms_h2d, ms_d2h;
+  double ms_host_split, ms_host_emit, ms_host_other, ms_total;
+  uint64_t launches, match_positions, iterate_positions, iterate_steps, h2d_bytes, d2h_bytes;
+} ZopfliB200Stats;
+void ZopfliB200GetStats(ZopfliB200Stats* out);
+void ZopfliB200ResetStats(void);
+void ZopfliB200SetStream(void* cuda_stream);
+int ZopfliB200Device(void);
+const char* ZopfliB200Version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

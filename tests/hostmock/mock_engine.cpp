@@ -1,0 +1,64 @@
+// TEST INFRASTRUCTURE ONLY -- never part of libzopfli.so.
+//
+// A stand-in for zb::Engine (zopfli_b200/csrc/engine.hpp) that answers parse requests with the
+// plain-C oracle (oracle/zopfli_oracle.c).  tests/hostmock/Makefile links it with the PRODUCT's
+// host sources (driver.cpp, api.cpp) into tests/_build/libzopfli_hostmock.so so that the host
+// logic -- block splitting, block-type choice, bit emission, containers, splice -- can be checked
+// against the reference on a box without a GPU.  The shipped library links engine.cu instead and
+// has no such path.
+#include <string.h>
+
+#include <vector>
+
+#include "../../oracle/zopfli_oracle.h"
+#include "../../zopfli_b200/csrc/engine.hpp"
+
+namespace zb {
+
+struct Engine::Impl {
+  std::vector<uint8_t> in;
+};
+
+Engine::Engine() : p_(new Impl) {}
+Engine& Engine::get() {
+  static Engine* e = new Engine;
+  return *e;
+}
+int Engine::device() const { return -1; }
+void Engine::set_stream(void*) {}
+EngineStats Engine::stats() {
+  EngineStats s;
+  memset(&s, 0, sizeof(s));
+  return s;
+}
+void Engine::reset_stats() {}
+void Engine::set_input_host(const uint8_t* in, size_t n) {
+  p_->in.assign(in, in + n);
+  p_->in.resize(n + 64, 0);
+}
+void Engine::set_input_device(const uint8_t*, size_t) {}
+void Engine::parse(const std::vector<ParseRange>& r, ParseResult& out) {
+  out.off.assign(r.size(), 0);
+  out.size.assign(r.size(), 0);
+  out.cost.assign(r.size(), 0);
+  out.ll.clear();
+  out.d.clear();
+  for (size_t i = 0; i < r.size(); i++) {
+    ZoStore st;
+    zo_store_init(&st);
+    if (r[i].mode == 0) zo_lz77_greedy(p_->in.data(), r[i].instart, r[i].inend, &st);
+    else if (r[i].mode == 1) zo_lz77_optimal(p_->in.data(), r[i].instart, r[i].inend, r[i].numiterations, &st);
+    else zo_lz77_optimal_fixed(p_->in.data(), r[i].instart, r[i].inend, &st);
+    out.off[i] = (uint32_t)out.ll.size();
+    out.size[i] = (uint32_t)st.size;
+    out.ll.insert(out.ll.end(), st.litlens, st.litlens + st.size);
+    out.d.insert(out.d.end(), st.dists, st.dists + st.size);
+    zo_store_free(&st);
+  }
+}
+void Engine::match_table(uint64_t, uint64_t, std::vector<uint16_t>&, std::vector<uint16_t>&,
+                         std::vector<uint16_t>&, std::vector<uint16_t>&, std::vector<uint16_t>&,
+                         std::vector<uint16_t>&) {}
+uint64_t Engine::device_block_bits(const uint32_t*) { return 0; }
+
+}  // namespace zb

@@ -1,0 +1,165 @@
+"""Host-side logic of the product (block splitter, size estimators, emitter, containers, splice,
+span sharding) against the UNMODIFIED reference -- runs without a GPU.
+
+End-to-end cases link the PRODUCT's host sources against a mock engine that answers LZ77 parse
+requests with the oracle (tests/hostmock/): whatever differs from the reference here is a host
+bug, not a kernel bug.  The shipped libzopfli.so.1 contains no such path.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import zopfli_b200 as zb
+import zref
+from zopfli_b200 import corpus
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TXT = corpus.synth_text(2200000, 2)
+
+
+@pytest.fixture(scope="module")
+def mock():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "hostmock")])
+    return zb.Library(os.path.join(ROOT, "tests", "_build", "libzopfli_hostmock.so"))
+
+
+@pytest.fixture(scope="module")
+def host():
+    """the real product library; only its GPU-free host seams are used in this file"""
+    if not os.path.exists(zb.LIB_PATH):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "zopfli_b200", "csrc")])
+    return zb.Library()
+
+
+def test_library_exports_every_declared_symbol(host):
+    import ctypes
+    import re
+    names = set()
+    for h in ("zopfli.h", "zopfli_b200.h"):
+        src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", h)).read(), flags=re.S)
+        names |= set(re.findall(r"\b(Zopfli[A-Za-z0-9]+)\s*\(", src))
+    assert names >= set(zb.EXPORTS)
+    for n in sorted(names):
+        assert hasattr(host.lib, n), n
+    o = zb.ZopfliOptions()
+    host.lib.ZopfliInitOptions(ctypes.byref(o))  # util.c:28-35
+    assert (o.verbose, o.verbose_more, o.numiterations, o.blocksplitting, o.blocksplittinglast,
+            o.blocksplittingmax) == (0, 0, 15, 1, 0, 15)
+    assert ctypes.sizeof(zb.ZopfliOptions) == 24
+
+
+def test_length_limited_host(ref, host):
+    rng = np.random.default_rng(0)
+    for t in range(600):
+        n = int(rng.choice([19, 32, 288]))
+        mb = 7 if n == 19 else 15
+        f = np.zeros(n, np.uint32)
+        k = int(rng.integers(0, n + 1))
+        idx = rng.choice(n, k, replace=False)
+        if t % 2:
+            f[idx] = (1.5 ** rng.integers(0, 30, k)).astype(np.uint32) + rng.integers(0, 2, k).astype(np.uint32)
+        else:
+            f[idx] = rng.integers(1, 9, k)
+        assert np.array_equal(ref.length_limited(f.astype(np.uint64), mb)[1], host.host_length_limited(f, mb)[1])
+
+
+def test_split_and_block_sizes(ref, host):
+    rng = np.random.default_rng(1)
+    for data, s, e in [(TXT, 0, 1000000), (corpus.synth_binary(400000), 0, 400000), (corpus.adv_runs(), 0, 200000)]:
+        ll, dd = ref.lz77(data, s, e, 3)
+        for maxblocks in (15, 4, 0):
+            assert np.array_equal(ref.block_split_lz77(data, ll, dd, maxblocks), host.host_block_split_lz77(ll, dd, maxblocks))
+        for t in range(40):
+            a = int(rng.integers(0, len(ll) - 1))
+            b = int(rng.integers(a + 1, min(len(ll), a + 1 + int(rng.choice([50, 900, 5000, 100000]))) + 1))
+            for bt in (0, 1, 2, -1):
+                assert ref.block_size(data, ll, dd, a, b, bt) == host.host_block_size(ll, dd, a, b, bt)
+    # small store: the `lz77->size > 1000` quirk of deflate.c:615 goes the other way
+    ll, dd = ref.lz77(TXT, 0, 1800, 3)
+    assert len(ll) < 1000
+    for a, b in [(0, len(ll)), (10, 200), (5, 6)]:
+        assert ref.block_size(TXT, ll, dd, a, b, -1) == host.host_block_size(ll, dd, a, b, -1)
+
+
+def test_emit_dynamic_block_matches_reference_stream(ref, host):
+    """single block, no splitting: the reference's whole output is one AddLZ77Block call"""
+    data = TXT[:30000]
+    ll, dd = ref.lz77(data, 0, len(data), 0, 15)
+    want, bp = ref.deflate_part(data, 0, len(data), final=1, blocksplitting=0)
+    got, bits = host.host_emit_block(ll, dd, 0, len(ll), 2, 1)
+    assert got == want and bits % 8 == bp
+
+
+END_TO_END = [
+    ("empty", b""), ("a", b"a"), ("ab", b"ab"), ("abc", b"abc"), ("foobar", corpus.go_case_foobar()),
+    ("rand3000", corpus.random_bytes(3000)), ("text40k", TXT[:40000]), ("runs", corpus.adv_runs()[:60000]),
+    ("mixed", corpus.mixed_small(50000)), ("zeros", b"\0" * 70000), ("rand70k", corpus.random_bytes(70000)),
+    ("binary", corpus.synth_binary(120000)), ("len258", b"q" * 258), ("len259", b"q" * 259),
+]
+
+
+@pytest.mark.parametrize("name,data", END_TO_END, ids=[c[0] for c in END_TO_END])
+def test_compress_all_formats(ref, mock, name, data):
+    for fmt in (0, 1, 2):
+        assert ref.compress(data, fmt) == mock.compress(data, fmt), fmt
+
+
+def test_known_answers(mock):
+    """oracle known answers recorded in SURVEY App. C"""
+    assert mock.compress(b"", 0).hex() == "1f8b08000000000002030300" + "0000000000000000"
+    assert mock.compress(b"", 1).hex() == "78da030000000001"
+    assert mock.compress(b"", 2).hex() == "0300"
+    assert mock.compress(b"a", 2).hex() == "4b0400"
+    assert mock.compress(b"a", 1).hex() == "78da4b040000620062"
+    assert mock.compress(b"a", 0).hex() == "1f8b08000000000002034b040043beb7e801000000"
+
+
+def test_options_and_btypes(ref, mock):
+    data = TXT[:60000]
+    for kw in ({"numiterations": 1}, {"numiterations": 5, "blocksplittingmax": 3}, {"blocksplitting": 0},
+               {"blocksplittingmax": 0, "numiterations": 2}):
+        assert ref.compress(data, 2, **kw) == mock.compress(data, 2, **kw), kw
+    for btype in (0, 1, 2):
+        for final in (0, 1):
+            a, abp = ref.deflate_part(data, 0, len(data), final=final, btype=btype, numiterations=3)
+            b, bbp = mock.deflate_part(data, 0, len(data), final=final, btype=btype, numiterations=3)
+            assert a == b and abp == bbp, (btype, final)
+    big = corpus.random_bytes(140000)  # stored blocks split at 65535
+    assert ref.deflate_part(big, 0, len(big), btype=0) == mock.deflate_part(big, 0, len(big), btype=0)
+
+
+def test_deflate_part_with_dictionary_and_chained_bp(ref, mock):
+    import ctypes as C
+    data = TXT[:150000]
+    a, abp = ref.deflate_part(data, 50000, 110000, final=1, numiterations=2)
+    b, bbp = mock.deflate_part(data, 50000, 110000, final=1, numiterations=2)
+    assert a == b and abp == bbp
+    # two chained calls sharing one output buffer and bit pointer (deflate.h:50-53)
+    outs = []
+    for lib in (ref.lib, mock.lib):
+        arr = np.frombuffer(data + b"\0" * 16, np.uint8)
+        o = zb.ZopfliOptions(0, 0, 2, 1, 0, 15)
+        out, n, bp = C.c_void_p(None), C.c_size_t(0), C.c_ubyte(0)
+        lib.ZopfliDeflatePart(C.byref(o), 2, 0, arr.ctypes.data, 0, 70000, C.byref(bp), C.byref(out), C.byref(n))
+        lib.ZopfliDeflatePart(C.byref(o), 2, 1, arr.ctypes.data, 70000, 150000, C.byref(bp), C.byref(out), C.byref(n))
+        outs.append((C.string_at(out, n.value), bp.value))
+    assert outs[0] == outs[1]
+    import zlib
+    assert zlib.decompress(outs[1][0], -15) == data
+
+
+def test_multi_master_block_and_spans(ref, mock):
+    data = TXT  # 2.2 MB: three master blocks, last one partial
+    want = ref.compress(data, 2, numiterations=1)
+    assert mock.compress(data, 2, numiterations=1) == want
+    # per-shard spans spliced by a bit-offset scan equal the single-call stream
+    spans = [mock.deflate_span(data, m, m + 1, final=int(m == 2), numiterations=1) for m in range(3)]
+    got, bp = mock.splice_spans(spans)
+    assert got == want
+    # stored blocks inside spans (random data -> stored), with a non-zero bit offset before them
+    mix = TXT[:1000000] + corpus.random_bytes(300000)
+    want = ref.compress(mix, 2, numiterations=1)
+    spans = [mock.deflate_span(mix, m, m + 1, final=int(m == 1), numiterations=1) for m in range(2)]
+    assert mock.splice_spans(spans)[0] == want

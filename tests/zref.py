@@ -19,10 +19,7 @@ u8p = C.POINTER(C.c_ubyte)
 u16p = C.POINTER(C.c_uint16)
 
 
-class ZopfliOptions(C.Structure):
-    _fields_ = [("verbose", C.c_int), ("verbose_more", C.c_int), ("numiterations", C.c_int),
-                ("blocksplitting", C.c_int), ("blocksplittinglast", C.c_int),
-                ("blocksplittingmax", C.c_int)]
+from zopfli_b200 import ZopfliOptions  # same 6-int layout, zopfli.h:33-64
 
 
 def ensure_built():

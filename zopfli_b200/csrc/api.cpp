@@ -1,0 +1,431 @@
+// C-ABI of libzopfli.so.1 (zopfli-b200): the reference's public entry points
+// (/root/reference/src/zopfli/zopfli.h, deflate.h, gzip_container.h, zlib_container.h) plus the
+// seams declared in include/zopfli_b200.h.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <thread>
+#include <vector>
+
+#include "../../include/zopfli_b200.h"
+#include "driver.hpp"
+#include "engine.hpp"
+#include "host_split.hpp"
+#include "lz77_store.hpp"
+
+using namespace zb;
+
+namespace {
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+double g_total_ms = 0;
+
+// ---- CRC-32 (gzip_container.c:27-81 computes the same polynomial bytewise): slicing-by-8 ----
+uint32_t g_crc_tab[8][256];
+bool g_crc_init = false;
+void crc_init() {
+  if (g_crc_init) return;
+  for (uint32_t i = 0; i < 256; i++) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+    g_crc_tab[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; i++)
+    for (int t = 1; t < 8; t++) g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 255];
+  g_crc_init = true;
+}
+uint32_t crc32_range(const unsigned char* p, size_t n, uint32_t crc) {  // crc is the running (inverted) state
+  while (n && ((uintptr_t)p & 7)) { crc = g_crc_tab[0][(crc ^ *p++) & 255] ^ (crc >> 8); n--; }
+  while (n >= 8) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    uint32_t lo = (uint32_t)v ^ crc, hi = (uint32_t)(v >> 32);
+    crc = g_crc_tab[7][lo & 255] ^ g_crc_tab[6][(lo >> 8) & 255] ^ g_crc_tab[5][(lo >> 16) & 255] ^
+          g_crc_tab[4][lo >> 24] ^ g_crc_tab[3][hi & 255] ^ g_crc_tab[2][(hi >> 8) & 255] ^
+          g_crc_tab[1][(hi >> 16) & 255] ^ g_crc_tab[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) crc = g_crc_tab[0][(crc ^ *p++) & 255] ^ (crc >> 8);
+  return crc;
+}
+// GF(2) combination of CRCs of adjacent chunks (the zlib crc32_combine construction)
+uint32_t gf2_times(const uint32_t* mat, uint32_t vec) {
+  uint32_t sum = 0;
+  for (int i = 0; vec; vec >>= 1, i++)
+    if (vec & 1) sum ^= mat[i];
+  return sum;
+}
+void gf2_square(uint32_t* sq, const uint32_t* mat) {
+  for (int n = 0; n < 32; n++) sq[n] = gf2_times(mat, mat[n]);
+}
+uint32_t crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2) {
+  if (len2 == 0) return crc1;
+  uint32_t even[32], odd[32];
+  odd[0] = 0xEDB88320u;
+  uint32_t row = 1;
+  for (int n = 1; n < 32; n++) { odd[n] = row; row <<= 1; }
+  gf2_square(even, odd);
+  gf2_square(odd, even);
+  do {
+    gf2_square(even, odd);
+    if (len2 & 1) crc1 = gf2_times(even, crc1);
+    len2 >>= 1;
+    if (len2 == 0) break;
+    gf2_square(odd, even);
+    if (len2 & 1) crc1 = gf2_times(odd, crc1);
+    len2 >>= 1;
+  } while (len2 != 0);
+  return crc1 ^ crc2;
+}
+uint32_t crc32_parallel(const unsigned char* p, size_t n) {
+  crc_init();
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > 16) nt = 16;
+  if (n < (4u << 20) || nt == 1) return crc32_range(p, n, 0xffffffffu) ^ 0xffffffffu;
+  std::vector<uint32_t> part(nt);
+  std::vector<std::thread> th;
+  size_t chunk = (n + nt - 1) / nt;
+  for (unsigned t = 0; t < nt; t++)
+    th.emplace_back([&, t] {
+      size_t a = t * chunk, b = a + chunk > n ? n : a + chunk;
+      part[t] = a < b ? (crc32_range(p + a, b - a, 0xffffffffu) ^ 0xffffffffu) : 0;
+    });
+  for (auto& t : th) t.join();
+  uint32_t crc = part[0];
+  for (unsigned t = 1; t < nt; t++) {
+    size_t a = t * chunk, b = a + chunk > n ? n : a + chunk;
+    if (a < b) crc = crc32_combine(crc, part[t], b - a);
+  }
+  return crc;
+}
+
+// ---- Adler-32 (zlib_container.c:29-48) ----
+uint32_t adler32(const unsigned char* data, size_t size) {
+  uint32_t s1 = 1, s2 = 0;
+  while (size > 0) {
+    size_t amount = size > 5550 ? 5550 : size;
+    size -= amount;
+    while (amount--) { s1 += *data++; s2 += s1; }
+    s1 %= 65521;
+    s2 %= 65521;
+  }
+  return (s2 << 16) | s1;
+}
+
+void put_byte(unsigned char v, unsigned char** out, size_t* outsize) { append_bytes(&v, 1, out, outsize); }
+
+std::vector<std::pair<size_t, size_t>> master_units(size_t insize, size_t mb_begin, size_t mb_end) {
+  std::vector<std::pair<size_t, size_t>> u;
+  for (size_t m = mb_begin; m < mb_end; m++) {
+    size_t a = m * (size_t)kMasterBlock, b = a + kMasterBlock;
+    if (b > insize) b = insize;
+    u.push_back({a, b});
+  }
+  return u;
+}
+size_t num_master_blocks(size_t insize) {  // deflate.c:912-924 do/while
+  return insize == 0 ? 1 : (insize + kMasterBlock - 1) / kMasterBlock;
+}
+
+void deflate_impl(const ZopfliOptions* options, int btype, int final, const unsigned char* in,
+                  size_t insize, const unsigned char* dev_in, unsigned char* bp, unsigned char** out,
+                  size_t* outsize) {
+  double t0 = now_ms();
+  size_t offset = *outsize;
+  std::vector<Piece> pieces;
+  if (btype != 0) {
+    if (dev_in) Engine::get().set_input_device(dev_in, insize);
+    else Engine::get().set_input_host(in, insize);
+  }
+  deflate_units(options, btype, final != 0, in, master_units(insize, 0, num_master_blocks(insize)), 0, pieces);
+  splice_pieces(pieces, in, bp, out, outsize);
+  if (options->verbose) {
+    fprintf(stderr, "Original Size: %lu, Deflate: %lu, Compression: %f%% Removed\n", (unsigned long)insize,
+            (unsigned long)(*outsize - offset), 100.0 * (double)(insize - (*outsize - offset)) / (double)insize);
+  }
+  g_total_ms += now_ms() - t0;
+}
+
+void compress_impl(const ZopfliOptions* options, ZopfliFormat fmt, const unsigned char* in, size_t insize,
+                   const unsigned char* dev_in, unsigned char** out, size_t* outsize) {
+  unsigned char bp = 0;
+  if (fmt == ZOPFLI_FORMAT_GZIP) {  // gzip_container.c:84-124
+    uint32_t crc = 0;
+    std::thread crc_thread([&] { crc = crc32_parallel(in, insize); });  // overlaps the GPU work
+    static const unsigned char hdr[10] = {31, 139, 8, 0, 0, 0, 0, 0, 2, 3};
+    append_bytes(hdr, 10, out, outsize);
+    deflate_impl(options, 2, 1, in, insize, dev_in, &bp, out, outsize);
+    crc_thread.join();
+    unsigned char tr[8] = {(unsigned char)(crc & 255), (unsigned char)((crc >> 8) & 255),
+                           (unsigned char)((crc >> 16) & 255), (unsigned char)((crc >> 24) & 255),
+                           (unsigned char)(insize & 255), (unsigned char)((insize >> 8) & 255),
+                           (unsigned char)((insize >> 16) & 255), (unsigned char)((insize >> 24) & 255)};
+    append_bytes(tr, 8, out, outsize);
+    if (options->verbose)
+      fprintf(stderr, "Original Size: %d, Gzip: %d, Compression: %f%% Removed\n", (int)insize, (int)*outsize,
+              100.0 * (double)(insize - *outsize) / (double)insize);
+  } else if (fmt == ZOPFLI_FORMAT_ZLIB) {  // zlib_container.c:50-79
+    uint32_t checksum = adler32(in, (unsigned)insize);
+    unsigned cmfflg = 256 * 120 + 3 * 64;
+    cmfflg += 31 - cmfflg % 31;
+    put_byte((unsigned char)(cmfflg / 256), out, outsize);
+    put_byte((unsigned char)(cmfflg % 256), out, outsize);
+    deflate_impl(options, 2, 1, in, insize, dev_in, &bp, out, outsize);
+    unsigned char tr[4] = {(unsigned char)((checksum >> 24) & 255), (unsigned char)((checksum >> 16) & 255),
+                           (unsigned char)((checksum >> 8) & 255), (unsigned char)(checksum & 255)};
+    append_bytes(tr, 4, out, outsize);
+    if (options->verbose)
+      fprintf(stderr, "Original Size: %d, Zlib: %d, Compression: %f%% Removed\n", (int)insize, (int)*outsize,
+              100.0 * (double)(insize - *outsize) / (double)insize);
+  } else if (fmt == ZOPFLI_FORMAT_DEFLATE) {
+    deflate_impl(options, 2, 1, in, insize, dev_in, &bp, out, outsize);
+  } else {
+    fprintf(stderr, "zopfli-b200: unknown output format %d\n", (int)fmt);  // zopfli_lib.c:40 assert(0)
+    abort();
+  }
+}
+
+void make_store(const unsigned short* ll, const unsigned short* dd, size_t n, Lz77Store& st) {
+  st.append(ll, dd, n, 0);
+  st.finalize();
+}
+
+}  // namespace
+
+extern "C" {
+
+void ZopfliInitOptions(ZopfliOptions* options) {  // util.c:28-35
+  options->verbose = 0;
+  options->verbose_more = 0;
+  options->numiterations = 15;
+  options->blocksplitting = 1;
+  options->blocksplittinglast = 0;
+  options->blocksplittingmax = 15;
+}
+
+void ZopfliCompress(const ZopfliOptions* options, ZopfliFormat output_type, const unsigned char* in,
+                    size_t insize, unsigned char** out, size_t* outsize) {
+  compress_impl(options, output_type, in, insize, nullptr, out, outsize);
+}
+
+void ZopfliB200CompressDevice(const ZopfliOptions* options, ZopfliFormat output_type, const unsigned char* in,
+                              size_t insize, const unsigned char* dev_in, unsigned char** out, size_t* outsize) {
+  compress_impl(options, output_type, in, insize, dev_in, out, outsize);
+}
+
+void ZopfliGzipCompress(const ZopfliOptions* options, const unsigned char* in, size_t insize,
+                        unsigned char** out, size_t* outsize) {
+  compress_impl(options, ZOPFLI_FORMAT_GZIP, in, insize, nullptr, out, outsize);
+}
+
+void ZopfliZlibCompress(const ZopfliOptions* options, const unsigned char* in, size_t insize,
+                        unsigned char** out, size_t* outsize) {
+  compress_impl(options, ZOPFLI_FORMAT_ZLIB, in, insize, nullptr, out, outsize);
+}
+
+void ZopfliDeflate(const ZopfliOptions* options, int btype, int final, const unsigned char* in, size_t insize,
+                   unsigned char* bp, unsigned char** out, size_t* outsize) {
+  deflate_impl(options, btype, final, in, insize, nullptr, bp, out, outsize);
+}
+
+void ZopfliDeflatePart(const ZopfliOptions* options, int btype, int final, const unsigned char* in,
+                       size_t instart, size_t inend, unsigned char* bp, unsigned char** out,
+                       size_t* outsize) {
+  // only in[max(0, instart-32768), inend) can influence the result (squeeze.c:229-241)
+  size_t base = instart > (size_t)kWindow ? instart - kWindow : 0;
+  base &= ~(size_t)15;
+  std::vector<Piece> pieces;
+  if (btype != 0) Engine::get().set_input_host(in + base, inend - base);
+  deflate_units(options, btype, final != 0, in, {{instart, inend}}, base, pieces);
+  splice_pieces(pieces, in, bp, out, outsize);
+}
+
+int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in, size_t insize,
+                          const unsigned char* dev_in, size_t mb_begin, size_t mb_end, int final,
+                          unsigned char** span, size_t* spansize) {
+  std::vector<Piece> pieces;
+  auto units = master_units(insize, mb_begin, mb_end);
+  if (units.empty()) return 0;
+  size_t base = 0;
+  if (dev_in) {
+    Engine::get().set_input_device(dev_in, insize);
+  } else {
+    base = units.front().first > (size_t)kWindow ? units.front().first - kWindow : 0;
+    base &= ~(size_t)15;
+    Engine::get().set_input_host(in + base, units.back().second - base);
+  }
+  deflate_units(options, 2, final != 0, in, units, base, pieces);
+  for (auto& p : pieces) {
+    unsigned char hdr[10];
+    hdr[0] = p.stored ? 1 : 0;
+    hdr[1] = p.final ? 1 : 0;
+    uint64_t v = p.stored ? (uint64_t)(p.inend - p.instart) : p.bits.nbits;
+    memcpy(hdr + 2, &v, 8);
+    append_bytes(hdr, 10, span, spansize);
+    if (p.stored) append_bytes(in + p.instart, p.inend - p.instart, span, spansize);
+    else append_bytes(p.bits.bytes.data(), p.bits.bytes.size(), span, spansize);
+  }
+  return 0;
+}
+
+void ZopfliB200AppendSpan(const unsigned char* span, size_t spansize, unsigned char* bp, unsigned char** out,
+                          size_t* outsize) {
+  std::vector<Piece> pieces;
+  std::vector<unsigned char> rawbytes;  // stored payloads, addressed through instart/inend
+  size_t o = 0;
+  // first pass: collect stored payloads contiguously so Piece offsets can index one buffer
+  while (o + 10 <= spansize) {
+    uint64_t v;
+    memcpy(&v, span + o + 2, 8);
+    bool stored = span[o] == 1;
+    size_t nbytes = stored ? (size_t)v : (size_t)((v + 7) / 8);
+    Piece p;
+    p.stored = stored;
+    p.final = span[o + 1] != 0;
+    if (stored) {
+      p.instart = rawbytes.size();
+      rawbytes.insert(rawbytes.end(), span + o + 10, span + o + 10 + nbytes);
+      p.inend = rawbytes.size();
+    } else {
+      p.bits.bytes.assign(span + o + 10, span + o + 10 + nbytes);
+      p.bits.nbits = v;
+    }
+    pieces.push_back(std::move(p));
+    o += 10 + nbytes;
+  }
+  splice_pieces(pieces, rawbytes.data(), bp, out, outsize);
+}
+
+int ZopfliB200LZ77Batch(const unsigned char* in, size_t insize, size_t n, const size_t* instart,
+                        const size_t* inend, int mode, int numiterations, unsigned short* litlens,
+                        unsigned short* dists, size_t cap, size_t* off, size_t* cnt, uint64_t* cost) {
+  Engine& e = Engine::get();
+  e.set_input_host(in, insize);
+  std::vector<ParseRange> pr(n);
+  for (size_t i = 0; i < n; i++) pr[i] = {instart[i], inend[i], mode == 0 ? 1 : (mode == 1 ? 2 : 0), numiterations};
+  ParseResult res;
+  e.parse(pr, res);
+  size_t total = 0;
+  for (size_t i = 0; i < n; i++) {
+    off[i] = total;
+    cnt[i] = res.size[i];
+    if (total + res.size[i] <= cap) {
+      memcpy(litlens + total, res.ll.data() + res.off[i], res.size[i] * 2);
+      memcpy(dists + total, res.d.data() + res.off[i], res.size[i] * 2);
+    }
+    total += res.size[i];
+    if (cost) cost[i] = res.cost[i];
+  }
+  return total <= cap ? 0 : 1;
+}
+
+int ZopfliB200LZ77(const unsigned char* in, size_t insize, size_t instart, size_t inend, int mode,
+                   int numiterations, unsigned short* litlens, unsigned short* dists, size_t cap, size_t* size) {
+  size_t off = 0, cnt = 0;
+  int r = ZopfliB200LZ77Batch(in, insize, 1, &instart, &inend, mode, numiterations, litlens, dists, cap, &off, &cnt, nullptr);
+  *size = cnt;
+  return r;
+}
+
+int ZopfliB200MatchTable(const unsigned char* in, size_t insize, size_t instart, size_t inend,
+                         unsigned short* length, unsigned short* distance, unsigned short* sublen,
+                         unsigned short* same, unsigned short* hashval, unsigned short* hashval2) {
+  Engine& e = Engine::get();
+  e.set_input_host(in, insize);
+  std::vector<uint16_t> l, d, s, sm, h1, h2;
+  e.match_table(instart, inend, l, d, s, sm, h1, h2);
+  size_t n = inend - instart;
+  if (length) memcpy(length, l.data(), n * 2);
+  if (distance) memcpy(distance, d.data(), n * 2);
+  if (sublen) memcpy(sublen, s.data(), n * 259 * 2);
+  if (same) memcpy(same, sm.data(), n * 2);
+  if (hashval) memcpy(hashval, h1.data(), n * 2);
+  if (hashval2) memcpy(hashval2, h2.data(), n * 2);
+  return 0;
+}
+
+uint64_t ZopfliB200DynamicBlockBits(const uint32_t* hist320, int where) {
+  if (where == 1) return Engine::get().device_block_bits(hist320);
+  DynScratch s;
+  return dynamic_block_bits(hist320, nullptr, nullptr, s);
+}
+
+size_t ZopfliB200HostBlockSplitLZ77(const unsigned char* in, const unsigned short* litlens,
+                                    const unsigned short* dists, size_t n, size_t maxblocks, size_t* points,
+                                    size_t cap) {
+  (void)in;
+  Lz77Store st;
+  make_store(litlens, dists, n, st);
+  auto cost = [&st](size_t a, size_t b) {
+    thread_local DynScratch s;
+    return auto_type_bits(st, a, b, s);
+  };
+  std::vector<size_t> p = block_split_lz77(cost, st.size(), maxblocks);
+  for (size_t i = 0; i < p.size() && i < cap; i++) points[i] = p[i];
+  return p.size();
+}
+
+double ZopfliB200HostBlockSize(const unsigned char* in, const unsigned short* litlens,
+                               const unsigned short* dists, size_t n, size_t lstart, size_t lend, int btype) {
+  (void)in;
+  Lz77Store st;
+  make_store(litlens, dists, n, st);
+  DynScratch s;
+  if (btype < 0) return (double)auto_type_bits(st, lstart, lend, s);
+  uint32_t h[320];
+  st.range_hist(lstart, lend, h);
+  if (btype == 0) return (double)stored_bits(st.byte_range(lstart, lend));
+  if (btype == 1) return (double)fixed_block_bits(h);
+  return (double)dynamic_block_bits(h, nullptr, nullptr, s);
+}
+
+uint64_t ZopfliB200HostEmitBlock(const unsigned char* in, const unsigned short* litlens,
+                                 const unsigned short* dists, size_t n, size_t lstart, size_t lend, int btype,
+                                 int final, unsigned char* out, size_t cap) {
+  (void)in;
+  Lz77Store st;
+  make_store(litlens, dists, n, st);
+  BitString bs;
+  emit_compressed_block(btype, final != 0, st, lstart, lend, bs);
+  if (bs.bytes.size() <= cap) memcpy(out, bs.bytes.data(), bs.bytes.size());
+  return bs.nbits;
+}
+
+int ZopfliB200HostLengthLimited(const uint32_t* freq, int n, int maxbits, unsigned* bitlengths) {
+  if (n > kNumLL || maxbits > 15) return 1;
+  static thread_local PmScratch<kNumLL, 15> s;
+  std::vector<uint8_t> out(n);
+  length_limited<kNumLL, 15>(freq, n, maxbits, out.data(), s);
+  for (int i = 0; i < n; i++) bitlengths[i] = out[i];
+  return 0;
+}
+
+void ZopfliB200GetStats(ZopfliB200Stats* o) {
+  EngineStats e = Engine::get().stats();
+  o->ms_same = e.ms_same; o->ms_keys = e.ms_keys; o->ms_scan = e.ms_scan; o->ms_scatter = e.ms_scatter;
+  o->ms_match = e.ms_match; o->ms_greedy = e.ms_greedy; o->ms_iterate = e.ms_iterate; o->ms_pack = e.ms_pack;
+  o->ms_h2d = e.ms_h2d; o->ms_d2h = e.ms_d2h;
+  o->ms_host_split = g_host_times.split; o->ms_host_emit = g_host_times.emit; o->ms_host_other = g_host_times.other;
+  o->ms_total = g_total_ms;
+  o->launches = e.launches; o->match_positions = e.match_positions; o->iterate_positions = e.iterate_positions;
+  o->iterate_steps = e.iterate_steps; o->h2d_bytes = e.h2d_bytes; o->d2h_bytes = e.d2h_bytes;
+}
+
+void ZopfliB200ResetStats(void) {
+  Engine::get().reset_stats();
+  g_host_times = HostTimes();
+  g_total_ms = 0;
+}
+
+void ZopfliB200SetStream(void* s) { Engine::get().set_stream(s); }
+int ZopfliB200Device(void) { return Engine::get().device(); }
+const char* ZopfliB200Version(void) { return "zopfli-b200 0.1 (ABI libzopfli.so.1, reference 1.0.3)"; }
+
+}  // extern "C"

@@ -1,0 +1,391 @@
+// Host driver behind ZopfliDeflate / ZopfliDeflatePart (drop-in boundary).
+//
+// Reference control flow (/root/reference/src/zopfli/deflate.c:811-931) is one master block at a
+// time, one block at a time.  Here every stage is batched over ALL master blocks of the call so
+// the GPU sees every independent unit at once:
+//
+//   stage A  GPU   greedy parse of every master block              (blocksplitter.c:288-296)
+//   stage B  host  split-point search per master block, threaded   (blocksplitter.c:215-273)
+//   stage C  GPU   optimal parse of every block of every master block (deflate.c:854-869)
+//   stage D  host  second split attempt + block-type choice        (deflate.c:872-893, 747-800)
+//   stage E  GPU   fixed-tree re-parses requested by stage D        (deflate.c:771-781)
+//   stage F  host  bit emission per block (threaded) + bit-offset splice
+#include "driver.hpp"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <chrono>
+#include <thread>
+
+#include "emit.hpp"
+#include "engine.hpp"
+#include "host_split.hpp"
+#include "lz77_store.hpp"
+
+namespace zb {
+
+HostTimes g_host_times;
+
+namespace {
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+int host_threads() {
+  static int n = [] {
+    const char* e = getenv("ZOPFLI_B200_THREADS");
+    int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+    return v < 1 ? 1 : (v > 256 ? 256 : v);
+  }();
+  return n;
+}
+
+template <typename F>
+void parallel_for(size_t n, F fn) {
+  int nt = (int)std::min<size_t>(n, (size_t)host_threads());
+  if (nt <= 1) {
+    for (size_t i = 0; i < n; i++) fn(i);
+    return;
+  }
+  std::atomic<size_t> next(0);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++)
+    th.emplace_back([&] {
+      for (;;) {
+        size_t i = next.fetch_add(1);
+        if (i >= n) break;
+        fn(i);
+      }
+    });
+  for (auto& t : th) t.join();
+}
+
+struct FinalBlock {
+  size_t lstart, lend;       // symbol range in the master block's store
+  uint64_t unc, fixed, dyn;
+  bool expensive = false;
+  int fixed_req = -1;        // index into the fixed re-parse batch
+};
+
+struct Master {
+  size_t ms, me;                       // byte range
+  Lz77Store greedy;
+  std::vector<size_t> cuts;            // block boundaries in bytes (ms, ..., me)
+  std::vector<Lz77Store> blockstores;
+  Lz77Store lz77;
+  std::vector<size_t> points;          // final split points (symbol indices)
+  std::vector<FinalBlock> finals;
+  std::vector<Lz77Store> fixedstores;
+  std::vector<Piece> pieces;
+};
+
+RangeCostFn make_cost(const Lz77Store& st) {
+  return [&st](size_t a, size_t b) {
+    thread_local DynScratch s;
+    return auto_type_bits(st, a, b, s);
+  };
+}
+
+void stored_pieces(size_t a, size_t b, bool final, std::vector<Piece>& out) {
+  Piece p;
+  p.stored = true;
+  p.instart = a;
+  p.inend = b;
+  p.final = final;
+  out.push_back(std::move(p));
+}
+
+}  // namespace
+
+// in_base: absolute position of device/engine byte 0 (the engine holds bytes [in_base, ...)).
+void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const unsigned char* in,
+                   const std::vector<std::pair<size_t, size_t>>& units, size_t in_base,
+                   std::vector<Piece>& pieces) {
+  Engine& eng = Engine::get();
+  const size_t nm = units.size();
+  std::vector<Master> M(nm);
+  for (size_t m = 0; m < nm; m++) { M[m].ms = units[m].first; M[m].me = units[m].second; }
+
+  if (btype == 0) {  // deflate.c:826-828
+    for (size_t m = 0; m < nm; m++) stored_pieces(M[m].ms, M[m].me, final_last && m + 1 == nm, pieces);
+    return;
+  }
+  double t0 = now_ms();
+  if (btype == 1) {  // deflate.c:829-841: one fixed-tree optimal parse per unit
+    std::vector<ParseRange> pr;
+    for (auto& mb : M) pr.push_back({mb.ms - in_base, mb.me - in_base, 2, 0});
+    ParseResult res;
+    eng.parse(pr, res);
+    for (size_t m = 0; m < nm; m++) {
+      Lz77Store st;
+      st.append(res.ll.data() + res.off[m], res.d.data() + res.off[m], res.size[m], M[m].ms);
+      st.finalize();
+      Piece p;
+      emit_compressed_block(1, final_last && m + 1 == nm, st, 0, st.size(), p.bits);
+      pieces.push_back(std::move(p));
+    }
+    return;
+  }
+
+  // ---- stage A: greedy parses (only needed when splitting) ----
+  const size_t maxblocks = (size_t)opt->blocksplittingmax;
+  if (opt->blocksplitting) {
+    std::vector<ParseRange> pr;
+    for (auto& mb : M) pr.push_back({mb.ms - in_base, mb.me - in_base, 0, 0});
+    ParseResult res;
+    eng.parse(pr, res);
+    double t1 = now_ms();
+    g_host_times.other += t1 - t0;
+    // ---- stage B: split search ----
+    parallel_for(nm, [&](size_t m) {
+      Master& mb = M[m];
+      mb.greedy.append(res.ll.data() + res.off[m], res.d.data() + res.off[m], res.size[m], mb.ms);
+      mb.greedy.finalize();
+      std::vector<size_t> lp = block_split_lz77(make_cost(mb.greedy), mb.greedy.size(), maxblocks);
+      mb.cuts.push_back(mb.ms);
+      for (size_t p : lp) mb.cuts.push_back(mb.greedy.pos[p]);  // blocksplitter.c:303-313
+      mb.cuts.push_back(mb.me);
+      if (opt->verbose) {
+        fprintf(stderr, "block split points: ");
+        for (size_t p : lp) fprintf(stderr, "%d ", (int)mb.greedy.pos[p]);
+        fprintf(stderr, "\n");
+      }
+      mb.greedy.clear();
+    });
+    double t2 = now_ms();
+    g_host_times.split += t2 - t1;
+    t0 = t2;
+  } else {
+    for (auto& mb : M) { mb.cuts.push_back(mb.ms); mb.cuts.push_back(mb.me); }
+  }
+
+  // ---- stage C: optimal parse of every block ----
+  {
+    std::vector<ParseRange> pr;
+    std::vector<std::pair<size_t, size_t>> owner;
+    for (size_t m = 0; m < nm; m++)
+      for (size_t i = 0; i + 1 < M[m].cuts.size(); i++) {
+        pr.push_back({M[m].cuts[i] - in_base, M[m].cuts[i + 1] - in_base, 1, opt->numiterations});
+        owner.push_back({m, i});
+      }
+    ParseResult res;
+    eng.parse(pr, res);
+    for (size_t m = 0; m < nm; m++) M[m].blockstores.resize(M[m].cuts.size() - 1);
+    parallel_for(pr.size(), [&](size_t k) {
+      Master& mb = M[owner[k].first];
+      Lz77Store& st = mb.blockstores[owner[k].second];
+      st.append(res.ll.data() + res.off[k], res.d.data() + res.off[k], res.size[k], mb.cuts[owner[k].second]);
+      st.finalize();
+    });
+  }
+  double t3 = now_ms();
+  g_host_times.other += t3 - t0;
+
+  // ---- stage D: second split attempt and block types ----
+  std::vector<std::vector<ParseRange>> fixed_req(nm);
+  parallel_for(nm, [&](size_t m) {
+    Master& mb = M[m];
+    DynScratch s;
+    uint64_t totalcost = 0;
+    const size_t nblocks = mb.blockstores.size();
+    std::vector<size_t> points;
+    for (size_t i = 0; i < nblocks; i++) {
+      totalcost += auto_type_bits(mb.blockstores[i], 0, mb.blockstores[i].size(), s);  // deflate.c:862
+      mb.lz77.append(mb.blockstores[i]);
+      if (i + 1 < nblocks) points.push_back(mb.lz77.size());
+    }
+    mb.blockstores.clear();
+    mb.lz77.finalize();
+    if (opt->blocksplitting && points.size() > 1) {  // deflate.c:872-893
+      std::vector<size_t> p2 = block_split_lz77(make_cost(mb.lz77), mb.lz77.size(), maxblocks);
+      uint64_t totalcost2 = 0;
+      for (size_t i = 0; i <= p2.size(); i++) {
+        size_t a = i == 0 ? 0 : p2[i - 1], b = i == p2.size() ? mb.lz77.size() : p2[i];
+        totalcost2 += auto_type_bits(mb.lz77, a, b, s);
+      }
+      if (totalcost2 < totalcost) points = p2;
+    }
+    mb.points = points;
+    for (size_t i = 0; i <= points.size(); i++) {  // AddLZ77BlockAutoType deflate.c:747-800
+      FinalBlock fb;
+      fb.lstart = i == 0 ? 0 : points[i - 1];
+      fb.lend = i == points.size() ? mb.lz77.size() : points[i];
+      uint32_t h[320];
+      mb.lz77.range_hist(fb.lstart, fb.lend, h);
+      fb.unc = stored_bits(mb.lz77.byte_range(fb.lstart, fb.lend));
+      fb.fixed = fixed_block_bits(h);
+      fb.dyn = dynamic_block_bits(h, nullptr, nullptr, s);
+      fb.expensive = (mb.lz77.size() < 1000) || ((double)fb.fixed <= (double)fb.dyn * 1.1);  // :760
+      if (fb.lstart == fb.lend) fb.expensive = false;
+      if (fb.expensive) {
+        size_t a = mb.lz77.pos[fb.lstart];
+        size_t b = a + mb.lz77.byte_range(fb.lstart, fb.lend);
+        fb.fixed_req = (int)fixed_req[m].size();
+        fixed_req[m].push_back({a - in_base, b - in_base, 2, 0});
+      }
+      mb.finals.push_back(fb);
+    }
+  });
+  double t4 = now_ms();
+  g_host_times.split += t4 - t3;
+
+  // ---- stage E: fixed-tree re-parses ----
+  {
+    std::vector<ParseRange> pr;
+    std::vector<size_t> base(nm, 0);
+    for (size_t m = 0; m < nm; m++) { base[m] = pr.size(); pr.insert(pr.end(), fixed_req[m].begin(), fixed_req[m].end()); }
+    if (!pr.empty()) {
+      ParseResult res;
+      eng.parse(pr, res);
+      for (size_t m = 0; m < nm; m++) {
+        M[m].fixedstores.resize(fixed_req[m].size());
+        for (size_t k = 0; k < fixed_req[m].size(); k++) {
+          size_t g = base[m] + k;
+          M[m].fixedstores[k].append(res.ll.data() + res.off[g], res.d.data() + res.off[g], res.size[g],
+                                     (size_t)pr[g].instart + in_base);
+          M[m].fixedstores[k].finalize();
+        }
+      }
+    }
+  }
+  double t5 = now_ms();
+  g_host_times.other += t5 - t4;
+
+  // ---- stage F: emission, one task per final block ----
+  std::vector<std::pair<size_t, size_t>> tasks;
+  for (size_t m = 0; m < nm; m++) {
+    M[m].pieces.resize(M[m].finals.size());
+    for (size_t i = 0; i < M[m].finals.size(); i++) tasks.push_back({m, i});
+  }
+  parallel_for(tasks.size(), [&](size_t t) {
+    Master& mb = M[tasks[t].first];
+    const size_t i = tasks[t].second;
+    FinalBlock& fb = mb.finals[i];
+    Piece& p = mb.pieces[i];
+    const bool final = final_last && tasks[t].first + 1 == nm && i + 1 == mb.finals.size();
+    if (fb.lstart == fb.lend) {  // deflate.c:763-768
+      p.bits.add_bits(final ? 1 : 0, 1);
+      p.bits.add_bits(1, 2);
+      p.bits.add_bits(0, 7);
+      p.bits.flush();
+      return;
+    }
+    uint64_t fixedcost = fb.fixed;
+    const Lz77Store* fst = nullptr;
+    if (fb.expensive) {
+      fst = &mb.fixedstores[fb.fixed_req];
+      uint32_t h[320];
+      fst->range_hist(0, fst->size(), h);
+      fixedcost = fixed_block_bits(h);  // deflate.c:779
+    }
+    if (fb.unc < fixedcost && fb.unc < fb.dyn) {  // deflate.c:783-785
+      p.stored = true;
+      p.instart = mb.lz77.pos[fb.lstart];
+      p.inend = p.instart + mb.lz77.byte_range(fb.lstart, fb.lend);
+      p.final = final;
+    } else if (fixedcost < fb.dyn) {
+      if (fb.expensive) emit_compressed_block(1, final, *fst, 0, fst->size(), p.bits);
+      else emit_compressed_block(1, final, mb.lz77, fb.lstart, fb.lend, p.bits);
+    } else {
+      emit_compressed_block(2, final, mb.lz77, fb.lstart, fb.lend, p.bits);
+    }
+  });
+  for (size_t m = 0; m < nm; m++)
+    for (auto& p : M[m].pieces) pieces.push_back(std::move(p));
+  g_host_times.emit += now_ms() - t5;
+  (void)in;
+}
+
+// ---------------------------------------------------------------------------------------------
+// splice: append pieces to a zopfli-style growing buffer (util.h:134-155 capacity rule)
+
+namespace {
+size_t pow2_ceil(size_t v) {
+  size_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+}  // namespace
+
+void append_bytes(const unsigned char* src, size_t n, unsigned char** out, size_t* outsize) {
+  if (n == 0) return;
+  size_t s = *outsize, ns = s + n;
+  size_t cap = s == 0 ? 0 : pow2_ceil(s), ncap = pow2_ceil(ns);
+  if (s == 0) {
+    *out = (unsigned char*)malloc(ncap);  // util.h:150: first append mallocs
+  } else if (ncap != cap) {
+    *out = (unsigned char*)realloc(*out, ncap);
+  }
+  if (!*out) { fprintf(stderr, "zopfli-b200: out of memory\n"); exit(EXIT_FAILURE); }
+  memcpy(*out + s, src, n);
+  *outsize = ns;
+}
+
+void splice_pieces(const std::vector<Piece>& pieces, const unsigned char* in, unsigned char* bp,
+                   unsigned char** out, size_t* outsize) {
+  // local bit accumulator seeded with the partially filled last byte
+  std::vector<unsigned char> buf;
+  uint64_t acc = 0;
+  int nacc = 0;
+  bool patch_last = false;
+  if (*bp != 0 && *outsize > 0) {
+    acc = (*out)[*outsize - 1];
+    nacc = *bp;
+    patch_last = true;
+  }
+  size_t total = 16;
+  for (auto& p : pieces) total += p.stored ? (p.inend - p.instart) + 5 * ((p.inend - p.instart) / 65535 + 2) : p.bits.bytes.size() + 1;
+  buf.reserve(total);
+  auto put = [&](uint32_t v, int n) {
+    acc |= (uint64_t)v << nacc;
+    nacc += n;
+    while (nacc >= 8) { buf.push_back((unsigned char)acc); acc >>= 8; nacc -= 8; }
+  };
+  for (auto& p : pieces) {
+    if (!p.stored) {
+      uint64_t nb = p.bits.nbits;
+      const std::vector<uint8_t>& by = p.bits.bytes;
+      size_t full = (size_t)(nb / 8);
+      if (nacc == 0) {
+        buf.insert(buf.end(), by.begin(), by.begin() + full);
+      } else {
+        for (size_t i = 0; i < full; i++) put(by[i], 8);
+      }
+      int rem = (int)(nb % 8);
+      if (rem) put(by[full] & ((1u << rem) - 1), rem);
+    } else {  // AddNonCompressedBlock deflate.c:625-663
+      size_t pos = p.instart;
+      for (;;) {
+        size_t bs = 65535;
+        if (pos + bs > p.inend) bs = p.inend - pos;
+        bool cur_final = pos + bs >= p.inend;
+        put((p.final && cur_final) ? 1 : 0, 1);
+        put(0, 2);
+        if (nacc > 0) { buf.push_back((unsigned char)acc); acc = 0; nacc = 0; }  // byte align
+        unsigned nlen = (~(unsigned)bs) & 0xffff;
+        buf.push_back((unsigned char)(bs % 256));
+        buf.push_back((unsigned char)((bs / 256) % 256));
+        buf.push_back((unsigned char)(nlen % 256));
+        buf.push_back((unsigned char)((nlen / 256) % 256));
+        buf.insert(buf.end(), in + pos, in + pos + bs);
+        if (cur_final) break;
+        pos += bs;
+      }
+    }
+  }
+  unsigned char newbp = (unsigned char)nacc;
+  if (nacc > 0) buf.push_back((unsigned char)acc);
+  size_t skip = 0;
+  if (patch_last && !buf.empty()) {
+    (*out)[*outsize - 1] = buf[0];
+    skip = 1;
+  }
+  append_bytes(buf.data() + skip, buf.size() - skip, out, outsize);
+  *bp = newbp;
+}
+
+}  // namespace zb

@@ -1,0 +1,502 @@
+// CUDA engine: device memory, launch sequencing and result transfer for the zopfli hot path.
+// Built for sm_100a only.  There is NO CPU fallback: any CUDA failure aborts with a message
+// (the reference's own error model is exit(), /root/reference/src/zopfli/squeeze.c:469-470).
+#include "engine.hpp"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <thread>
+
+#include "iterate.cuh"
+#include "kernels.cuh"
+
+namespace zb {
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      fprintf(stderr, "zopfli-b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_),      \
+              __FILE__, __LINE__, cudaGetErrorString(e_));                                    \
+      abort();                                                                                \
+    }                                                                                         \
+  } while (0)
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) CK(cudaFree(p));
+    size_t want = bytes + bytes / 8 + 256;
+    CK(cudaMalloc(&p, want));
+    cap = want;
+  }
+  template <typename T>
+  T* as() { return (T*)p; }
+};
+
+__global__ void k_test_block_bits(Batch b, const uint32_t* hist, uint64_t* out) {
+  __shared__ IterSmem s;
+  const uint32_t lane = threadIdx.x;
+  for (int i = lane; i < 320; i += 32) s.hist[i] = hist[i];
+  __syncwarp();
+  if (lane == 0) s.hist[256] = 1;
+  __syncwarp();
+  uint64_t r = warp_dynamic_bits(s, b.scratch, lane);
+  if (lane == 0) *out = r;
+}
+
+struct Timer {
+  cudaEvent_t a, b;
+  Timer() { CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); }
+};
+
+constexpr uint32_t kLogTabN = 1u << 21;
+
+}  // namespace
+
+struct Engine::Impl {
+  std::mutex mu;
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  // input
+  DevBuf in_buf, same_buf, tile_first, next_tile;
+  const uint8_t* d_in = nullptr;
+  uint64_t insize = 0;
+  // batch arenas
+  DevBuf segs, keywork, poswork, order, hv, hv2, idx1, idx2, rank1, rank2, bkt1, bkt2, ld, mlen, runs,
+      ovf, la, path, st[4], jobs, scratch, out_ll, out_d, counters, logtab, misc;
+  uint32_t ovf_cap = 1u << 22;
+  std::thread log_thread;
+  std::vector<double> log_host;
+  bool log_ready = false;
+  EngineStats st_acc;
+  cudaEvent_t ev[2];
+  uint8_t* pinned = nullptr;
+  size_t pinned_cap = 0;
+
+  Impl() {
+    memset(&st_acc, 0, sizeof(st_acc));
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      fprintf(stderr, "zopfli-b200: no CUDA device available (%s). This library has no CPU path.\n",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+      abort();
+    }
+    const char* dv = getenv("ZOPFLI_B200_DEVICE");
+    if (dv) dev = atoi(dv);
+    else {
+      const char* lr = getenv("LOCAL_RANK");
+      if (lr) dev = atoi(lr) % n;
+    }
+    CK(cudaSetDevice(dev));
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev[0]));
+    CK(cudaEventCreate(&ev[1]));
+    CK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+    // L[n] = log(n) * kInvLog2 with the HOST libm, exactly the two operations of tree.c:79,85
+    log_thread = std::thread([this]() {
+      log_host.resize(kLogTabN);
+      static const double kInvLog2 = 1.4426950408889;
+      log_host[0] = 0.0;
+      for (uint32_t i = 1; i < kLogTabN; i++) {
+        volatile double l = log((double)i);
+        log_host[i] = l * kInvLog2;
+      }
+    });
+  }
+
+  void ensure_log() {
+    if (log_ready) return;
+    log_thread.join();
+    logtab.ensure(kLogTabN * sizeof(double));
+    CK(cudaMemcpyAsync(logtab.p, log_host.data(), kLogTabN * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CK(cudaStreamSynchronize(stream));
+    log_ready = true;
+  }
+
+  void tic() { CK(cudaEventRecord(ev[0], stream)); }
+  void toc(double& acc) {
+    CK(cudaEventRecord(ev[1], stream));
+    CK(cudaEventSynchronize(ev[1]));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+    acc += ms;
+  }
+
+  void compute_same() {
+    if (insize == 0) return;
+    uint32_t ntiles = (uint32_t)((insize + kSameTile - 1) / kSameTile);
+    same_buf.ensure(insize * sizeof(uint16_t) + 64);
+    tile_first.ensure(ntiles * sizeof(uint32_t));
+    next_tile.ensure(ntiles * sizeof(uint32_t));
+    tic();
+    k_same_tiles<<<ntiles, 256, 0, stream>>>(d_in, insize, tile_first.as<uint32_t>());
+    k_same_next_tile<<<1, 1024, 0, stream>>>(tile_first.as<uint32_t>(), ntiles, next_tile.as<uint32_t>());
+    k_same_fill<<<ntiles, 256, 0, stream>>>(d_in, insize, tile_first.as<uint32_t>(), next_tile.as<uint32_t>(),
+                                            ntiles, same_buf.as<uint16_t>());
+    CK(cudaGetLastError());
+    toc(st_acc.ms_same);
+    st_acc.launches += 3;
+  }
+
+  struct Layout {
+    std::vector<SegDesc> segs;
+    std::vector<KeyWork> kw;
+    std::vector<PosWork> pw;
+    std::vector<uint32_t> order;
+    uint64_t nkeys = 0, npos = 0;
+    bool any_parse = false;
+  };
+
+  void build_layout(const std::vector<ParseRange>& r, Layout& L) {
+    L.segs.resize(r.size());
+    for (size_t i = 0; i < r.size(); i++) {
+      SegDesc& s = L.segs[i];
+      if (r[i].inend < r[i].instart || r[i].inend > insize || r[i].inend - r[i].instart > 0x7fff0000ull) {
+        fprintf(stderr, "zopfli-b200: bad parse range [%llu,%llu) for input of %llu bytes\n",
+                (unsigned long long)r[i].instart, (unsigned long long)r[i].inend, (unsigned long long)insize);
+        abort();
+      }
+      s.instart = r[i].instart;
+      s.inend = r[i].inend;
+      s.winstart = s.instart > (uint64_t)kWindow ? s.instart - kWindow : 0;  // squeeze.c:229-230
+      s.key_off = L.nkeys;
+      s.pos_off = L.npos;
+      s.nkeys = (uint32_t)(s.inend - s.winstart);
+      s.npos = (uint32_t)(s.inend - s.instart);
+      s.mode = r[i].mode;
+      s.numiterations = r[i].numiterations;
+      if (s.npos == 0) s.nkeys = 0;
+      L.nkeys += s.nkeys;
+      L.npos += s.npos;
+      if (s.mode != 0) L.any_parse = true;
+      for (uint32_t f = 0; f < s.nkeys; f += kKeyChunk) L.kw.push_back({(uint32_t)i, f});
+      for (uint32_t f = 0; f < s.npos; f += kMatchPosPerCta) L.pw.push_back({(uint32_t)i, f});
+    }
+    L.order.resize(r.size());
+    for (size_t i = 0; i < r.size(); i++) L.order[i] = (uint32_t)i;
+    std::stable_sort(L.order.begin(), L.order.end(), [&](uint32_t a, uint32_t b) {
+      uint64_t wa = (uint64_t)L.segs[a].npos * (L.segs[a].mode == 1 ? L.segs[a].numiterations : 1);
+      uint64_t wb = (uint64_t)L.segs[b].npos * (L.segs[b].mode == 1 ? L.segs[b].numiterations : 1);
+      return wa > wb;
+    });
+  }
+
+  template <typename T>
+  void upload(DevBuf& d, const std::vector<T>& v) {
+    d.ensure(v.size() * sizeof(T) + 16);
+    if (!v.empty()) CK(cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+  }
+
+  // runs everything up to and including the match table; returns the Batch
+  Batch prepare(const Layout& L) {
+    const size_t ns = L.segs.size();
+    upload(segs, L.segs);
+    upload(keywork, L.kw);
+    upload(poswork, L.pw);
+    upload(order, L.order);
+    hv.ensure(L.nkeys * 2 + 64);
+    hv2.ensure(L.nkeys * 2 + 64);
+    idx1.ensure(L.nkeys * 4 + 64);
+    idx2.ensure(L.nkeys * 4 + 64);
+    rank1.ensure(L.nkeys * 4 + 64);
+    rank2.ensure(L.nkeys * 4 + 64);
+    bkt1.ensure(ns * 32769 * 4 + 64);
+    bkt2.ensure(ns * 32769 * 4 + 64);
+    ld.ensure(L.npos * 4 + 64);
+    for (int i = 0; i < 4; i++) st[i].ensure(L.npos * 2 + 64);
+    jobs.ensure(ns * sizeof(JobState) + 64);
+    out_ll.ensure(L.npos * 2 + 64);
+    out_d.ensure(L.npos * 2 + 64);
+    counters.ensure(256);
+    scratch.ensure(std::max<size_t>(ns, 1) * kIterScratch);
+    if (L.any_parse) {
+      mlen.ensure(L.npos * 2 + 64);
+      runs.ensure(L.npos * kRunSlots * 4 + 64);
+      ovf.ensure((size_t)ovf_cap * 4);
+      la.ensure((L.npos + ns) * 2 + 64);
+      path.ensure((L.npos + ns) * 2 + 64);
+      ensure_log();
+    }
+    Batch b;
+    memset(&b, 0, sizeof(b));
+    b.in = d_in;
+    b.insize = insize;
+    b.same_g = same_buf.as<uint16_t>();
+    b.segs = segs.as<SegDesc>();
+    b.nsegs = (int)ns;
+    b.hv = hv.as<uint16_t>();
+    b.hv2 = hv2.as<uint16_t>();
+    b.idx1 = idx1.as<uint32_t>();
+    b.idx2 = idx2.as<uint32_t>();
+    b.rank1 = rank1.as<uint32_t>();
+    b.rank2 = rank2.as<uint32_t>();
+    b.bkt1 = bkt1.as<uint32_t>();
+    b.bkt2 = bkt2.as<uint32_t>();
+    b.ld = ld.as<uint32_t>();
+    b.mlen = mlen.as<uint16_t>();
+    b.runs = runs.as<uint32_t>();
+    b.ovf = ovf.as<uint32_t>();
+    b.ovf_used = counters.as<uint32_t>();
+    b.ovf_cap = ovf_cap;
+    b.la = la.as<uint16_t>();
+    b.path = path.as<uint16_t>();
+    b.st_ll[0] = st[0].as<uint16_t>();
+    b.st_d[0] = st[1].as<uint16_t>();
+    b.st_ll[1] = st[2].as<uint16_t>();
+    b.st_d[1] = st[3].as<uint16_t>();
+    b.st_ll[2] = nullptr;
+    b.st_d[2] = nullptr;
+    b.jobs = jobs.as<JobState>();
+    b.scratch = scratch.as<uint8_t>();
+    b.logtab = logtab.as<double>();
+    b.logtab_n = kLogTabN;
+    b.out_ll = out_ll.as<uint16_t>();
+    b.out_d = out_d.as<uint16_t>();
+    b.out_used = counters.as<uint32_t>() + 1;
+
+    CK(cudaMemsetAsync(bkt1.p, 0, ns * 32769 * 4, stream));
+    CK(cudaMemsetAsync(bkt2.p, 0, ns * 32769 * 4, stream));
+    CK(cudaMemsetAsync(counters.p, 0, 256, stream));
+    CK(cudaMemsetAsync(jobs.p, 0, ns * sizeof(JobState), stream));
+    if (L.nkeys) {
+      tic();
+      k_keys<<<(unsigned)L.kw.size(), 256, 0, stream>>>(b, keywork.as<KeyWork>());
+      CK(cudaGetLastError());
+      toc(st_acc.ms_keys);
+      tic();
+      k_bucket_scan<<<(unsigned)(2 * ns), 1024, 0, stream>>>(b);
+      CK(cudaGetLastError());
+      toc(st_acc.ms_scan);
+      tic();
+      k_scatter<<<(unsigned)(2 * ns), 32, 32768 * 4, stream>>>(b);
+      CK(cudaGetLastError());
+      toc(st_acc.ms_scatter);
+      tic();
+      k_match<<<(unsigned)L.pw.size(), kMatchWarps * 32, 0, stream>>>(b, poswork.as<PosWork>());
+      CK(cudaGetLastError());
+      toc(st_acc.ms_match);
+      st_acc.launches += 4;
+      st_acc.match_positions += L.npos;
+    }
+    return b;
+  }
+};
+
+Engine::Engine() : p_(new Impl) {}
+
+Engine& Engine::get() {
+  static Engine* e = new Engine;  // intentionally leaked: CUDA teardown order at exit is undefined
+  return *e;
+}
+
+int Engine::device() const { return p_->dev; }
+
+void Engine::set_stream(void* s) {
+  std::lock_guard<std::mutex> g(p_->mu);
+  CK(cudaSetDevice(p_->dev));
+  if (s) { p_->stream = (cudaStream_t)s; p_->own_stream = false; }
+}
+
+EngineStats Engine::stats() {
+  std::lock_guard<std::mutex> g(p_->mu);
+  return p_->st_acc;
+}
+void Engine::reset_stats() {
+  std::lock_guard<std::mutex> g(p_->mu);
+  memset(&p_->st_acc, 0, sizeof(p_->st_acc));
+}
+
+void Engine::set_input_host(const uint8_t* in, size_t insize) {
+  std::lock_guard<std::mutex> g(p_->mu);
+  Impl& m = *p_;
+  CK(cudaSetDevice(m.dev));
+  m.in_buf.ensure(insize + 64);
+  m.tic();
+  CK(cudaMemsetAsync((uint8_t*)m.in_buf.p + insize, 0, 64, m.stream));
+  if (insize) CK(cudaMemcpyAsync(m.in_buf.p, in, insize, cudaMemcpyHostToDevice, m.stream));
+  m.toc(m.st_acc.ms_h2d);
+  m.st_acc.h2d_bytes += insize;
+  m.d_in = m.in_buf.as<uint8_t>();
+  m.insize = insize;
+  m.compute_same();
+}
+
+void Engine::set_input_device(const uint8_t* dev_in, size_t insize) {
+  std::lock_guard<std::mutex> g(p_->mu);
+  Impl& m = *p_;
+  CK(cudaSetDevice(m.dev));
+  if (((uintptr_t)dev_in & 15) != 0) {
+    fprintf(stderr, "zopfli-b200: device input must be 16-byte aligned\n");
+    abort();
+  }
+  m.d_in = dev_in;
+  m.insize = insize;
+  m.compute_same();
+}
+
+void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out) {
+  std::lock_guard<std::mutex> g(p_->mu);
+  Impl& m = *p_;
+  CK(cudaSetDevice(m.dev));
+  const size_t ns = ranges.size();
+  out.off.assign(ns, 0);
+  out.size.assign(ns, 0);
+  out.cost.assign(ns, 0);
+  out.ll.clear();
+  out.d.clear();
+  if (ns == 0) return;
+  Impl::Layout L;
+  m.build_layout(ranges, L);
+  std::vector<JobState> js(ns);
+  uint32_t counters[2] = {0, 0};
+  for (int attempt = 0;; attempt++) {
+    Batch b = m.prepare(L);
+    m.tic();
+    k_greedy<<<(unsigned)ns, 32, 0, m.stream>>>(b, 0);
+    CK(cudaGetLastError());
+    m.toc(m.st_acc.ms_greedy);
+    m.st_acc.launches++;
+    if (L.any_parse) {
+      m.tic();
+      k_iterate<<<(unsigned)ns, 32, 0, m.stream>>>(b, m.order.as<uint32_t>());
+      CK(cudaGetLastError());
+      m.toc(m.st_acc.ms_iterate);
+      m.st_acc.launches++;
+    }
+    m.tic();
+    k_pack<<<(unsigned)ns, 256, 0, m.stream>>>(b, L.any_parse ? 0 : 1);
+    CK(cudaGetLastError());
+    m.toc(m.st_acc.ms_pack);
+    m.st_acc.launches++;
+    m.tic();
+    CK(cudaMemcpyAsync(js.data(), m.jobs.p, ns * sizeof(JobState), cudaMemcpyDeviceToHost, m.stream));
+    CK(cudaMemcpyAsync(counters, m.counters.p, sizeof(counters), cudaMemcpyDeviceToHost, m.stream));
+    CK(cudaStreamSynchronize(m.stream));
+    if (L.any_parse && counters[0] > m.ovf_cap) {  // run-list overflow arena too small: grow, redo
+      m.ovf_cap = counters[0] + counters[0] / 4 + 1024;
+      if (attempt > 2) { fprintf(stderr, "zopfli-b200: overflow arena did not converge\n"); abort(); }
+      continue;
+    }
+    const uint32_t total = counters[1];
+    out.ll.resize(total);
+    out.d.resize(total);
+    if (total) {
+      CK(cudaMemcpyAsync(out.ll.data(), m.out_ll.p, (size_t)total * 2, cudaMemcpyDeviceToHost, m.stream));
+      CK(cudaMemcpyAsync(out.d.data(), m.out_d.p, (size_t)total * 2, cudaMemcpyDeviceToHost, m.stream));
+    }
+    m.toc(m.st_acc.ms_d2h);
+    m.st_acc.d2h_bytes += (uint64_t)total * 4 + ns * sizeof(JobState);
+    break;
+  }
+  for (size_t i = 0; i < ns; i++) {
+    const bool greedy_only = !L.any_parse;
+    out.off[i] = js[i].out_off;
+    out.size[i] = greedy_only ? js[i].greedy_size : js[i].best_size;
+    out.cost[i] = js[i].best_cost;
+    if (!greedy_only && ranges[i].mode == 0) {
+      fprintf(stderr, "zopfli-b200: greedy and optimal ranges cannot share a batch\n");
+      abort();
+    }
+    if (js[i].flags & 1) {
+      fprintf(stderr, "zopfli-b200: symbol count beyond the %u-entry log table in block %zu "
+              "(iteration %u); not supported yet\n", kLogTabN, i, js[i].iters_done);
+      abort();
+    }
+    if (js[i].flags & 2) { fprintf(stderr, "zopfli-b200: corrupted length chain in block %zu\n", i); abort(); }
+    if (ranges[i].mode == 1) {
+      m.st_acc.iterate_positions += L.segs[i].npos;
+      m.st_acc.iterate_steps += (uint64_t)L.segs[i].npos * ranges[i].numiterations;
+    }
+  }
+}
+
+void Engine::match_table(uint64_t instart, uint64_t inend, std::vector<uint16_t>& len,
+                         std::vector<uint16_t>& dist, std::vector<uint16_t>& sublen,
+                         std::vector<uint16_t>& same, std::vector<uint16_t>& hvv, std::vector<uint16_t>& hv2v) {
+  std::lock_guard<std::mutex> g(p_->mu);
+  Impl& m = *p_;
+  CK(cudaSetDevice(m.dev));
+  std::vector<ParseRange> r{{instart, inend, 1, 1}};
+  Impl::Layout L;
+  m.build_layout(r, L);
+  std::vector<uint32_t> h_ld, h_runs, h_ovf;
+  std::vector<uint16_t> h_mlen, h_hv, h_hv2, h_same;
+  const size_t n = (size_t)(inend - instart);
+  for (int attempt = 0;; attempt++) {
+    m.prepare(L);
+    uint32_t used = 0;
+    CK(cudaMemcpyAsync(&used, m.counters.p, 4, cudaMemcpyDeviceToHost, m.stream));
+    CK(cudaStreamSynchronize(m.stream));
+    if (used > m.ovf_cap) { m.ovf_cap = used + used / 4 + 1024; if (attempt > 2) abort(); continue; }
+    h_ld.resize(n); h_runs.resize(n * kRunSlots); h_mlen.resize(n); h_ovf.resize(used + 1);
+    h_hv.resize(L.nkeys); h_hv2.resize(L.nkeys); h_same.resize(n);
+    if (n) {
+      CK(cudaMemcpy(h_ld.data(), m.ld.p, n * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h_runs.data(), m.runs.p, n * kRunSlots * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h_mlen.data(), m.mlen.p, n * 2, cudaMemcpyDeviceToHost));
+      if (used) CK(cudaMemcpy(h_ovf.data(), m.ovf.p, (size_t)used * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h_hv.data(), m.hv.p, L.nkeys * 2, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h_hv2.data(), m.hv2.p, L.nkeys * 2, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h_same.data(), m.same_buf.as<uint16_t>() + instart, n * 2, cudaMemcpyDeviceToHost));
+    }
+    break;
+  }
+  len.assign(n, 0); dist.assign(n, 0); sublen.assign(n * 259, 0); same.assign(n, 0); hvv.assign(n, 0); hv2v.assign(n, 0);
+  const size_t woff = (size_t)(instart - L.segs[0].winstart);
+  for (size_t j = 0; j < n; j++) {
+    len[j] = (uint16_t)(h_ld[j] >> 16);
+    dist[j] = (uint16_t)(h_ld[j] & 0xffff);
+    uint64_t clip = inend - 1 - (instart + j);
+    same[j] = (uint16_t)std::min<uint64_t>(h_same[j], clip);
+    hvv[j] = h_hv[woff + j];
+    hv2v[j] = h_hv2[woff + j];
+    uint32_t prev = 2;
+    auto put = [&](uint32_t e) {
+      for (uint32_t k = std::max<uint32_t>(prev + 1, 3); k <= run_len(e); k++) sublen[j * 259 + k] = (uint16_t)run_dist(e);
+      prev = run_len(e);
+    };
+    if (h_mlen[j] >= 3) {
+      for (int r2 = 0; r2 < kRunSlots; r2++) {
+        uint32_t e = h_runs[j * kRunSlots + r2];
+        if (r2 == kRunSlots - 1 && (e & kOverflowBit)) {
+          uint32_t off = e & ~kOverflowBit, cnt = h_ovf[off];
+          for (uint32_t t = 0; t < cnt; t++) put(h_ovf[off + 1 + t]);
+        } else if (run_len(e)) put(e);
+      }
+    }
+  }
+}
+
+uint64_t Engine::device_block_bits(const uint32_t* hist320) {
+  std::lock_guard<std::mutex> g(p_->mu);
+  Impl& m = *p_;
+  CK(cudaSetDevice(m.dev));
+  m.scratch.ensure(kIterScratch);
+  m.misc.ensure(320 * 4 + 64);
+  Batch b;
+  memset(&b, 0, sizeof(b));
+  b.scratch = m.scratch.as<uint8_t>();
+  CK(cudaMemcpyAsync(m.misc.p, hist320, 320 * 4, cudaMemcpyHostToDevice, m.stream));
+  uint64_t* dout = (uint64_t*)((uint8_t*)m.misc.p + 320 * 4 + 16);
+  k_test_block_bits<<<1, 32, 0, m.stream>>>(b, m.misc.as<uint32_t>(), dout);
+  CK(cudaGetLastError());
+  uint64_t r = 0;
+  CK(cudaMemcpyAsync(&r, dout, 8, cudaMemcpyDeviceToHost, m.stream));
+  CK(cudaStreamSynchronize(m.stream));
+  return r;
+}
+
+}  // namespace zb

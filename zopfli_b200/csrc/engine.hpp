@@ -1,0 +1,61 @@
+// Host-visible interface of the CUDA engine (no CUDA types leak out of engine.cu).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <vector>
+
+namespace zb {
+
+struct ParseRange {
+  uint64_t instart, inend;
+  int mode;           // 0 greedy parse only (ZopfliLZ77Greedy), 1 optimal parse (ZopfliLZ77Optimal),
+                      // 2 optimal parse with fixed-tree costs (ZopfliLZ77OptimalFixed)
+  int numiterations;  // mode 1 only
+};
+
+struct ParseResult {        // symbols of range i: [off[i], off[i]+size[i]) in ll / d
+  std::vector<uint32_t> off, size;
+  std::vector<uint16_t> ll, d;
+  std::vector<uint64_t> cost;  // mode 1: exact dynamic-block bit cost of the returned parse
+};
+
+struct EngineStats {  // accumulated since the last reset; times from CUDA events on the engine stream
+  double ms_same, ms_keys, ms_scan, ms_scatter, ms_match, ms_greedy, ms_iterate, ms_pack, ms_h2d, ms_d2h;
+  uint64_t launches;
+  uint64_t match_positions, iterate_positions, iterate_steps;  // steps = positions x iterations
+  uint64_t h2d_bytes, d2h_bytes;
+};
+
+class Engine {
+ public:
+  // one engine per process and device; thread-safe (calls are serialised)
+  static Engine& get();
+
+  // Input residency. set_input_host copies to the device (inside the caller's timed region);
+  // set_input_device adopts an existing device buffer that must stay valid and be readable
+  // 16 bytes past insize (e.g. a padded torch tensor).
+  void set_input_host(const uint8_t* in, size_t insize);
+  void set_input_device(const uint8_t* dev_in, size_t insize);
+
+  void parse(const std::vector<ParseRange>& ranges, ParseResult& out);
+
+  // test seam: raw match table of one range (length, dist, expanded sublen[259] per position)
+  void match_table(uint64_t instart, uint64_t inend, std::vector<uint16_t>& len,
+                   std::vector<uint16_t>& dist, std::vector<uint16_t>& sublen,
+                   std::vector<uint16_t>& same, std::vector<uint16_t>& hv, std::vector<uint16_t>& hv2);
+  // test seam: device-side exact dynamic block size of a 320-bin histogram
+  uint64_t device_block_bits(const uint32_t* hist320);
+
+  void set_stream(void* cuda_stream);  // optional: run on the caller's stream
+  EngineStats stats();
+  void reset_stats();
+  int device() const;
+
+ private:
+  Engine();
+  struct Impl;
+  Impl* p_;
+};
+
+}  // namespace zb

@@ -1,0 +1,466 @@
+// k_iterate: the whole ZopfliLZ77Optimal loop for one deflate block in one persistent warp
+// (/root/reference/src/zopfli/squeeze.c:446-526; fixed-tree variant :528-560).
+//
+//   per iteration:  cost model constants (GetCostModelMinCost squeeze.c:163-198)
+//                   forward DP          (GetBestLengths squeeze.c:217-309)   push form, costs in a
+//                                        512-entry shared-memory ring, fp64 add / fp32 store
+//                   trace-back          (TraceBackwards squeeze.c:317-336)   shared-memory windows
+//                   follow + histogram  (FollowPath squeeze.c:338-389)       table lookups, 32 wide
+//                   exact block size    (ZopfliCalculateBlockSize deflate.c:584-608)
+//                   statistics          (squeeze.c:496-518, tree.c:71-94, RNG squeeze.c:80-107)
+//
+// fp discipline: every cost is (double)(lbits+dbits) + ll + d, then + (double)costs[j], compared
+// in double against (double)float, stored rounded to float -- the reference's exact sequence.
+// The file is compiled with -fmad=false; there is no multiply on the path anyway.
+// log() is not evaluated on the device: entropies come from a table L[n] = log(n)*1.4426950408889
+// filled by the host's libm, so they are bit-identical to what the reference computes on this box.
+#pragma once
+#include "kernels.cuh"
+
+namespace zb {
+
+struct IterSmem {
+  double llcost[kNumLL];   // ll_symbols
+  double dcost[kNumD];     // d_symbols
+  double lencost[260];     // llcost[length_symbol(k)]
+  float ringc[512];
+  uint16_t ringl[512];
+  uint32_t stage[2][32 * kRunSlots];  // run lists of 2 x 32 positions
+  uint32_t hist[320];
+  uint32_t stats[320], last[320], bests[320];
+  uint32_t cnt2[320];      // RLE-smoothed copies (ll: [0,288), d: [288,320))
+  uint8_t len[2][320];     // code lengths: set 0 plain, set 1 smoothed
+  uint16_t win[1024];
+};
+
+__device__ __forceinline__ double warp_min_first(double v, int& idx) {
+  // minimum with the smallest index among equals (sequential strict-< scan order)
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, v, d);
+    int oi = __shfl_xor_sync(0xffffffffu, idx, d);
+    if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  return v;
+}
+
+// ZopfliCalculateEntropy tree.c:71-94 over n counts (n = 288 or 32). Returns false if a count or
+// the sum falls outside the host-provided log table.
+__device__ bool warp_entropy(const uint32_t* cnt, int n, double* out, const Batch& b, uint32_t lane) {
+  uint32_t sum = 0;
+  for (int i = lane; i < n; i += 32) sum += cnt[i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  uint32_t si = sum == 0 ? (uint32_t)n : sum;
+  bool ok = si < b.logtab_n;
+  double log2sum = ok ? b.logtab[si] : 0.0;
+  for (int i = lane; i < n; i += 32) {
+    uint32_t c = cnt[i];
+    double v = log2sum;
+    if (c) {
+      if (c < b.logtab_n) v = log2sum - b.logtab[c];
+      else ok = false;
+    }
+    if (v < 0 && v > -1e-5) v = 0;  // tree.c:91
+    out[i] = v;
+  }
+  return __all_sync(0xffffffffu, ok);
+}
+
+// exact dynamic block size from s.hist (hist[256] already 1): deflate.c:569-608.
+__device__ uint64_t warp_dynamic_bits(IterSmem& s, uint8_t* scratch, uint32_t lane) {
+  // four length-limited code constructions side by side: lanes 0..3 run the same instruction
+  // stream on (ll plain, d plain, ll smoothed, d smoothed)
+  if (lane < 4) {
+    const bool isd = lane & 1, smooth = lane >= 2;
+    const int n = isd ? kNumD : kNumLL;
+    const uint32_t* src = s.hist + (isd ? 288 : 0);
+    uint32_t* c2 = s.cnt2 + (isd ? 288 : 0);
+    PmBig* pb = (PmBig*)(scratch + (size_t)lane * (kIterScratch / 4));
+    if (smooth) {
+      for (int i = 0; i < n; i++) c2[i] = src[i];
+      optimize_for_rle(n, c2, pb->good);
+      src = c2;
+    }
+    uint8_t* out = s.len[smooth ? 1 : 0] + (isd ? 288 : 0);
+    length_limited<kNumLL, 15>(src, n, 15, out, pb->pm);
+    if (isd) patch_distance_codes(out);
+  }
+  __syncwarp();
+  uint32_t tsz = 0xffffffffu;
+  if (lane < 16) {
+    const uint8_t* l = s.len[lane >> 3];
+    tsz = encode_tree_size(l, l + 288, (lane & 1) != 0, (lane & 2) != 0, (lane & 4) != 0);
+  }
+  // min over lanes 0..7 and 8..15 (deflate.c:277-290)
+#pragma unroll
+  for (int d = 4; d > 0; d >>= 1) {
+    uint32_t o = __shfl_xor_sync(0xffffffffu, tsz, d);
+    tsz = o < tsz ? o : tsz;
+  }
+  const uint32_t tree0 = __shfl_sync(0xffffffffu, tsz, 0), tree1 = __shfl_sync(0xffffffffu, tsz, 8);
+  // symbol bits of both length sets (deflate.c:379-401), all lanes
+  uint64_t sb0 = 0, sb1 = 0;
+  for (int i = lane; i < 320; i += 32) {
+    uint32_t c = s.hist[i];
+    int extra;
+    bool use;
+    if (i < 288) { use = i < 256 || (i >= 257 && i < 286); extra = i >= 257 ? length_symbol_extra_bits(i) : 0; }
+    else { use = (i - 288) < 30; extra = dist_symbol_extra_bits(i - 288); }
+    if (use) {
+      sb0 += (uint64_t)(s.len[0][i] + extra) * c;
+      sb1 += (uint64_t)(s.len[1][i] + extra) * c;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    sb0 += __shfl_xor_sync(0xffffffffu, sb0, d);
+    sb1 += __shfl_xor_sync(0xffffffffu, sb1, d);
+  }
+  const uint64_t size0 = tree0 + sb0 + s.len[0][256];
+  const uint64_t size1 = tree1 + sb1 + s.len[1][256];
+  return 3 + (size1 < size0 ? size1 : size0);  // deflate.c:553-559
+}
+
+__device__ __forceinline__ uint32_t first_dist_of_symbol(int sd) {  // squeeze.c:176-179 table
+  return sd < 4 ? (uint32_t)sd + 1 : 1u + ((2u + (uint32_t)(sd & 1)) << (sd / 2 - 1));
+}
+
+__global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restrict__ order) {
+  __shared__ IterSmem s;
+  const uint32_t seg = order[blockIdx.x], lane = threadIdx.x;
+  const SegDesc sd = b.segs[seg];
+  if (sd.mode == 0) return;
+  JobState* js = &b.jobs[seg];
+  const uint32_t nb = sd.npos;
+  if (nb == 0) {
+    if (lane == 0) { js->best_size = 0; js->best_buf = 0; js->best_cost = 0; js->iters_done = 0; }
+    return;
+  }
+  uint16_t* la = b.la + sd.pos_off + seg;
+  uint16_t* path = b.path + sd.pos_off + seg;
+  const uint8_t* in = b.in + sd.instart;
+  const uint16_t* sameg = b.same_g + sd.instart;
+  const uint16_t* mlen = b.mlen + sd.pos_off;
+  const uint4* runs4 = (const uint4*)(b.runs + sd.pos_off * kRunSlots);
+  uint8_t* scratch = b.scratch + (size_t)seg * kIterScratch;
+  const bool fixed = sd.mode == 2;
+  int curbuf = 0, bestbuf = 1;
+  uint32_t flags = 0;
+
+  // ---- initial statistics: greedy parse (squeeze.c:481-482) or the fixed tree (:125-140) ----
+  if (!fixed) {
+    for (int i = lane; i < 320; i += 32) s.stats[i] = 0;
+    __syncwarp();
+    const uint32_t gs = js->greedy_size;
+    const uint16_t* gl = b.st_ll[0] + sd.pos_off;
+    const uint16_t* gd = b.st_d[0] + sd.pos_off;
+    for (uint32_t t = lane; t < gs; t += 32) {
+      uint32_t l = gl[t], d = gd[t];
+      if (d == 0) atomicAdd(&s.stats[l], 1u);
+      else { atomicAdd(&s.stats[length_symbol((int)l)], 1u); atomicAdd(&s.stats[288 + dist_symbol((int)d)], 1u); }
+    }
+    __syncwarp();
+    if (lane == 0) s.stats[256] = 1;  // squeeze.c:409
+    __syncwarp();
+    bool ok = warp_entropy(s.stats, kNumLL, s.llcost, b, lane);
+    ok &= warp_entropy(s.stats + 288, kNumD, s.dcost, b, lane);
+    if (!ok) flags |= 1;
+  } else {
+    for (int i = lane; i < kNumLL; i += 32) s.llcost[i] = (double)fixed_ll_length(i);
+    if (lane < kNumD) s.dcost[lane] = 5.0;
+  }
+  __syncwarp();
+
+  uint64_t bestcost = ~(uint64_t)0, lastcost = 0;
+  uint32_t ran_w = 1, ran_z = 2;  // squeeze.c:85-88
+  int lastrandomstep = -1;
+  uint32_t best_size = 0;
+  const int niter = fixed ? 1 : sd.numiterations;
+  int it = 0;
+
+  for (; it < niter && !(flags & 1); it++) {
+    // ------------------------------------------------------------------ model constants
+    for (int k = lane; k < 260; k += 32) s.lencost[k] = k >= 3 && k <= 258 ? s.llcost[length_symbol(k)] : 0.0;
+    __syncwarp();
+    double mincost;
+    {
+      double bv = 1e30; int bi = 0x7fffffff;
+      for (int k = 3 + (int)lane; k < 259; k += 32) {  // squeeze.c:181-187, dist 1
+        double c = (double)(length_extra_bits(k) + 0) + s.lencost[k] + s.dcost[0];
+        if (c < bv) { bv = c; bi = k; }
+      }
+      if (!(bv < 1e30)) bi = 0x7fffffff;
+      warp_min_first(bv, bi);
+      bi = __shfl_sync(0xffffffffu, bi, 0);
+      const int bestlength = bi == 0x7fffffff ? 0 : bi;
+      double dv = 1e30; int di = 0x7fffffff;
+      if (lane < 30) {  // squeeze.c:190-196, length 3
+        double c = (double)(0 + dist_symbol_extra_bits((int)lane)) + s.lencost[3] + s.dcost[lane];
+        if (c < dv) { dv = c; di = (int)lane; }
+      }
+      warp_min_first(dv, di);
+      di = __shfl_sync(0xffffffffu, di, 0);
+      // squeeze.c:198 costmodel(bestlength, bestdist); bestlength/bestdist stay 0 if nothing
+      // was below 1e30 (not reachable with finite entropies)
+      const int bl = bestlength, dsym = di == 0x7fffffff ? 0 : di;
+      mincost = (double)(length_extra_bits(bl) + dist_symbol_extra_bits(dsym)) + s.lencost[bl < 3 ? 3 : bl] + s.dcost[dsym];
+      (void)first_dist_of_symbol;
+    }
+    const double cost258 = (double)(0 + 0) + s.lencost[258] + s.dcost[0];  // costmodel(258, 1)
+
+    // ------------------------------------------------------------------ forward DP
+    for (int t = lane; t < 512; t += 32) { s.ringc[t] = (float)1e30; s.ringl[t] = 0; }
+    __syncwarp();
+    if (lane == 0) s.ringc[0] = 0.f;
+    __syncwarp();
+    {
+      uint32_t skip_left = 0;
+      bool just_finished = false;
+      // lane-distributed per-position scalars for the current group of 32 positions
+      uint32_t g_mlen = 0, g_byte = 0, g_same = 0;
+      auto load_group_scalars = [&](uint32_t j0, uint32_t& m, uint32_t& by, uint32_t& sm) {
+        uint32_t p = j0 + lane;
+        if (p < nb) {
+          m = mlen[p];
+          by = in[p];
+          uint32_t sg = sameg[p];
+          uint32_t clip = nb - 1 - p;
+          sm = sg > clip ? clip : sg;
+        } else { m = 0; by = 0; sm = 0; }
+      };
+      auto load_group_runs = [&](uint32_t j0, int bufi) {
+        uint32_t p = j0 + lane;
+        uint4 a = make_uint4(0, 0, 0, 0), c = a;
+        if (p < nb) { a = runs4[(uint64_t)p * 2]; c = runs4[(uint64_t)p * 2 + 1]; }
+        uint4* dst = (uint4*)&s.stage[bufi][lane * kRunSlots];
+        dst[0] = a; dst[1] = c;
+      };
+      uint32_t n_mlen, n_byte, n_same;
+      load_group_scalars(0, n_mlen, n_byte, n_same);
+      load_group_runs(0, 0);
+      __syncwarp();
+      for (uint32_t j = 0; j < nb; j++) {
+        const uint32_t jl = j & 31;
+        if (jl == 0) {
+          g_mlen = n_mlen; g_byte = n_byte; g_same = n_same;
+          load_group_scalars(j + 32, n_mlen, n_byte, n_same);
+          load_group_runs(j + 32, ((j >> 5) + 1) & 1);
+          if (j > 0) la[j - 32 + lane] = s.ringl[(j - 32 + lane) & 511];
+          __syncwarp();
+        }
+        const float cjf = s.ringc[j & 511];
+        const double cj = (double)cjf;
+        if (lane == 0) s.ringc[(j + 259) & 511] = (float)1e30;  // target j+259 is first touched at j+1
+        const uint32_t same_j = __shfl_sync(0xffffffffu, g_same, jl);
+        // long-run shortcut squeeze.c:251-271
+        if (skip_left == 0 && !just_finished && same_j > (uint32_t)kMaxMatch * 2 && j > (uint32_t)kMaxMatch + 1 &&
+            j + kMaxMatch * 2 + 1 < nb) {
+          uint32_t sg = sameg[j - kMaxMatch];
+          uint32_t clip = nb - 1 - (j - kMaxMatch);
+          if ((sg > clip ? clip : sg) > (uint32_t)kMaxMatch) skip_left = kMaxMatch;
+        }
+        if (skip_left > 0) {
+          if (lane == 0) {
+            s.ringc[(j + kMaxMatch) & 511] = (float)(cj + cost258);
+            s.ringl[(j + kMaxMatch) & 511] = kMaxMatch;
+          }
+          skip_left--;
+          just_finished = skip_left == 0;
+          __syncwarp();
+          continue;
+        }
+        just_finished = false;
+        const uint32_t ml = __shfl_sync(0xffffffffu, g_mlen, jl);
+        const uint32_t byte = __shfl_sync(0xffffffffu, g_byte, jl);
+        if (lane == 0) {  // literal squeeze.c:277-284
+          double nc = s.llcost[byte] + cj;
+          uint32_t tg = (j + 1) & 511;
+          if (nc < (double)s.ringc[tg]) { s.ringc[tg] = (float)nc; s.ringl[tg] = 1; }
+        }
+        uint32_t kend = nb - j;
+        if (ml < kend) kend = ml;
+        if (kend >= (uint32_t)kMinMatch) {  // squeeze.c:286-302
+          const uint4* st = (const uint4*)&s.stage[(j >> 5) & 1][jl * kRunSlots];
+          const uint4 ea = st[0], eb = st[1];
+          const double mc = mincost + cj;
+          const bool ovf = (eb.w & kOverflowBit) != 0;
+          for (uint32_t k = 3 + lane; k <= kend; k += 32) {
+            uint32_t e = eb.w;
+            if (ovf) {
+              e = 0;
+              if (k > run_len(eb.z)) {
+                uint32_t off = eb.w & ~kOverflowBit, cnt = b.ovf[off];
+                for (uint32_t r = 0; r < cnt; r++) { uint32_t x = b.ovf[off + 1 + r]; if (run_len(x) >= k) { e = x; break; } }
+              }
+            }
+            if (k <= run_len(eb.z)) e = eb.z;
+            if (k <= run_len(eb.y)) e = eb.y;
+            if (k <= run_len(eb.x)) e = eb.x;
+            if (k <= run_len(ea.w)) e = ea.w;
+            if (k <= run_len(ea.z)) e = ea.z;
+            if (k <= run_len(ea.y)) e = ea.y;
+            if (k <= run_len(ea.x)) e = ea.x;
+            const uint32_t tg = (j + k) & 511;
+            const float pend = s.ringc[tg];
+            if ((double)pend <= mc) continue;  // squeeze.c:293
+            const int dsym = (int)run_dsym(e);
+            double nc = (double)(length_extra_bits((int)k) + dist_symbol_extra_bits(dsym)) + s.lencost[k] + s.dcost[dsym];
+            nc = nc + cj;
+            if (nc < (double)pend) { s.ringc[tg] = (float)nc; s.ringl[tg] = (uint16_t)k; }
+          }
+        }
+        __syncwarp();
+      }
+      // flush the tail of length_array, entries [flushed, nb]
+      const uint32_t flushed = nb & ~31u;
+      // when nb is a multiple of 32 the group [nb-32, nb) has not been flushed yet
+      const uint32_t from = (nb & 31u) == 0 && nb > 0 ? nb - 32 : flushed;
+      for (uint32_t t = from + lane; t <= nb; t += 32) la[t] = s.ringl[t & 511];
+      __syncwarp();
+    }
+
+    // ------------------------------------------------------------------ trace back
+    uint32_t cursor = nb + 1;  // path[cursor .. nb+1) holds the symbols in order
+    {
+      uint32_t idx = nb;
+      while (idx > 0) {
+        const uint32_t wlo = idx >= 1024u ? idx - 1023u : 0u;
+        for (uint32_t t = lane; t <= idx - wlo; t += 32) s.win[t] = la[wlo + t];
+        __syncwarp();
+        if (lane == 0) {
+          while (idx > 0 && idx >= wlo) {
+            uint32_t l = s.win[idx - wlo];
+            if (l == 0 || l > idx) { l = 1; flags |= 2; }  // corrupted chain guard (never expected)
+            path[--cursor] = (uint16_t)l;
+            idx -= l;
+            if (idx < wlo) break;
+          }
+        }
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        cursor = __shfl_sync(0xffffffffu, cursor, 0);
+        flags = __shfl_sync(0xffffffffu, flags, 0);
+        __syncwarp();
+      }
+    }
+    const uint32_t nsym = nb + 1 - cursor;
+
+    // ------------------------------------------------------------------ follow path + histogram
+    uint16_t* cl = b.st_ll[curbuf] + sd.pos_off;
+    uint16_t* cd = b.st_d[curbuf] + sd.pos_off;
+    for (int i = lane; i < 320; i += 32) s.hist[i] = 0;
+    __syncwarp();
+    {
+      uint32_t posbase = 0;
+      for (uint32_t base = 0; base < nsym; base += 32) {
+        const uint32_t t = base + lane;
+        const bool act = t < nsym;
+        const uint32_t len = act ? path[cursor + t] : 0;
+        const uint32_t step = act ? (len >= (uint32_t)kMinMatch ? len : 1u) : 0u;
+        uint32_t incl = step;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= (uint32_t)d) incl += o;
+        }
+        if (act) {
+          const uint32_t pj = posbase + incl - step;
+          if (len >= (uint32_t)kMinMatch) {
+            const uint32_t dist = table_dist(b, sd.pos_off + pj, len);
+            cl[t] = (uint16_t)len; cd[t] = (uint16_t)dist;
+            atomicAdd(&s.hist[length_symbol((int)len)], 1u);
+            atomicAdd(&s.hist[288 + dist_symbol((int)dist)], 1u);
+          } else {
+            const uint32_t by = in[pj];
+            cl[t] = (uint16_t)by; cd[t] = 0;
+            atomicAdd(&s.hist[by], 1u);
+          }
+        }
+        posbase += __shfl_sync(0xffffffffu, incl, 31);
+      }
+    }
+    __syncwarp();
+    if (fixed) { bestbuf = curbuf; best_size = nsym; bestcost = 0; it++; break; }
+    if (lane == 0) s.hist[256] = 1;  // deflate.c:575 and squeeze.c:409
+    __syncwarp();
+
+    // ------------------------------------------------------------------ block size, best, statistics
+    const uint64_t cost = warp_dynamic_bits(s, scratch, lane);  // squeeze.c:492
+    if (cost < bestcost) {  // squeeze.c:496-501
+      int t = curbuf; curbuf = bestbuf; bestbuf = t;
+      best_size = nsym;
+      for (int i = lane; i < 320; i += 32) s.bests[i] = s.stats[i];
+      bestcost = cost;
+    }
+    for (int i = lane; i < 320; i += 32) { s.last[i] = s.stats[i]; s.stats[i] = s.hist[i]; }  // :502-504
+    __syncwarp();
+    bool need_entropy = true;
+    if (lastrandomstep != -1) {  // :505-511; (size_t)(a*1.0 + b*0.5) == a + (b >> 1)
+      for (int i = lane; i < 320; i += 32) s.stats[i] = s.stats[i] + (s.last[i] >> 1);
+      __syncwarp();
+      if (lane == 0) s.stats[256] = 1;
+      __syncwarp();
+    }
+    if (it > 5 && cost == lastcost) {  // :512-517
+      for (int i = lane; i < 320; i += 32) s.stats[i] = s.bests[i];
+      __syncwarp();
+      if (lane == 0) {  // RandomizeFreqs squeeze.c:96-101 (sequential, in place)
+        for (int part = 0; part < 2; part++) {
+          uint32_t* f = s.stats + (part ? 288 : 0);
+          const uint32_t n = part ? kNumD : kNumLL;
+          for (uint32_t i = 0; i < n; i++) {
+            ran_z = 36969u * (ran_z & 65535u) + (ran_z >> 16);
+            ran_w = 18000u * (ran_w & 65535u) + (ran_w >> 16);
+            uint32_t r = (ran_z << 16) + ran_w;
+            if ((r >> 4) % 3 == 0) {
+              ran_z = 36969u * (ran_z & 65535u) + (ran_z >> 16);
+              ran_w = 18000u * (ran_w & 65535u) + (ran_w >> 16);
+              uint32_t r2 = (ran_z << 16) + ran_w;
+              f[i] = f[r2 % n];
+            }
+          }
+        }
+        s.stats[256] = 1;
+      }
+      ran_z = __shfl_sync(0xffffffffu, ran_z, 0);
+      ran_w = __shfl_sync(0xffffffffu, ran_w, 0);
+      __syncwarp();
+      lastrandomstep = it;
+    }
+    if (need_entropy) {
+      bool ok = warp_entropy(s.stats, kNumLL, s.llcost, b, lane);
+      ok &= warp_entropy(s.stats + 288, kNumD, s.dcost, b, lane);
+      if (!ok) flags |= 1;
+      __syncwarp();
+    }
+    lastcost = cost;
+  }
+
+  if (lane == 0) {
+    js->best_size = best_size;
+    js->best_buf = (uint32_t)bestbuf;
+    js->best_cost = bestcost;
+    js->flags = flags;
+    js->iters_done = (uint32_t)it;
+  }
+}
+
+// copies every segment's best parse into one packed buffer (offsets via atomic allocation)
+__global__ void k_pack(Batch b, int greedy) {
+  __shared__ uint32_t off;
+  const uint32_t seg = blockIdx.x;
+  const SegDesc sd = b.segs[seg];
+  JobState* js = &b.jobs[seg];
+  const uint32_t n = greedy ? js->greedy_size : js->best_size;
+  const int buf = greedy ? 0 : (int)js->best_buf;
+  if (threadIdx.x == 0) { off = atomicAdd(b.out_used, n); js->out_off = off; }
+  __syncthreads();
+  const uint16_t* sl = b.st_ll[buf] + sd.pos_off;
+  const uint16_t* sdp = b.st_d[buf] + sd.pos_off;
+  for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+    b.out_ll[off + t] = sl[t];
+    b.out_d[off + t] = sdp[t];
+  }
+}
+
+}  // namespace zb

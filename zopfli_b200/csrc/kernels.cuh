@@ -1,0 +1,556 @@
+// sm_100a kernels of the zopfli hot path.
+//
+// Pipeline per batch of parse ranges ("segments": a master block for the splitter's greedy
+// pass, or one deflate block for the optimal parse; both carry their own `inend`, which clips
+// matches, `same` and therefore the second hash, exactly like the reference's per-call hash):
+//
+//   k_same_*      run lengths of equal bytes for the whole input            hash.c:116-126
+//   k_keys        hv / hv2 per (segment, position) + bucket histograms      hash.c:96-135
+//   k_bucket_scan exclusive scan of the 32768 bucket counts
+//   k_scatter     stable counting sort = both hash chains laid out as       hash.c:110-114,131-135
+//                 position-sorted buckets (the chains become coalesced lists)
+//   k_match       one warp per position: walk the bucket slices 32 candidates  lz77.c:407-542
+//                 at a time, replay the sequential best/sublen/switch/hop-cap
+//                 semantics with warp scans; emits (len,dist) and the run list
+//   k_greedy      lazy-matching greedy parse over the (len,dist) table      lz77.c:544-630
+//   k_iterate     persistent warp per block: forward DP, trace-back, follow-path, histogram,
+//                 exact dynamic-block size, statistics / entropy / randomisation -- the whole
+//                 ZopfliLZ77Optimal loop with no host round trip            squeeze.c:217-526
+//
+// No tensor-core work exists on this path (no dense contraction); the kernels are integer /
+// byte kernels plus a scalar fp64 dependency chain in the DP.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "deflate_size.hpp"
+#include "symbols.hpp"
+
+namespace zb {
+
+constexpr int kRunSlots = 8;           // table slots per position (cache.c:30-33 keeps 8 too)
+constexpr uint32_t kOverflowBit = 0x80000000u;
+constexpr int kSameTile = 1024;        // tile of the run-length pre-pass
+constexpr uint32_t kNoBreak = 0xffffffffu;
+
+// run-list entry: len_end (9 bits) | dist << 9 (15 bits) | dsym << 24 (5 bits)
+__host__ __device__ inline uint32_t run_pack(uint32_t len_end, uint32_t dist) {
+  return len_end | (dist << 9) | ((uint32_t)dist_symbol((int)dist) << 24);
+}
+__host__ __device__ inline uint32_t run_len(uint32_t e) { return e & 511u; }
+__host__ __device__ inline uint32_t run_dist(uint32_t e) { return (e >> 9) & 32767u; }
+__host__ __device__ inline uint32_t run_dsym(uint32_t e) { return (e >> 24) & 31u; }
+
+struct SegDesc {
+  uint64_t instart, inend, winstart;  // absolute byte positions
+  uint64_t key_off;   // element offset of this segment in hv/hv2/idx/rank arrays
+  uint64_t pos_off;   // element offset of this segment in per-parse-position arrays
+  uint32_t nkeys;     // inend - winstart
+  uint32_t npos;      // inend - instart
+  int32_t mode;       // 0 greedy only, 1 optimal (iterate), 2 optimal with fixed-tree costs
+  int32_t numiterations;
+};
+
+struct JobState {   // per segment, written by k_greedy / k_iterate
+  uint32_t greedy_size;
+  uint32_t best_size;
+  uint32_t best_buf;     // which of the 3 store buffers holds the best parse
+  uint32_t out_off;      // offset of the packed result (k_pack)
+  uint32_t flags;        // bit0: log table overflow (needs host assistance)
+  uint32_t iters_done;
+  uint64_t best_cost;
+  uint64_t pad;
+};
+
+struct Batch {
+  const uint8_t* in;        // whole input (device), padded by >= 16 readable bytes
+  uint64_t insize;
+  const uint16_t* same_g;   // per input byte: min(65535, following equal bytes)
+  const SegDesc* segs;
+  int nsegs;
+  // hash chains as sorted buckets
+  uint16_t* hv;
+  uint16_t* hv2;
+  uint32_t* idx1;
+  uint32_t* idx2;
+  uint32_t* rank1;
+  uint32_t* rank2;
+  uint32_t* bkt1;   // [nsegs][32769] counts -> starts
+  uint32_t* bkt2;
+  // match table
+  uint32_t* ld;     // [npos] (len << 16) | dist of the longest match (raw, len may be 0/1/2)
+  uint16_t* mlen;   // [npos] longest length or 0 (optimal segments only)
+  uint32_t* runs;   // [npos][kRunSlots]
+  uint32_t* ovf;    // overflow arena: [count, entries...]
+  uint32_t* ovf_used;
+  uint32_t ovf_cap;
+  // parse state
+  uint16_t* la;     // [npos + nsegs] length_array, nb+1 per segment (offset pos_off + seg)
+  uint16_t* path;   // [npos + nsegs]
+  uint16_t* st_ll[3];
+  uint16_t* st_d[3];
+  JobState* jobs;
+  uint8_t* scratch;          // per segment kIterScratch bytes
+  const double* logtab;      // L[n] = log(n) * 1.4426950408889 (host libm), n in [0, logtab_n)
+  uint32_t logtab_n;
+  // packed results
+  uint16_t* out_ll;
+  uint16_t* out_d;
+  uint32_t* out_used;
+};
+
+struct PmBig { PmScratch<kNumLL, 15> pm; uint8_t good[kNumLL]; };
+constexpr size_t kIterScratch = 4 * ((sizeof(PmBig) + 255) / 256 * 256);
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+
+__device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* p) {
+  const uintptr_t a = (uintptr_t)p;
+  const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+  uint32_t lo = __ldg(w), hi = __ldg(w + 1);
+  return __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8);
+}
+
+// common prefix of in[a..] and in[b..], capped at limit; starts comparing at offset `from`
+// (bytes before `from` are known equal or irrelevant to the caller).
+__device__ __forceinline__ uint32_t match_len(const uint8_t* a, const uint8_t* b, uint32_t from,
+                                              uint32_t limit) {
+  uint32_t m = from;
+  while (m < limit) {
+    uint32_t x = ld_u32_unaligned(a + m) ^ ld_u32_unaligned(b + m);
+    if (x) { m += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+    m += 4;
+  }
+  return m < limit ? m : limit;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// ---------------------------------------------------------------------------------------------
+// k_same_*: same_g[p] = min(65535, #{t>=1: in[p+t]==in[p] contiguous}) over the whole input.
+// A "break" at e means in[e] != in[e+1] (or e is the last byte).  same_g[p] = nextbreak(p) - p.
+
+__global__ void k_same_tiles(const uint8_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ tile_first) {
+  // first break position inside each tile (relative), or kNoBreak
+  __shared__ uint32_t first;
+  uint64_t tile = blockIdx.x;
+  uint64_t base = tile * kSameTile;
+  if (threadIdx.x == 0) first = kNoBreak;
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < kSameTile; t += blockDim.x) {
+    uint64_t p = base + t;
+    if (p < n) {
+      bool brk = (p + 1 >= n) || in[p] != in[p + 1];
+      if (brk) atomicMin(&first, t);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) tile_first[tile] = first;
+}
+
+// next_tile[t] = smallest tile index >= t that contains a break (always exists: last byte breaks).
+__global__ void k_same_next_tile(const uint32_t* __restrict__ tile_first, uint32_t ntiles,
+                                 uint32_t* __restrict__ next_tile) {
+  // single CTA, backward sweep in chunks; ntiles <= insize/1024 so this is tiny
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = ntiles;  // sentinel
+  __syncthreads();
+  for (int64_t hi = ntiles; hi > 0; hi -= blockDim.x) {
+    int64_t t = hi - 1 - threadIdx.x;
+    // each thread: nearest tile >= t with a break, searched within this chunk first
+    uint32_t mine = kNoBreak;
+    if (t >= 0 && tile_first[t] != kNoBreak) mine = (uint32_t)t;
+    // suffix-min within the chunk via shared memory (chunk is reversed: thread 0 is highest t)
+    __shared__ uint32_t buf[1024];
+    buf[threadIdx.x] = mine;
+    __syncthreads();
+    // thread i needs min over threads j <= i (higher tiles have smaller thread idx) of tiles >= t
+    // i.e. the smallest tile index >= t: scan from own index towards lower thread idx is wrong
+    // direction (those are higher tiles); we want the closest one, i.e. the largest j <= i
+    // with buf[j] != kNoBreak has the smallest tile >= t.
+    uint32_t res = kNoBreak;
+    for (int j = threadIdx.x; j >= 0; j--) {
+      if (buf[j] != kNoBreak) { res = buf[j]; break; }
+    }
+    if (res == kNoBreak) res = carry;
+    if (t >= 0) next_tile[t] = res;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1 || t == 0) {
+      // lowest tile of this chunk becomes the carry for the next (lower) chunk
+      if (t >= 0) carry = res;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_same_fill(const uint8_t* __restrict__ in, uint64_t n,
+                            const uint32_t* __restrict__ tile_first,
+                            const uint32_t* __restrict__ next_tile, uint32_t ntiles,
+                            uint16_t* __restrict__ same_g) {
+  __shared__ uint32_t brk[kSameTile];  // per position: 1 if break
+  __shared__ uint32_t nb[kSameTile];   // next break position (relative) at or after t, or kNoBreak
+  uint64_t tile = blockIdx.x, base = tile * kSameTile;
+  for (uint32_t t = threadIdx.x; t < kSameTile; t += blockDim.x) {
+    uint64_t p = base + t;
+    brk[t] = (p < n) && ((p + 1 >= n) || in[p] != in[p + 1]);
+  }
+  __syncthreads();
+  // backward sweep by warp 0 in 32-wide steps using ballots
+  if (threadIdx.x < 32) {
+    uint32_t carry = kNoBreak;
+    for (int w = kSameTile / 32 - 1; w >= 0; w--) {
+      uint32_t t = (uint32_t)w * 32 + threadIdx.x;
+      uint32_t mask = __ballot_sync(0xffffffffu, brk[t] != 0);
+      uint32_t up = mask & (0xffffffffu << threadIdx.x);  // breaks at lanes >= mine
+      uint32_t r = up ? (uint32_t)w * 32 + (uint32_t)(__ffs((int)up) - 1) : carry;
+      nb[t] = r;
+      if (mask) carry = (uint32_t)w * 32 + (uint32_t)(__ffs((int)mask) - 1);
+    }
+  }
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < kSameTile; t += blockDim.x) {
+    uint64_t p = base + t;
+    if (p >= n) continue;
+    uint64_t e;
+    if (nb[t] != kNoBreak) {
+      e = base + nb[t];
+    } else {
+      uint32_t nt = (tile + 1 < ntiles) ? next_tile[tile + 1] : ntiles;
+      e = (nt < ntiles) ? (uint64_t)nt * kSameTile + tile_first[nt] : n - 1;
+    }
+    uint64_t s = e - p;
+    same_g[p] = (uint16_t)(s > 65535 ? 65535 : s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_keys: hv/hv2 per (segment, key position) and bucket histograms.
+// work item = (segment, first key) covering kKeyChunk keys.
+
+constexpr int kKeyChunk = 2048;
+struct KeyWork { uint32_t seg, first; };
+
+__global__ void k_keys(Batch b, const KeyWork* __restrict__ work) {
+  KeyWork w = work[blockIdx.x];
+  const SegDesc sd = b.segs[w.seg];
+  uint32_t* c1 = b.bkt1 + (uint64_t)w.seg * 32769;
+  uint32_t* c2 = b.bkt2 + (uint64_t)w.seg * 32769;
+  for (uint32_t t = threadIdx.x; t < kKeyChunk; t += blockDim.x) {
+    uint32_t i = w.first + t;
+    if (i >= sd.nkeys) break;
+    uint64_t p = sd.winstart + i;
+    // hash.c:96-98,107-108 (bytes at or past `end` count as 0)
+    uint32_t b0 = b.in[p];
+    uint32_t b1 = p + 1 < sd.inend ? b.in[p + 1] : 0;
+    uint32_t b2 = p + 2 < sd.inend ? b.in[p + 2] : 0;
+    uint32_t hv = ((b0 << 10) ^ (b1 << 5) ^ b2) & 32767u;
+    // hash.c:116-126 with `end` = this segment's inend
+    uint64_t clip = sd.inend - 1 - p;
+    uint32_t same = b.same_g[p];
+    if ((uint64_t)same > clip) same = (uint32_t)clip;
+    uint32_t hv2 = (((int)same - kMinMatch) & 255) ^ hv;  // hash.c:129
+    b.hv[sd.key_off + i] = (uint16_t)hv;
+    b.hv2[sd.key_off + i] = (uint16_t)hv2;
+    atomicAdd(&c1[hv], 1u);
+    atomicAdd(&c2[hv2], 1u);
+  }
+}
+
+// exclusive scan of 32768 counts per (segment, chain); entry 32768 receives the total
+__global__ void k_bucket_scan(Batch b) {
+  uint32_t seg = blockIdx.x >> 1;
+  uint32_t* c = ((blockIdx.x & 1) ? b.bkt2 : b.bkt1) + (uint64_t)seg * 32769;
+  __shared__ uint32_t part[1024];
+  const int per = 32;  // 1024 threads x 32 bins
+  uint32_t base = threadIdx.x * per, sum = 0;
+  uint32_t v[per];
+#pragma unroll
+  for (int i = 0; i < per; i++) { v[i] = c[base + i]; sum += v[i]; }
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    uint32_t t = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += t;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - sum;
+#pragma unroll
+  for (int i = 0; i < per; i++) { c[base + i] = run; run += v[i]; }
+  if (threadIdx.x == 1023) c[32768] = run;
+}
+
+// Stable scatter: one warp per (segment, chain) walks the keys in position order; the running
+// bucket cursors live in 128 KiB of shared memory.  idx[dest] = position, rank[position] = dest.
+__global__ void __launch_bounds__(32) k_scatter(Batch b) {
+  extern __shared__ uint32_t cursor[];  // 32768
+  uint32_t seg = blockIdx.x >> 1;
+  bool second = blockIdx.x & 1;
+  const SegDesc sd = b.segs[seg];
+  const uint32_t* bs = (second ? b.bkt2 : b.bkt1) + (uint64_t)seg * 32769;
+  const uint16_t* key = (second ? b.hv2 : b.hv) + sd.key_off;
+  uint32_t* idx = (second ? b.idx2 : b.idx1) + sd.key_off;
+  uint32_t* rank = (second ? b.rank2 : b.rank1) + sd.key_off;
+  const uint32_t lane = threadIdx.x;
+  for (uint32_t i = lane; i < 32768; i += 32) cursor[i] = bs[i];
+  __syncwarp();
+  for (uint32_t base = 0; base < sd.nkeys; base += 32) {
+    uint32_t i = base + lane;
+    bool act = i < sd.nkeys;
+    uint32_t k = act ? key[i] : 0xffffffffu;  // inactive lanes get a key no active lane has
+    uint32_t peers = __match_any_sync(0xffffffffu, k);
+    uint32_t before = __popc(peers & ((1u << lane) - 1));
+    uint32_t cur = act ? cursor[k] : 0;
+    __syncwarp();
+    if (act && before == 0) cursor[k] = cur + __popc(peers);
+    __syncwarp();
+    if (act) {
+      uint32_t d = cur + before;
+      idx[d] = i;
+      rank[i] = d;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_match: ZopfliFindLongestMatch for every parse position, cache-free (lz77.c:407-542).
+
+constexpr int kMatchWarps = 8;
+constexpr int kMatchPosPerCta = 128;
+struct PosWork { uint32_t seg, first; };
+
+__global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWork* __restrict__ work) {
+  __shared__ uint32_t stage[kMatchWarps][256];  // run list of the position being walked
+  const PosWork w = work[blockIdx.x];
+  const SegDesc sd = b.segs[w.seg];
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint16_t* hv = b.hv + sd.key_off;
+  const uint16_t* hv2 = b.hv2 + sd.key_off;
+  const uint32_t* bs1 = b.bkt1 + (uint64_t)w.seg * 32769;
+  const uint32_t* bs2 = b.bkt2 + (uint64_t)w.seg * 32769;
+  const uint32_t woff = (uint32_t)(sd.instart - sd.winstart);  // key index of parse position 0
+  const uint8_t* wbase = b.in + sd.winstart;                   // byte of key index 0
+  uint32_t* myruns = stage[warp];
+
+  for (uint32_t t = warp; t < kMatchPosPerCta; t += kMatchWarps) {
+    const uint32_t j = w.first + t;  // parse position within the segment
+    if (j >= sd.npos) break;
+    const uint32_t ip = woff + j;    // key index of pos
+    const uint32_t remain = sd.npos - j;  // inend - pos
+    uint32_t best = 1, bestdist = 0, nruns = 0;
+    if (remain >= (uint32_t)kMinMatch) {  // lz77.c:440-446
+      const uint32_t limit = remain < (uint32_t)kMaxMatch ? remain : (uint32_t)kMaxMatch;  // :448-450
+      uint32_t same0 = b.same_g[sd.winstart + ip];
+      { uint64_t clip = sd.inend - 1 - (sd.winstart + ip); if (same0 > clip) same0 = (uint32_t)clip; }
+      const uint32_t v2 = hv2[ip];
+      int hops = kMaxChainHits;
+      bool chain2 = false;
+      const uint32_t* idx = b.idx1 + sd.key_off;
+      uint32_t lo = bs1[hv[ip]];
+      uint32_t cur = b.rank1[sd.key_off + ip];  // next candidate is idx[cur-1]
+      const uint8_t* src = wbase + ip;
+      for (;;) {
+        uint32_t avail = cur - lo;
+        uint32_t take = avail < 32u ? avail : 32u;
+        if ((uint32_t)hops < take) take = (uint32_t)hops;
+        if (take == 0) break;  // bucket exhausted == self link lz77.c:523
+        uint32_t iq = 0, dist = 0, m = 0;
+        bool valid = lane < take;
+        if (valid) {
+          iq = idx[cur - 1 - lane];
+          dist = ip - iq;
+          valid = dist < (uint32_t)kWindow;  // lz77.c:464
+        }
+        bool h2eq = false;
+        if (valid) {
+          const uint8_t* cand = wbase + iq;
+          // lz77.c:478-479: a candidate that differs at offset `best` cannot beat it
+          if (src[best] == cand[best]) m = match_len(src, cand, 0, limit);
+          if (!chain2) h2eq = hv2[iq] == v2;
+        }
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        const uint32_t nv = __popc(vmask);  // valid lanes form a prefix (distances increase)
+        if (nv == 0) break;
+        // inclusive prefix max of m, seeded with best
+        uint32_t pm = m;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          uint32_t o = __shfl_up_sync(0xffffffffu, pm, d);
+          if (lane >= (uint32_t)d && o > pm) pm = o;
+        }
+        uint32_t pm_prev = __shfl_up_sync(0xffffffffu, pm, 1);
+        const uint32_t pm_excl = (lane == 0) ? best : (pm_prev > best ? pm_prev : best);
+        const uint32_t pm_incl = pm > best ? pm : best;
+        const bool improved = valid && m > pm_excl;
+        const uint32_t exitmask = __ballot_sync(0xffffffffu, valid && m >= limit);
+        const uint32_t swmask = __ballot_sync(0xffffffffu, valid && h2eq && pm_incl >= same0);
+        uint32_t c = nv - 1;
+        bool do_exit = false, do_switch = false;
+        uint32_t e = exitmask ? (uint32_t)(__ffs((int)exitmask) - 1) : 32u;
+        uint32_t s = swmask ? (uint32_t)(__ffs((int)swmask) - 1) : 32u;
+        if (e <= c && e <= s) { c = e; do_exit = true; }       // break before the switch test
+        else if (s <= c) { c = s; do_switch = true; }
+        const uint32_t keep = (c == 31) ? 0xffffffffu : ((1u << (c + 1)) - 1);
+        const uint32_t impmask = __ballot_sync(0xffffffffu, improved) & keep;
+        if (improved && lane <= c) {
+          uint32_t slot = nruns + __popc(impmask & ((1u << lane) - 1));
+          myruns[slot] = run_pack(m, dist);  // lengths (pm_excl, m] first reached at `dist`
+        }
+        nruns += __popc(impmask);
+        if (impmask) {
+          int last = 31 - __clz((int)impmask);
+          bestdist = __shfl_sync(0xffffffffu, dist, last);
+        }
+        best = __shfl_sync(0xffffffffu, pm_incl, c);
+        hops -= (int)(c + 1);
+        if (do_exit) break;
+        if (do_switch) {  // lz77.c:509-519: continue from this candidate along chain 2
+          uint32_t iqs = __shfl_sync(0xffffffffu, iq, s);
+          chain2 = true;
+          idx = b.idx2 + sd.key_off;
+          lo = bs2[v2];
+          cur = b.rank2[sd.key_off + iqs];
+        } else {
+          if (nv < 32u) break;  // window limit / bucket end / hop cap inside this round
+          cur -= 32u;
+        }
+        if (hops <= 0) break;  // lz77.c:527-530
+      }
+    } else {
+      best = 0;
+    }
+    __syncwarp();
+    // outputs
+    const uint64_t o = sd.pos_off + j;
+    if (lane == 0) b.ld[o] = (best << 16) | bestdist;
+    if (sd.mode != 0) {
+      if (lane == 0) b.mlen[o] = (uint16_t)(best >= (uint32_t)kMinMatch ? best : 0);
+      uint32_t* dst = b.runs + o * kRunSlots;
+      if (best < (uint32_t)kMinMatch) nruns = 0;
+      // runs reaching only length < 3 never exist on their own: the first run's len_end >= 3
+      // unless best < 3; entries are stored as found (first run covers lengths 2..m, harmless)
+      if (nruns <= (uint32_t)kRunSlots) {
+        if (lane < (uint32_t)kRunSlots) dst[lane] = lane < nruns ? myruns[lane] : 0u;
+      } else {
+        uint32_t off = 0;
+        uint32_t extra = nruns - (kRunSlots - 1);
+        if (lane == 0) off = atomicAdd(b.ovf_used, extra + 1);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        if (off + extra + 1 <= b.ovf_cap) {
+          if (lane == 0) b.ovf[off] = extra;
+          for (uint32_t r = lane; r < extra; r += 32) b.ovf[off + 1 + r] = myruns[kRunSlots - 1 + r];
+          if (lane < (uint32_t)kRunSlots - 1) dst[lane] = myruns[lane];
+          if (lane == (uint32_t)kRunSlots - 1) dst[lane] = kOverflowBit | off;
+        } else {
+          // arena exhausted: flagged through ovf_used > ovf_cap, host re-runs with a larger arena
+          if (lane < (uint32_t)kRunSlots) dst[lane] = 0;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// distance of the shortest-distance match of length >= len at parse position (table lookup,
+// this is what FollowPath's limited search returns, squeeze.c:367)
+__device__ __forceinline__ uint32_t table_dist(const Batch& b, uint64_t o, uint32_t len) {
+  const uint32_t* r = b.runs + o * kRunSlots;
+#pragma unroll
+  for (int i = 0; i < kRunSlots - 1; i++) {
+    uint32_t e = r[i];
+    if (run_len(e) >= len) return run_dist(e);
+  }
+  uint32_t e = r[kRunSlots - 1];
+  if (!(e & kOverflowBit)) return run_dist(e);
+  uint32_t off = e & ~kOverflowBit;
+  uint32_t cnt = b.ovf[off];
+  for (uint32_t i = 0; i < cnt; i++) {
+    uint32_t x = b.ovf[off + 1 + i];
+    if (run_len(x) >= len) return run_dist(x);
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_greedy: ZopfliLZ77Greedy (lz77.c:544-630) over the (len,dist) table; one warp per segment,
+// lane 0 runs the lazy-matching state machine out of shared-memory windows the warp refills.
+
+constexpr int kGreedyWin = 2048;
+
+__global__ void __launch_bounds__(32) k_greedy(Batch b, int buf) {
+  __shared__ uint32_t wld[kGreedyWin];
+  __shared__ uint8_t wby[kGreedyWin];
+  __shared__ uint16_t oll[1024], od[1024];
+  const uint32_t seg = blockIdx.x, lane = threadIdx.x;
+  const SegDesc sd = b.segs[seg];
+  if (sd.mode == 2) {  // fixed-tree parse needs no greedy seed
+    if (lane == 0) b.jobs[seg].greedy_size = 0;
+    return;
+  }
+  const uint32_t* ld = b.ld + sd.pos_off;
+  const uint8_t* in = b.in + sd.instart;
+  uint16_t* out_ll = b.st_ll[buf] + sd.pos_off;
+  uint16_t* out_d = b.st_d[buf] + sd.pos_off;
+  uint32_t i = 0, nout = 0, flushed = 0;
+  uint32_t prev_length = 0, prev_match = 0;
+  int match_available = 0;
+  const uint32_t n = sd.npos;
+  while (i < n) {
+    const uint32_t wb = i;
+    const uint32_t wn = (n - wb) < (uint32_t)kGreedyWin ? (n - wb) : (uint32_t)kGreedyWin;
+    for (uint32_t t = lane; t < wn; t += 32) { wld[t] = ld[wb + t]; wby[t] = in[wb + t]; }
+    __syncwarp();
+    if (lane == 0) {
+      while (i < wb + wn && nout - flushed < 1022) {
+        uint32_t e = wld[i - wb];
+        uint32_t leng = e >> 16, dist = e & 0xffffu;
+        int lengthscore = dist > 1024 ? (int)leng - 1 : (int)leng;  // GetLengthScore lz77.c:265-271
+        int prevlengthscore = prev_match > 1024 ? (int)prev_length - 1 : (int)prev_length;
+        bool emit_normal = true;
+        if (match_available) {  // lz77.c:584-609
+          match_available = 0;
+          if (lengthscore > prevlengthscore + 1) {
+            // previous position becomes a literal; its byte is in the window unless i == wb
+            uint8_t pb = (i > wb) ? wby[i - 1 - wb] : in[i - 1];
+            oll[(nout - flushed)] = pb; od[(nout - flushed)] = 0; nout++;
+            if (lengthscore >= kMinMatch && leng < (uint32_t)kMaxMatch) {
+              match_available = 1; prev_length = leng; prev_match = dist;
+              i++;
+              emit_normal = false;
+            }
+          } else {
+            oll[(nout - flushed)] = (uint16_t)prev_length; od[(nout - flushed)] = (uint16_t)prev_match; nout++;
+            i += prev_length - 1;  // match started at i-1
+            emit_normal = false;
+          }
+        } else if (lengthscore >= kMinMatch && leng < (uint32_t)kMaxMatch) {  // lz77.c:610-615
+          match_available = 1; prev_length = leng; prev_match = dist;
+          i++;
+          emit_normal = false;
+        }
+        if (emit_normal) {  // lz77.c:619-629
+          if (lengthscore >= kMinMatch) {
+            oll[(nout - flushed)] = (uint16_t)leng; od[(nout - flushed)] = (uint16_t)dist; nout++;
+            i += leng;
+          } else {
+            oll[(nout - flushed)] = wby[i - wb]; od[(nout - flushed)] = 0; nout++;
+            i += 1;
+          }
+        }
+      }
+    }
+    i = __shfl_sync(0xffffffffu, i, 0);
+    nout = __shfl_sync(0xffffffffu, nout, 0);
+    match_available = __shfl_sync(0xffffffffu, match_available, 0);
+    prev_length = __shfl_sync(0xffffffffu, prev_length, 0);
+    prev_match = __shfl_sync(0xffffffffu, prev_match, 0);
+    __syncwarp();
+    for (uint32_t t = lane; t < nout - flushed; t += 32) { out_ll[flushed + t] = oll[t]; out_d[flushed + t] = od[t]; }
+    flushed = nout;
+    __syncwarp();
+  }
+  if (lane == 0) b.jobs[seg].greedy_size = nout;
+}
+
+}  // namespace zb
