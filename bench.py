@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- input MiB/s of ZopfliCompress(gzip, numiterations=15, blocksplittingmax=15).
+
+A "step" is one whole compression of the workload: config C2 of BASELINE.json (100,000,000 B of
+enwik8-like text, numiterations=15) per GPU.  With N>1 (torchrun, one rank per GPU) the job is ONE
+gzip stream over N x 100 MB: each rank owns a contiguous shard of master blocks, receives the
+32 KiB halo of its left neighbour and ships its compressed spans to rank 0 over NCCL; rank 0
+splices them by a bit-offset scan.  Weak scaling: per-GPU work is fixed.
+
+  value   whole-job MiB/s with the input already resident in HBM when the timed region starts
+  e2e     the same through the reference-facing C ABI with HOST buffers (H2D + D2H inside)
+  --impl reference   the reference's own CPU implementation (oracle/_ref) on a bounded sample
+"""
+import argparse
+import gzip
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+MIB = float(1 << 20)
+SHARD = 100_000_000          # config C2 per GPU
+NUMITER = 15
+ALG_BYTES_PER_STEP = 34.0    # 28 table + 1 input + 2+2 length_array + ~0.6 store, per position-iteration
+REF_SAMPLE = 2_000_000       # bytes of the workload the CPU reference is timed on (2 master blocks)
+
+
+def workload(nbytes, seed):
+    path = os.environ.get("ZOPFLI_BENCH_ENWIK8")
+    if path and os.path.exists(path) and seed == 2:
+        return open(path, "rb").read()[:nbytes], "file:" + os.path.basename(path)
+    from zopfli_b200 import corpus
+    return corpus.synth_text(nbytes, seed), "synthetic"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev, self.stop_flag, self.sm, self.maxsm, self.reasons = dev, False, [], 0, set()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.sm.append(float(o[0]))
+                self.maxsm = float(o[1])
+                for n, v in zip(names, o[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.maxsm or None,
+                "reasons": sorted(self.reasons)}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("k_iterate_bytes_per_launch")
+        except Exception:
+            pass
+    return None
+
+
+def cpu_reference(data, steps, warmup):
+    """the reference's own single-threaded implementation (it has no threading)"""
+    import zref
+    ref = zref.Ref(ndebug=True)
+    sample = data[:REF_SAMPLE]
+    times = []
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        out = ref.compress(sample, 0, numiterations=NUMITER)
+        if i >= warmup:
+            times.append(time.perf_counter() - t)
+    sec = sum(times) / len(times)
+    return len(sample) / MIB / sec, sec, out
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    data, kind = workload(SHARD, 2)
+    steps, warmup = args.steps, args.warmup
+    v, sec, _ = cpu_reference(data, steps, warmup)
+    line = {"impl": "reference", "metric": "input MiB/s at numiterations=15", "value": v, "unit": "MiB/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": kind,
+            "config": {"workload": "C2 enwik8-like text 100,000,000 B, gzip, numiterations=15, blocksplittingmax=15",
+                       "sample": "first %d bytes" % REF_SAMPLE},
+            "cpu_baseline": {"value": v, "unit": "MiB/s", "cores": 1, "kind": "reference",
+                             "sample": "first %d bytes (2 master blocks) of the workload, -O3 -DNDEBUG, 1 thread "
+                                       "(the reference has no threading)" % REF_SAMPLE},
+            "e2e": {"value": v, "unit": "MiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_product(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    import zopfli_b200 as zb
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ["ZOPFLI_B200_DEVICE"] = str(local)
+    lib = zb.library()
+    lib.set_stream(torch.cuda.current_stream().cuda_stream)
+    steps, warmup = args.steps, args.warmup
+
+    data, kind = workload(SHARD, 2 + rank)
+    n = len(data)
+    halo = 32768 if rank > 0 else 0
+    # pinned host buffer [halo | shard | pad], device copy of the same
+    host = torch.zeros(halo + n + 64, dtype=torch.uint8).pin_memory()
+    host[halo:halo + n] = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+    devbuf = torch.zeros(halo + n + 64, dtype=torch.uint8, device=dev)
+    if world > 1:  # halo exchange over NCCL: last 32 KiB of rank r -> rank r+1
+        devbuf[halo:halo + n].copy_(host[halo:halo + n])
+        tail = devbuf[halo + n - 32768: halo + n].contiguous()
+        recv = torch.empty(32768, dtype=torch.uint8, device=dev)
+        ops = []
+        if rank + 1 < world:
+            ops.append(dist.P2POp(dist.isend, tail, rank + 1))
+        if rank > 0:
+            ops.append(dist.P2POp(dist.irecv, recv, rank - 1))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if rank > 0:
+            devbuf[:halo].copy_(recv)
+            host[:halo].copy_(recv.cpu())
+    devbuf.copy_(host)
+    torch.cuda.synchronize()
+    hptr, dptr = host.data_ptr(), devbuf.data_ptr()
+    total = halo + n
+
+    def job(resident):
+        """one whole compression; returns rank 0's gzip bytes"""
+        if world == 1:
+            return lib.compress_ptr(hptr, n, zb.ZOPFLI_FORMAT_GZIP, dev_ptr=dptr if resident else None,
+                                    numiterations=NUMITER)
+        span = lib.deflate_span_ptr(hptr, total, halo, total, final=int(rank == world - 1),
+                                    dev_ptr=dptr if resident else None, numiterations=NUMITER)
+        crc = lib.crc32(hptr + halo, n)
+        # gather spans + crc to rank 0 over NCCL
+        meta = torch.tensor([len(span), crc, n], dtype=torch.int64, device=dev)
+        metas = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(metas, meta)
+        sizes = [int(m[0]) for m in metas]
+        mx = max(sizes)
+        sp = torch.zeros(mx, dtype=torch.uint8, device=dev)
+        sp[: len(span)] = torch.frombuffer(bytearray(span), dtype=torch.uint8).to(dev)
+        gathered = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(sp, gathered, dst=0)
+        if rank != 0:
+            return None
+        spans = [g[:s].cpu().numpy().tobytes() for g, s in zip(gathered, sizes)]
+        body, _ = lib.splice_spans(spans, prefix=bytes([31, 139, 8, 0, 0, 0, 0, 0, 2, 3]))
+        c, tot = 0, 0
+        for i, m in enumerate(metas):
+            c = int(m[1]) if i == 0 else lib.crc32_combine(c, int(m[1]), int(m[2]))
+            tot += int(m[2])
+        return body + int(c).to_bytes(4, "little") + int(tot & 0xffffffff).to_bytes(4, "little")
+
+    def timed(resident):
+        for _ in range(warmup):
+            job(resident)
+        lib.reset_stats()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local)
+        sampler.start()
+        t0 = time.perf_counter()
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = job(resident)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - t0
+        sampler.stop_flag = True
+        ms = max(e0.elapsed_time(e1), wall * 1e3)  # host phases sit between kernels: wall >= event span
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps, out, lib.stats(), sampler.summary()
+
+    ms_res, out_res, st_res, clocks = timed(True)
+    ms_e2e, out_e2e, st_e2e, _ = timed(False)
+    if rank == 0:
+        units = n * world
+        assert out_res == out_e2e, "resident and host-buffer runs disagree"
+        check = {}
+        if world == 1:
+            assert gzip.decompress(out_res) == data, "output does not inflate to the input"
+            cpu_v, cpu_sec, ref_out = cpu_reference(data, 1, 0)
+            # bit-exactness on the sample the CPU baseline ran on: same bytes as our own run of it
+            mine = lib.compress(data[:REF_SAMPLE], zb.ZOPFLI_FORMAT_GZIP, numiterations=NUMITER)
+            check = {"sample_bytes": REF_SAMPLE, "delta_bytes_vs_reference": len(mine) - len(ref_out),
+                     "identical": mine == ref_out}
+            cpu = {"value": cpu_v, "unit": "MiB/s", "cores": 1, "kind": "reference",
+                   "sample": "first %d bytes (2 master blocks) of the workload, oracle/_ref -O3 -DNDEBUG, 1 thread "
+                             "(the reference has no threading)" % REF_SAMPLE}
+        else:
+            cpu = None
+        peak, peak_src = peak_hbm()
+        it_s = st_res["ms_iterate"] / 1e3 / steps
+        alg = ALG_BYTES_PER_STEP * st_res["iterate_steps"] / steps
+        achieved = alg / it_s / 1e9 if it_s > 0 else 0.0
+        line = {"metric": "input MiB/s at numiterations=15", "value": units / MIB / (ms_res / 1e3), "unit": "MiB/s",
+                "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_res, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": kind,
+                "config": {"workload": "C2 enwik8-like text, %d B per GPU (%d B total), gzip, numiterations=15, "
+                                       "blocksplittingmax=15" % (n, units),
+                           "l2": "inputs and working set (GBs) far larger than the 126 MB L2; no flush needed",
+                           "parallelism": "master-block shards x%d, NCCL halo exchange + span gather" % world if world > 1
+                           else "single GPU, all blocks of all master blocks in flight"},
+                "e2e": {"value": units / MIB / (ms_e2e / 1e3), "unit": "MiB/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": st_e2e["h2d_bytes"] / steps, "d2h_bytes_per_step": st_e2e["d2h_bytes"] / steps},
+                "gpu_launches": int(st_res["launches"]),
+                "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "k_iterate", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg, "launch_ms": it_s * 1e3,
+                             "note": "DP dependency chain, not bandwidth, bounds this kernel (SURVEY 7.2 #5)"},
+                "cpu_baseline": cpu,
+                "parity": check,
+                "output_bytes": len(out_res),
+                "kernel_ms_per_step": {k: v / steps for k, v in st_res.items() if k.startswith("ms_")}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_product(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,15 +64,16 @@ uint64_t ZopfliB200HostEmitBlock(const unsigned char* in, const unsigned short* 
 /* ZopfliLengthLimitedCodeLengths (katajainen.h:35-36) as restated for host and device. */
 int ZopfliB200HostLengthLimited(const uint32_t* freq, int n, int maxbits, unsigned* bitlengths);
 
-/* Sharding: compress master blocks [mb_begin, mb_end) of `in` (1,000,000-byte
- * units, util.h:60; deflate.c:912-924) into a position-independent SPAN: a sequence of records
+/* Sharding: compress in[start, end) -- cut into master blocks of 1,000,000 bytes
+ * counted from `start` (util.h:60; deflate.c:912-924), bytes before `start` being the LZ77
+ * dictionary (the 32 KiB halo of a shard) -- into a position-independent SPAN: a sequence of
  *   u8 kind (0 bits, 1 stored) | u8 final | u64 nbits-or-nbytes | payload bytes
  * Compressed blocks are encoded at bit offset 0; stored blocks carry their raw bytes because
  * their padding depends on the final bit offset (deflate.c:643-649).  `final` marks the last
- * block of the last unit.  If dev_in is non-NULL it is a device pointer holding the same bytes
- * as `in` (16-byte aligned, readable 16 bytes past insize) and no host-to-device copy is made. */
+ * block of the range.  If dev_in is non-NULL it is a device pointer holding the same bytes as
+ * `in` (16-byte aligned, readable 16 bytes past insize) and no host-to-device copy is made. */
 int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in, size_t insize,
-                          const unsigned char* dev_in, size_t mb_begin, size_t mb_end, int final,
+                          const unsigned char* dev_in, size_t start, size_t end, int final,
                           unsigned char** span, size_t* spansize);
 /* Splices a span onto a stream whose last byte has *bp bits in use (bit-offset scan). */
 void ZopfliB200AppendSpan(const unsigned char* span, size_t spansize, unsigned char* bp,
@@ -82,11 +83,16 @@ void ZopfliB200CompressDevice(const ZopfliOptions* options, ZopfliFormat output_
                               const unsigned char* in, size_t insize, const unsigned char* dev_in,
                               unsigned char** out, size_t* outsize);
 
+/* CRC-32 of the gzip trailer (gzip_container.c:27-81) and its combination across shards. */
+uint32_t ZopfliB200Crc32(const unsigned char* data, size_t size);
+uint32_t ZopfliB200Crc32Combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
+
 /* Engine control / introspection. */
 typedef struct ZopfliB200Stats {
   double ms_same, ms_keys, ms_scan, ms_scatter, ms_match, ms_greedy, ms_iterate, ms_pack, ms_h2d, ms_d2h;
   double ms_host_split, ms_host_emit, ms_host_other, ms_total;
   uint64_t launches, match_positions, iterate_positions, iterate_steps, h2d_bytes, d2h_bytes;
+  uint64_t cyc_sum[6], cyc_max[6], max_block_positions; /* k_iterate phase cycles, see engine.hpp */
 } ZopfliB200Stats;
 void ZopfliB200GetStats(ZopfliB200Stats* out);
 void ZopfliB200ResetStats(void);

@@ -70,10 +70,10 @@ def test_store_seam_50_iterations_and_batch(ref, lib):
         r = ref.lz77(TXT, s, e, 0, 5)
         assert np.array_equal(r[0], ll) and np.array_equal(r[1], dd)
         if e > s:  # the device's per-iteration block size is exact (squeeze.c:492)
-            pos0 = np.concatenate([TXT[:0], b""])  # noqa: F841
             llc, dc = zref.histogram(ll, dd)
             h = np.concatenate([llc, dc]).astype(np.uint32)
-            assert lib.dynamic_block_bits(h, device=False) <= int(c) or True
+            assert lib.dynamic_block_bits(h, device=False) == int(c)
+            assert ref.block_size(TXT[s:e], ll, dd, 0, len(ll), 2) == float(c)
 
 
 def test_device_block_bits(lib):

@@ -34,17 +34,18 @@ class Stats(C.Structure):
                                            "ms_greedy", "ms_iterate", "ms_pack", "ms_h2d", "ms_d2h",
                                            "ms_host_split", "ms_host_emit", "ms_host_other", "ms_total")] + \
                [(n, C.c_uint64) for n in ("launches", "match_positions", "iterate_positions",
-                                          "iterate_steps", "h2d_bytes", "d2h_bytes")]
+                                          "iterate_steps", "h2d_bytes", "d2h_bytes")] + \
+               [("cyc_sum", C.c_uint64 * 6), ("cyc_max", C.c_uint64 * 6), ("max_block_positions", C.c_uint64)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n.startswith("cyc_") else getattr(self, n)) for n, _ in self._fields_}
 
 
 EXPORTS = ["ZopfliInitOptions", "ZopfliCompress", "ZopfliDeflate", "ZopfliDeflatePart",
            "ZopfliGzipCompress", "ZopfliZlibCompress", "ZopfliB200LZ77", "ZopfliB200LZ77Batch",
            "ZopfliB200MatchTable", "ZopfliB200DynamicBlockBits", "ZopfliB200HostBlockSplitLZ77",
            "ZopfliB200HostBlockSize", "ZopfliB200HostEmitBlock", "ZopfliB200HostLengthLimited",
-           "ZopfliB200DeflateSpan", "ZopfliB200AppendSpan", "ZopfliB200CompressDevice",
+           "ZopfliB200DeflateSpan", "ZopfliB200AppendSpan", "ZopfliB200Crc32", "ZopfliB200Crc32Combine", "ZopfliB200CompressDevice",
            "ZopfliB200GetStats", "ZopfliB200ResetStats", "ZopfliB200SetStream", "ZopfliB200Device",
            "ZopfliB200Version"]
 
@@ -96,6 +97,10 @@ class Library:
                                             C.POINTER(vp), C.POINTER(sz)]
         L.ZopfliB200AppendSpan.argtypes = [vp, sz, C.POINTER(C.c_ubyte), C.POINTER(vp), C.POINTER(sz)]
         L.ZopfliB200AppendSpan.restype = None
+        L.ZopfliB200Crc32.argtypes = [vp, sz]
+        L.ZopfliB200Crc32.restype = C.c_uint32
+        L.ZopfliB200Crc32Combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
+        L.ZopfliB200Crc32Combine.restype = C.c_uint32
         L.ZopfliB200GetStats.argtypes = [C.POINTER(Stats)]
         L.ZopfliB200SetStream.argtypes = [vp]
         L.ZopfliB200Version.restype = C.c_char_p
@@ -224,15 +229,27 @@ class Library:
         return rc, out
 
     # ---- sharding ----
-    def deflate_span(self, data, mb_begin, mb_end, final, dev_ptr=None, host_ptr=None, nbytes=None, **kw) -> bytes:
+    def deflate_span(self, data, mb_begin, mb_end, final, **kw) -> bytes:
+        """span of master blocks [mb_begin, mb_end) of `data` (1,000,000-byte units)"""
+        a = _pad(data)
+        start = min(len(data), mb_begin * MASTER_BLOCK_SIZE)
+        end = min(len(data), mb_end * MASTER_BLOCK_SIZE)
+        return self.deflate_span_ptr(a.ctypes.data, len(data), start, end, final, **kw)
+
+    def deflate_span_ptr(self, host_ptr, nbytes, start, end, final, dev_ptr=None, **kw) -> bytes:
+        """span of bytes [start, end) of a raw host buffer; bytes before `start` are the halo"""
         o = self.options(**kw)
-        if host_ptr is None:
-            a = _pad(data)
-            host_ptr, nbytes = a.ctypes.data, len(data)
         out, n = C.c_void_p(None), C.c_size_t(0)
-        self.lib.ZopfliB200DeflateSpan(C.byref(o), host_ptr, nbytes, dev_ptr, mb_begin, mb_end, final,
-                                       C.byref(out), C.byref(n))
+        rc = self.lib.ZopfliB200DeflateSpan(C.byref(o), host_ptr, nbytes, dev_ptr, start, end, final,
+                                            C.byref(out), C.byref(n))
+        assert rc == 0
         return self._take(out, n)
+
+    def crc32(self, host_ptr, nbytes) -> int:
+        return int(self.lib.ZopfliB200Crc32(host_ptr, nbytes))
+
+    def crc32_combine(self, crc1, crc2, len2) -> int:
+        return int(self.lib.ZopfliB200Crc32Combine(crc1, crc2, len2))
 
     def splice_spans(self, spans, prefix=b"") -> tuple[bytes, int]:
         out, n, bp = C.c_void_p(None), C.c_size_t(0), C.c_ubyte(0)

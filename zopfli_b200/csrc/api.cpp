@@ -248,18 +248,21 @@ void ZopfliDeflatePart(const ZopfliOptions* options, int btype, int final, const
 }
 
 int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in, size_t insize,
-                          const unsigned char* dev_in, size_t mb_begin, size_t mb_end, int final,
+                          const unsigned char* dev_in, size_t start, size_t end, int final,
                           unsigned char** span, size_t* spansize) {
   std::vector<Piece> pieces;
-  auto units = master_units(insize, mb_begin, mb_end);
+  std::vector<std::pair<size_t, size_t>> units;
+  if (end > insize || start > end) return 1;
+  for (size_t a = start; a < end; a += kMasterBlock) units.push_back({a, a + kMasterBlock < end ? a + kMasterBlock : end});
+  if (units.empty() && insize == 0) units.push_back({0, 0});
   if (units.empty()) return 0;
   size_t base = 0;
   if (dev_in) {
     Engine::get().set_input_device(dev_in, insize);
   } else {
-    base = units.front().first > (size_t)kWindow ? units.front().first - kWindow : 0;
+    base = start > (size_t)kWindow ? start - kWindow : 0;
     base &= ~(size_t)15;
-    Engine::get().set_input_host(in + base, units.back().second - base);
+    Engine::get().set_input_host(in + base, end - base);
   }
   deflate_units(options, 2, final != 0, in, units, base, pieces);
   for (auto& p : pieces) {
@@ -274,6 +277,9 @@ int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in,
   }
   return 0;
 }
+
+uint32_t ZopfliB200Crc32(const unsigned char* data, size_t size) { return crc32_parallel(data, size); }
+uint32_t ZopfliB200Crc32Combine(uint32_t crc1, uint32_t crc2, uint64_t len2) { return crc32_combine(crc1, crc2, len2); }
 
 void ZopfliB200AppendSpan(const unsigned char* span, size_t spansize, unsigned char* bp, unsigned char** out,
                           size_t* outsize) {
@@ -416,6 +422,8 @@ void ZopfliB200GetStats(ZopfliB200Stats* o) {
   o->ms_total = g_total_ms;
   o->launches = e.launches; o->match_positions = e.match_positions; o->iterate_positions = e.iterate_positions;
   o->iterate_steps = e.iterate_steps; o->h2d_bytes = e.h2d_bytes; o->d2h_bytes = e.d2h_bytes;
+  for (int k = 0; k < 6; k++) { o->cyc_sum[k] = e.cyc_sum[k]; o->cyc_max[k] = e.cyc_max[k]; }
+  o->max_block_positions = e.max_block_positions;
 }
 
 void ZopfliB200ResetStats(void) {

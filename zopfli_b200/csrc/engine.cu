@@ -417,6 +417,9 @@ void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out) {
     }
     if (js[i].flags & 2) { fprintf(stderr, "zopfli-b200: corrupted length chain in block %zu\n", i); abort(); }
     if (ranges[i].mode == 1) {
+      uint64_t tot = 0, cur = 0;
+      for (int k = 0; k < 6; k++) { m.st_acc.cyc_sum[k] += js[i].cyc[k]; tot += js[i].cyc[k]; cur += m.st_acc.cyc_max[k]; }
+      if (tot > cur) { for (int k = 0; k < 6; k++) m.st_acc.cyc_max[k] = js[i].cyc[k]; m.st_acc.max_block_positions = L.segs[i].npos; }
       m.st_acc.iterate_positions += L.segs[i].npos;
       m.st_acc.iterate_steps += (uint64_t)L.segs[i].npos * ranges[i].numiterations;
     }

@@ -25,6 +25,9 @@ struct EngineStats {  // accumulated since the last reset; times from CUDA event
   uint64_t launches;
   uint64_t match_positions, iterate_positions, iterate_steps;  // steps = positions x iterations
   uint64_t h2d_bytes, d2h_bytes;
+  uint64_t cyc_sum[6];   // k_iterate phase cycles summed over blocks (model, DP, trace, follow, cost, stats)
+  uint64_t cyc_max[6];   // same for the block with the largest total (the critical path)
+  uint64_t max_block_positions;
 };
 
 class Engine {

@@ -178,6 +178,9 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
   uint32_t best_size = 0;
   const int niter = fixed ? 1 : sd.numiterations;
   int it = 0;
+  long long cyc[6] = {0, 0, 0, 0, 0, 0};
+  long long tk = clock64();
+#define ZB_TICK(i) do { long long t_ = clock64(); cyc[i] += t_ - tk; tk = t_; } while (0)
 
   for (; it < niter && !(flags & 1); it++) {
     // ------------------------------------------------------------------ model constants
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       (void)first_dist_of_symbol;
     }
     const double cost258 = (double)(0 + 0) + s.lencost[258] + s.dcost[0];  // costmodel(258, 1)
+    ZB_TICK(0);
 
     // ------------------------------------------------------------------ forward DP
     for (int t = lane; t < 512; t += 32) { s.ringc[t] = (float)1e30; s.ringl[t] = 0; }
@@ -320,6 +324,7 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       __syncwarp();
     }
 
+    ZB_TICK(1);
     // ------------------------------------------------------------------ trace back
     uint32_t cursor = nb + 1;  // path[cursor .. nb+1) holds the symbols in order
     {
@@ -344,6 +349,7 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       }
     }
     const uint32_t nsym = nb + 1 - cursor;
+    ZB_TICK(2);
 
     // ------------------------------------------------------------------ follow path + histogram
     uint16_t* cl = b.st_ll[curbuf] + sd.pos_off;
@@ -380,12 +386,14 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       }
     }
     __syncwarp();
+    ZB_TICK(3);
     if (fixed) { bestbuf = curbuf; best_size = nsym; bestcost = 0; it++; break; }
     if (lane == 0) s.hist[256] = 1;  // deflate.c:575 and squeeze.c:409
     __syncwarp();
 
     // ------------------------------------------------------------------ block size, best, statistics
     const uint64_t cost = warp_dynamic_bits(s, scratch, lane);  // squeeze.c:492
+    ZB_TICK(4);
     if (cost < bestcost) {  // squeeze.c:496-501
       int t = curbuf; curbuf = bestbuf; bestbuf = t;
       best_size = nsym;
@@ -434,9 +442,11 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       __syncwarp();
     }
     lastcost = cost;
+    ZB_TICK(5);
   }
 
   if (lane == 0) {
+    for (int i = 0; i < 6; i++) js->cyc[i] = (uint64_t)cyc[i];
     js->best_size = best_size;
     js->best_buf = (uint32_t)bestbuf;
     js->best_cost = bestcost;

@@ -59,7 +59,7 @@ struct JobState {   // per segment, written by k_greedy / k_iterate
   uint32_t flags;        // bit0: log table overflow (needs host assistance)
   uint32_t iters_done;
   uint64_t best_cost;
-  uint64_t pad;
+  uint64_t cyc[6];       // SM cycles spent in: model, DP, trace, follow, block cost, statistics
 };
 
 struct Batch {
@@ -393,11 +393,14 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
         else if (s <= c) { c = s; do_switch = true; }
         const uint32_t keep = (c == 31) ? 0xffffffffu : ((1u << (c + 1)) - 1);
         const uint32_t impmask = __ballot_sync(0xffffffffu, improved) & keep;
-        if (improved && lane <= c) {
-          uint32_t slot = nruns + __popc(impmask & ((1u << lane) - 1));
+        // a candidate that only reaches length 2 moves `best` but owns no usable length
+        const bool rec = improved && m >= (uint32_t)kMinMatch;
+        const uint32_t recmask = __ballot_sync(0xffffffffu, rec) & keep;
+        if (rec && lane <= c) {
+          uint32_t slot = nruns + __popc(recmask & ((1u << lane) - 1));
           myruns[slot] = run_pack(m, dist);  // lengths (pm_excl, m] first reached at `dist`
         }
-        nruns += __popc(impmask);
+        nruns += __popc(recmask);
         if (impmask) {
           int last = 31 - __clz((int)impmask);
           bestdist = __shfl_sync(0xffffffffu, dist, last);
@@ -428,8 +431,6 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
       if (lane == 0) b.mlen[o] = (uint16_t)(best >= (uint32_t)kMinMatch ? best : 0);
       uint32_t* dst = b.runs + o * kRunSlots;
       if (best < (uint32_t)kMinMatch) nruns = 0;
-      // runs reaching only length < 3 never exist on their own: the first run's len_end >= 3
-      // unless best < 3; entries are stored as found (first run covers lengths 2..m, harmless)
       if (nruns <= (uint32_t)kRunSlots) {
         if (lane < (uint32_t)kRunSlots) dst[lane] = lane < nruns ? myruns[lane] : 0u;
       } else {
