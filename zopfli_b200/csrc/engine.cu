@@ -74,7 +74,7 @@ struct Engine::Impl {
   const uint8_t* d_in = nullptr;
   uint64_t insize = 0;
   // batch arenas
-  DevBuf segs, keywork, poswork, order, hv, hv2, idx1, idx2, rank1, rank2, bkt1, bkt2, ld, mlen, runs,
+  DevBuf segs, keywork, poswork, order, hv, hv2, idx1, idx2, rank1, rank2, bkt1, bkt2, ld, mlen, runs, dsx,
       ovf, la, path, st[4], jobs, scratch, out_ll, out_d, counters, logtab, misc;
   uint32_t ovf_cap = 1u << 22;
   std::thread log_thread;
@@ -225,6 +225,7 @@ struct Engine::Impl {
     if (L.any_parse) {
       mlen.ensure(L.npos * 2 + 64);
       runs.ensure(L.npos * kRunSlots * 4 + 64);
+      dsx.ensure(L.npos * 32 + 64);
       ovf.ensure((size_t)ovf_cap * 4);
       la.ensure((L.npos + ns) * 2 + 64);
       path.ensure((L.npos + ns) * 2 + 64);
@@ -248,6 +249,7 @@ struct Engine::Impl {
     b.ld = ld.as<uint32_t>();
     b.mlen = mlen.as<uint16_t>();
     b.runs = runs.as<uint32_t>();
+    b.dsx = dsx.as<uint8_t>();
     b.ovf = ovf.as<uint32_t>();
     b.ovf_used = counters.as<uint32_t>();
     b.ovf_cap = ovf_cap;
@@ -471,7 +473,7 @@ void Engine::match_table(uint64_t instart, uint64_t inend, std::vector<uint16_t>
       for (uint32_t k = std::max<uint32_t>(prev + 1, 3); k <= run_len(e); k++) sublen[j * 259 + k] = (uint16_t)run_dist(e);
       prev = run_len(e);
     };
-    if (h_mlen[j] >= 3) {
+    if ((h_mlen[j] & 0x7fff) >= 3) {
       for (int r2 = 0; r2 < kRunSlots; r2++) {
         uint32_t e = h_runs[j * kRunSlots + r2];
         if (r2 == kRunSlots - 1 && (e & kOverflowBit)) {

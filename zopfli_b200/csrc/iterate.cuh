@@ -19,19 +19,53 @@
 
 namespace zb {
 
+struct DpStage {                       // forward-DP working set
+  uint2 ring[512];                     // {cost as float bits, best incoming length} per target
+  uint32_t runs[3][32 * kRunSlots];    // TMA-staged run lists, 3 groups of 32 positions
+  uint8_t dsx[3][32 * 32];             // TMA-staged first-round distance symbols
+};
+struct CostStage {                     // block-size working set
+  uint32_t cnt2[320];                  // RLE-smoothed copies (ll: [0,288), d: [288,320))
+  uint8_t len[2][320];                 // code lengths: set 0 plain, set 1 smoothed
+};
 struct IterSmem {
   double llcost[kNumLL];   // ll_symbols
   double dcost[kNumD];     // d_symbols
   double lencost[260];     // llcost[length_symbol(k)]
-  float ringc[512];
-  uint16_t ringl[512];
-  uint32_t stage[2][32 * kRunSlots];  // run lists of 2 x 32 positions
+  double t0[30 * 32];      // first-round edge costs: t0[dsym*32 + l] = cost(3+l, dist of dsym)
+  union __align__(16) {
+    DpStage dp;
+    CostStage cs;
+    uint16_t win[1024];    // trace-back window
+  } u;
+  __align__(8) uint64_t mbar[3];
   uint32_t hist[320];
   uint32_t stats[320], last[320], bests[320];
-  uint32_t cnt2[320];      // RLE-smoothed copies (ll: [0,288), d: [288,320))
-  uint8_t len[2][320];     // code lengths: set 0 plain, set 1 smoothed
-  uint16_t win[1024];
 };
+
+// ---- mbarrier / bulk-copy (TMA 1-D) primitives ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
 
 __device__ __forceinline__ double warp_min_first(double v, int& idx) {
   // minimum with the smallest index among equals (sequential strict-< scan order)
@@ -75,21 +109,21 @@ __device__ uint64_t warp_dynamic_bits(IterSmem& s, uint8_t* scratch, uint32_t la
     const bool isd = lane & 1, smooth = lane >= 2;
     const int n = isd ? kNumD : kNumLL;
     const uint32_t* src = s.hist + (isd ? 288 : 0);
-    uint32_t* c2 = s.cnt2 + (isd ? 288 : 0);
+    uint32_t* c2 = s.u.cs.cnt2 + (isd ? 288 : 0);
     PmBig* pb = (PmBig*)(scratch + (size_t)lane * (kIterScratch / 4));
     if (smooth) {
       for (int i = 0; i < n; i++) c2[i] = src[i];
       optimize_for_rle(n, c2, pb->good);
       src = c2;
     }
-    uint8_t* out = s.len[smooth ? 1 : 0] + (isd ? 288 : 0);
+    uint8_t* out = s.u.cs.len[smooth ? 1 : 0] + (isd ? 288 : 0);
     length_limited<kNumLL, 15>(src, n, 15, out, pb->pm);
     if (isd) patch_distance_codes(out);
   }
   __syncwarp();
   uint32_t tsz = 0xffffffffu;
   if (lane < 16) {
-    const uint8_t* l = s.len[lane >> 3];
+    const uint8_t* l = s.u.cs.len[lane >> 3];
     tsz = encode_tree_size(l, l + 288, (lane & 1) != 0, (lane & 2) != 0, (lane & 4) != 0);
   }
   // min over lanes 0..7 and 8..15 (deflate.c:277-290)
@@ -108,8 +142,8 @@ __device__ uint64_t warp_dynamic_bits(IterSmem& s, uint8_t* scratch, uint32_t la
     if (i < 288) { use = i < 256 || (i >= 257 && i < 286); extra = i >= 257 ? length_symbol_extra_bits(i) : 0; }
     else { use = (i - 288) < 30; extra = dist_symbol_extra_bits(i - 288); }
     if (use) {
-      sb0 += (uint64_t)(s.len[0][i] + extra) * c;
-      sb1 += (uint64_t)(s.len[1][i] + extra) * c;
+      sb0 += (uint64_t)(s.u.cs.len[0][i] + extra) * c;
+      sb1 += (uint64_t)(s.u.cs.len[1][i] + extra) * c;
     }
   }
 #pragma unroll
@@ -117,8 +151,8 @@ __device__ uint64_t warp_dynamic_bits(IterSmem& s, uint8_t* scratch, uint32_t la
     sb0 += __shfl_xor_sync(0xffffffffu, sb0, d);
     sb1 += __shfl_xor_sync(0xffffffffu, sb1, d);
   }
-  const uint64_t size0 = tree0 + sb0 + s.len[0][256];
-  const uint64_t size1 = tree1 + sb1 + s.len[1][256];
+  const uint64_t size0 = tree0 + sb0 + s.u.cs.len[0][256];
+  const uint64_t size1 = tree1 + sb1 + s.u.cs.len[1][256];
   return 3 + (size1 < size0 ? size1 : size0);  // deflate.c:553-559
 }
 
@@ -142,11 +176,18 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
   const uint8_t* in = b.in + sd.instart;
   const uint16_t* sameg = b.same_g + sd.instart;
   const uint16_t* mlen = b.mlen + sd.pos_off;
-  const uint4* runs4 = (const uint4*)(b.runs + sd.pos_off * kRunSlots);
+  const uint32_t* runs_g = b.runs + sd.pos_off * kRunSlots;
+  const uint8_t* dsx_g = b.dsx + sd.pos_off * 32;
   uint8_t* scratch = b.scratch + (size_t)seg * kIterScratch;
   const bool fixed = sd.mode == 2;
   int curbuf = 0, bestbuf = 1;
   uint32_t flags = 0;
+  if (lane == 0) {
+    for (int i = 0; i < 3; i++) mbar_init(&s.mbar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t seq_base = 0;  // running group sequence number: stage = seq % 3, parity = (seq / 3) & 1
 
   // ---- initial statistics: greedy parse (squeeze.c:481-482) or the fixed tree (:125-140) ----
   if (!fixed) {
@@ -186,6 +227,11 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
     // ------------------------------------------------------------------ model constants
     for (int k = lane; k < 260; k += 32) s.lencost[k] = k >= 3 && k <= 258 ? s.llcost[length_symbol(k)] : 0.0;
     __syncwarp();
+    for (int i = lane; i < 30 * 32; i += 32) {  // GetCostStat squeeze.c:146-157 for lengths 3..34
+      const int ds = i >> 5, k = 3 + (i & 31);
+      s.t0[i] = (double)(length_extra_bits(k) + dist_symbol_extra_bits(ds)) + s.lencost[k] + s.dcost[ds];
+    }
+    __syncwarp();
     double mincost;
     {
       double bv = 1e30; int bi = 0x7fffffff;
@@ -214,82 +260,90 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
     ZB_TICK(0);
 
     // ------------------------------------------------------------------ forward DP
-    for (int t = lane; t < 512; t += 32) { s.ringc[t] = (float)1e30; s.ringl[t] = 0; }
+    // Push form.  c_j lives in a register: c_{j+1} = min(pending[j+1], literal from j), where
+    // pending[j+1] was completed two steps earlier, so the loop-carried chain is one DADD, one
+    // compare and one rounding.  Run lists / first-round distance symbols arrive through
+    // cp.async.bulk (TMA) two groups of 32 positions ahead.
+    const uint32_t kInf = __float_as_uint((float)1e30);
+    for (int t = lane; t < 512; t += 32) s.u.dp.ring[t] = make_uint2(kInf, 0u);
     __syncwarp();
-    if (lane == 0) s.ringc[0] = 0.f;
+    if (lane == 0) s.u.dp.ring[0].x = 0u;
     __syncwarp();
     {
-      uint32_t skip_left = 0;
+      const uint32_t ngroups = (nb + 31) >> 5;
+      auto issue_group = [&](uint32_t g, uint32_t seq) {  // lane 0
+        const uint32_t cnt = nb - g * 32 < 32u ? nb - g * 32 : 32u;
+        const uint32_t st = seq % 3, bytes = cnt * 32;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&s.mbar[st], bytes * 2);
+        bulk_g2s(s.u.dp.dsx[st], dsx_g + (size_t)g * 1024, bytes, &s.mbar[st]);
+        bulk_g2s(s.u.dp.runs[st], runs_g + (size_t)g * 256, bytes, &s.mbar[st]);
+      };
+      auto load_scalars = [&](uint32_t j0) -> uint32_t {  // (mlen16 << 8) | byte of position j0+lane
+        const uint32_t p = j0 + lane;
+        return p < nb ? ((uint32_t)mlen[p] << 8) | in[p] : 0u;
+      };
+      if (lane == 0) {
+        issue_group(0, seq_base);
+        if (ngroups > 1) issue_group(1, seq_base + 1);
+      }
+      uint32_t pk_cur = 0, pk_next = load_scalars(0);
+      uint32_t skip_left = 0, cur_st = 0;
       bool just_finished = false;
-      // lane-distributed per-position scalars for the current group of 32 positions
-      uint32_t g_mlen = 0, g_byte = 0, g_same = 0;
-      auto load_group_scalars = [&](uint32_t j0, uint32_t& m, uint32_t& by, uint32_t& sm) {
-        uint32_t p = j0 + lane;
-        if (p < nb) {
-          m = mlen[p];
-          by = in[p];
-          uint32_t sg = sameg[p];
-          uint32_t clip = nb - 1 - p;
-          sm = sg > clip ? clip : sg;
-        } else { m = 0; by = 0; sm = 0; }
-      };
-      auto load_group_runs = [&](uint32_t j0, int bufi) {
-        uint32_t p = j0 + lane;
-        uint4 a = make_uint4(0, 0, 0, 0), c = a;
-        if (p < nb) { a = runs4[(uint64_t)p * 2]; c = runs4[(uint64_t)p * 2 + 1]; }
-        uint4* dst = (uint4*)&s.stage[bufi][lane * kRunSlots];
-        dst[0] = a; dst[1] = c;
-      };
-      uint32_t n_mlen, n_byte, n_same;
-      load_group_scalars(0, n_mlen, n_byte, n_same);
-      load_group_runs(0, 0);
-      __syncwarp();
+      double cj = 0.0;
+      float pend_n = (float)1e30;  // pending[1]
       for (uint32_t j = 0; j < nb; j++) {
         const uint32_t jl = j & 31;
         if (jl == 0) {
-          g_mlen = n_mlen; g_byte = n_byte; g_same = n_same;
-          load_group_scalars(j + 32, n_mlen, n_byte, n_same);
-          load_group_runs(j + 32, ((j >> 5) + 1) & 1);
-          if (j > 0) la[j - 32 + lane] = s.ringl[(j - 32 + lane) & 511];
+          const uint32_t g = j >> 5, seq = seq_base + g;
+          cur_st = seq % 3;
+          mbar_wait(&s.mbar[cur_st], (seq / 3) & 1);
           __syncwarp();
+          if (lane == 0 && g + 2 < ngroups) issue_group(g + 2, seq + 2);
+          pk_cur = pk_next;
+          pk_next = load_scalars(j + 32);
+          if (j > 0) la[j - 32 + lane] = (uint16_t)s.u.dp.ring[(j - 32 + lane) & 511].y;
         }
-        const float cjf = s.ringc[j & 511];
-        const double cj = (double)cjf;
-        if (lane == 0) s.ringc[(j + 259) & 511] = (float)1e30;  // target j+259 is first touched at j+1
-        const uint32_t same_j = __shfl_sync(0xffffffffu, g_same, jl);
-        // long-run shortcut squeeze.c:251-271
-        if (skip_left == 0 && !just_finished && same_j > (uint32_t)kMaxMatch * 2 && j > (uint32_t)kMaxMatch + 1 &&
-            j + kMaxMatch * 2 + 1 < nb) {
-          uint32_t sg = sameg[j - kMaxMatch];
-          uint32_t clip = nb - 1 - (j - kMaxMatch);
-          if ((sg > clip ? clip : sg) > (uint32_t)kMaxMatch) skip_left = kMaxMatch;
-        }
+        const float pend1 = pend_n;
+        pend_n = __uint_as_float(s.u.dp.ring[(j + 2) & 511].x);   // complete: sources <= j-1 are done
+        if (lane == 0) s.u.dp.ring[(j + 259) & 511].x = kInf;     // target j+259 is first touched at j+1
+        const uint32_t pk = __shfl_sync(0xffffffffu, pk_cur, jl);
+        // long-run shortcut squeeze.c:251-271 (candidate flag precomputed by k_match)
+        if ((pk & ((uint32_t)kShortcutFlag << 8)) && skip_left == 0 && !just_finished) skip_left = kMaxMatch;
         if (skip_left > 0) {
-          if (lane == 0) {
-            s.ringc[(j + kMaxMatch) & 511] = (float)(cj + cost258);
-            s.ringl[(j + kMaxMatch) & 511] = kMaxMatch;
-          }
+          if (lane == 0) s.u.dp.ring[(j + kMaxMatch) & 511] = make_uint2(__float_as_uint((float)(cj + cost258)), (uint32_t)kMaxMatch);
           skip_left--;
           just_finished = skip_left == 0;
           __syncwarp();
+          cj = (double)pend1;  // a skipped source contributes no literal edge
           continue;
         }
         just_finished = false;
-        const uint32_t ml = __shfl_sync(0xffffffffu, g_mlen, jl);
-        const uint32_t byte = __shfl_sync(0xffffffffu, g_byte, jl);
-        if (lane == 0) {  // literal squeeze.c:277-284
-          double nc = s.llcost[byte] + cj;
-          uint32_t tg = (j + 1) & 511;
-          if (nc < (double)s.ringc[tg]) { s.ringc[tg] = (float)nc; s.ringl[tg] = 1; }
+        // literal squeeze.c:277-284 (every lane computes the same values)
+        const double lit = s.llcost[pk & 255u] + cj;
+        const bool take = lit < (double)pend1;
+        const float cnf = take ? (float)lit : pend1;
+        if (take && lane == 0) s.u.dp.ring[(j + 1) & 511] = make_uint2(__float_as_uint(cnf), 1u);
+        // lengths squeeze.c:286-302; first round: lane l owns length 3+l
+        const double mc = mincost + cj;
+        const uint32_t room = nb - j;
+        {
+          const uint32_t ds = s.u.dp.dsx[cur_st][jl * 32 + lane];
+          const uint32_t k = 3 + lane;
+          if (ds != 0xffu && k <= room) {
+            const uint32_t tg = (j + k) & 511;
+            const float pend = __uint_as_float(s.u.dp.ring[tg].x);
+            const double nc = s.t0[ds * 32 + lane] + cj;
+            if (!((double)pend <= mc) && nc < (double)pend) s.u.dp.ring[tg] = make_uint2(__float_as_uint((float)nc), k);
+          }
         }
-        uint32_t kend = nb - j;
-        if (ml < kend) kend = ml;
-        if (kend >= (uint32_t)kMinMatch) {  // squeeze.c:286-302
-          const uint4* st = (const uint4*)&s.stage[(j >> 5) & 1][jl * kRunSlots];
-          const uint4 ea = st[0], eb = st[1];
-          const double mc = mincost + cj;
+        const uint32_t ml = (pk >> 8) & 0x7fffu;
+        if (ml > 34u) {  // further rounds: run-list lookup
+          const uint32_t kend = ml < room ? ml : room;
+          const uint4* st4 = (const uint4*)&s.u.dp.runs[cur_st][jl * kRunSlots];
+          const uint4 ea = st4[0], eb = st4[1];
           const bool ovf = (eb.w & kOverflowBit) != 0;
-          for (uint32_t k = 3 + lane; k <= kend; k += 32) {
+          for (uint32_t k = 35 + lane; k <= kend; k += 32) {
             uint32_t e = eb.w;
             if (ovf) {
               e = 0;
@@ -306,21 +360,21 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
             if (k <= run_len(ea.y)) e = ea.y;
             if (k <= run_len(ea.x)) e = ea.x;
             const uint32_t tg = (j + k) & 511;
-            const float pend = s.ringc[tg];
+            const float pend = __uint_as_float(s.u.dp.ring[tg].x);
             if ((double)pend <= mc) continue;  // squeeze.c:293
             const int dsym = (int)run_dsym(e);
             double nc = (double)(length_extra_bits((int)k) + dist_symbol_extra_bits(dsym)) + s.lencost[k] + s.dcost[dsym];
             nc = nc + cj;
-            if (nc < (double)pend) { s.ringc[tg] = (float)nc; s.ringl[tg] = (uint16_t)k; }
+            if (nc < (double)pend) s.u.dp.ring[tg] = make_uint2(__float_as_uint((float)nc), k);
           }
         }
         __syncwarp();
+        cj = (double)cnf;
       }
-      // flush the tail of length_array, entries [flushed, nb]
-      const uint32_t flushed = nb & ~31u;
-      // when nb is a multiple of 32 the group [nb-32, nb) has not been flushed yet
-      const uint32_t from = (nb & 31u) == 0 && nb > 0 ? nb - 32 : flushed;
-      for (uint32_t t = from + lane; t <= nb; t += 32) la[t] = s.ringl[t & 511];
+      seq_base += ngroups;
+      // flush the tail of length_array, entries [from, nb]
+      const uint32_t from = (nb & 31u) == 0 ? nb - 32 : (nb & ~31u);
+      for (uint32_t t = from + lane; t <= nb; t += 32) la[t] = (uint16_t)s.u.dp.ring[t & 511].y;
       __syncwarp();
     }
 
@@ -331,11 +385,11 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       uint32_t idx = nb;
       while (idx > 0) {
         const uint32_t wlo = idx >= 1024u ? idx - 1023u : 0u;
-        for (uint32_t t = lane; t <= idx - wlo; t += 32) s.win[t] = la[wlo + t];
+        for (uint32_t t = lane; t <= idx - wlo; t += 32) s.u.win[t] = la[wlo + t];
         __syncwarp();
         if (lane == 0) {
           while (idx > 0 && idx >= wlo) {
-            uint32_t l = s.win[idx - wlo];
+            uint32_t l = s.u.win[idx - wlo];
             if (l == 0 || l > idx) { l = 1; flags |= 2; }  // corrupted chain guard (never expected)
             path[--cursor] = (uint16_t)l;
             idx -= l;

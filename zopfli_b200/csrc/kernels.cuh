@@ -28,6 +28,7 @@
 
 namespace zb {
 
+constexpr uint16_t kShortcutFlag = 0x8000;
 constexpr int kRunSlots = 8;           // table slots per position (cache.c:30-33 keeps 8 too)
 constexpr uint32_t kOverflowBit = 0x80000000u;
 constexpr int kSameTile = 1024;        // tile of the run-length pre-pass
@@ -79,8 +80,11 @@ struct Batch {
   uint32_t* bkt2;
   // match table
   uint32_t* ld;     // [npos] (len << 16) | dist of the longest match (raw, len may be 0/1/2)
-  uint16_t* mlen;   // [npos] longest length or 0 (optimal segments only)
+  uint16_t* mlen;   // [npos] longest length or 0 (optimal segments only); bit 15 = long-run
+                    // shortcut candidate (squeeze.c:251-257 condition, a pure function of position)
   uint32_t* runs;   // [npos][kRunSlots]
+  uint8_t* dsx;     // [npos][32] distance symbol of the shortest-distance match of length 3+l,
+                    // 0xff if longer than the longest match (the DP's 32-wide first round)
   uint32_t* ovf;    // overflow arena: [count, entries...]
   uint32_t* ovf_used;
   uint32_t ovf_cap;
@@ -428,9 +432,27 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
     const uint64_t o = sd.pos_off + j;
     if (lane == 0) b.ld[o] = (best << 16) | bestdist;
     if (sd.mode != 0) {
-      if (lane == 0) b.mlen[o] = (uint16_t)(best >= (uint32_t)kMinMatch ? best : 0);
-      uint32_t* dst = b.runs + o * kRunSlots;
       if (best < (uint32_t)kMinMatch) nruns = 0;
+      if (lane == 0) {
+        uint16_t ml = (uint16_t)(best >= (uint32_t)kMinMatch ? best : 0);
+        // squeeze.c:251-257: same[i] > 516 && i > instart+259 && i+517 < inend && same[i-258] > 258
+        if (j > (uint32_t)kMaxMatch + 1 && j + kMaxMatch * 2 + 1 < sd.npos) {
+          const uint64_t p = sd.instart + j;
+          uint64_t s0 = b.same_g[p], c0 = sd.inend - 1 - p;
+          uint64_t s1 = b.same_g[p - kMaxMatch], c1 = sd.inend - 1 - (p - kMaxMatch);
+          if ((s0 > c0 ? c0 : s0) > (uint64_t)kMaxMatch * 2 && (s1 > c1 ? c1 : s1) > (uint64_t)kMaxMatch) ml |= kShortcutFlag;
+        }
+        b.mlen[o] = ml;
+      }
+      {  // first-round distance symbols: lane l serves length 3+l
+        const uint32_t k = 3 + lane;
+        uint32_t v = 0xff;
+        if (nruns && k <= best) {
+          for (uint32_t r = 0; r < nruns; r++) { uint32_t e = myruns[r]; if (run_len(e) >= k) { v = run_dsym(e); break; } }
+        }
+        b.dsx[o * 32 + lane] = (uint8_t)v;
+      }
+      uint32_t* dst = b.runs + o * kRunSlots;
       if (nruns <= (uint32_t)kRunSlots) {
         if (lane < (uint32_t)kRunSlots) dst[lane] = lane < nruns ? myruns[lane] : 0u;
       } else {
