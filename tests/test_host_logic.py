@@ -77,7 +77,7 @@ def test_split_and_block_sizes(ref, host):
             for bt in (0, 1, 2, -1):
                 assert ref.block_size(data, ll, dd, a, b, bt) == host.host_block_size(ll, dd, a, b, bt)
     # small store: the `lz77->size > 1000` quirk of deflate.c:615 goes the other way
-    ll, dd = ref.lz77(TXT, 0, 1800, 3)
+    ll, dd = ref.lz77(TXT, 2000, 3200, 3)
     assert len(ll) < 1000
     for a, b in [(0, len(ll)), (10, 200), (5, 6)]:
         assert ref.block_size(TXT, ll, dd, a, b, -1) == host.host_block_size(ll, dd, a, b, -1)

@@ -1,9 +1,10 @@
 """Deterministic synthetic inputs for parity tests and bench.py (no corpora ship with the box).
 
 Shapes follow SURVEY.md section 8(d) / Appendix C:
-  synth_text    -- Zipf-distributed word soup with punctuation, ~3 % markup tokens and topic
-                   drift every 64 KiB (so the block splitter finds real split points); the
-                   stand-in for enwik8 (config C2) and the 1 GiB web-text corpus (C3).
+  synth_text    -- a stream of wiki-like pages (XML page headers, per-page topic vocabulary over a
+                   Zipf word soup, prose / link-list / table / citation / foreign-language
+                   sections), so the statistics drift and the block splitter finds real split
+                   points; the stand-in for enwik8 (config C2) and the 1 GiB web-text corpus (C3).
   synth_binary  -- ELF-like mix of constant runs, mutated records and text (config C4).
   adv_*         -- adversarial inputs that exercise the exact walk semantics of
                    ZopfliFindLongestMatch (/root/reference/src/zopfli/lz77.c:407-542): the
@@ -34,12 +35,30 @@ def _vocab(rng: np.random.Generator, nwords: int):
     return flat, starts, lens
 
 
+_SECTION_KINDS = ("prose", "links", "table", "refs", "foreign")
+
+
+def _tokens_to_bytes(tok, space, flat, all_starts, all_lens):
+    tl = all_lens[tok]
+    tot = tl + space
+    offs = np.concatenate([[0], np.cumsum(tot)[:-1]])
+    total = int(offs[-1] + tot[-1]) if len(tok) else 0
+    buf = np.full(total, 32, dtype=np.uint8)
+    idx_tok = np.repeat(np.arange(len(tok)), tl)
+    within = np.arange(int(tl.sum())) - np.repeat(np.cumsum(tl) - tl, tl)
+    buf[offs[idx_tok] + within] = flat[all_starts[tok][idx_tok] + within]
+    return buf
+
+
 def synth_text(nbytes: int, seed: int = 2) -> bytes:
-    """~2.7-3 bits/byte under zopfli, enwik8-like structure. Vectorised: ~10 MB/s."""
+    """enwik8-like stand-in: a stream of "wiki pages" of very different sizes, each with its own
+    topic vocabulary and a mix of section kinds (prose, link lists, tables, citation blocks,
+    foreign-language text) wrapped in XML page headers.  The statistics drift from page to page and
+    section to section, so the block splitter finds real split points (uniform word soup leaves
+    1 MB blocks unsplit and overstates the critical path).  ~2.6-3 bits/byte."""
     rng = np.random.default_rng(seed)
     nwords = 65536
     flat, starts, lens = _vocab(rng, nwords)
-    # append markup tokens and punctuation "words" to the vocabulary
     extra = _MARKUP + [b".", b",", b";", b"\n\n", b"\n", b"?", b"(", b")", b":", b"1", b"19", b"200"]
     ex_flat = np.frombuffer(b"".join(extra), dtype=np.uint8)
     ex_lens = np.array([len(e) for e in extra], dtype=np.int64)
@@ -48,45 +67,100 @@ def synth_text(nbytes: int, seed: int = 2) -> bytes:
     all_starts = np.concatenate([starts[:-1], ex_starts])
     all_lens = np.concatenate([lens, ex_lens])
     n_markup = len(_MARKUP)
-    # Zipf(s=1.1) rank weights
+    n_punct = len(extra) - n_markup
     ranks = np.arange(1, nwords + 1, dtype=np.float64)
-    w = ranks ** -1.1
-    cdf = np.cumsum(w / w.sum())
-    perm = rng.permutation(nwords)  # rank -> word id, re-ranked by topic drift
-    out = np.empty(nbytes + 64, dtype=np.uint8)
+    cdf = np.cumsum(ranks ** -1.1)
+    cdf /= cdf[-1]
+    foreign_map = np.arange(256, dtype=np.uint8)
+    foreign_map[97:123] = rng.permutation(np.arange(97, 123)).astype(np.uint8)  # another letter distribution
+    out = np.empty(nbytes + 1024, dtype=np.uint8)
     pos = 0
-    chunk = 64 * 1024
+    page_id = 1000
     while pos < nbytes:
-        # topic drift: re-rank 5 % of the vocabulary every 64 KiB
-        k = nwords // 20
-        a = rng.integers(0, nwords, k)
-        b = rng.integers(0, min(nwords, 4096), k)  # promote some words into the head
-        perm[a], perm[b] = perm[b].copy(), perm[a].copy()
-        nw = chunk // 5 + 64
-        r = np.searchsorted(cdf, rng.random(nw))
-        ids = perm[np.minimum(r, nwords - 1)]
-        kind = rng.random(nw)
-        # 3 % markup, ~12 % punctuation, rest words
-        tok = ids.copy()
-        mk = kind < 0.03
-        tok[mk] = nwords + rng.integers(0, n_markup, int(mk.sum()))
-        pk = (kind >= 0.03) & (kind < 0.15)
-        tok[pk] = nwords + n_markup + rng.choice(len(extra) - n_markup, int(pk.sum()),
-                                                 p=_punct_p(len(extra) - n_markup))
-        tl = all_lens[tok]
-        # words are followed by a space unless the next token is punctuation
-        space = np.ones(nw, dtype=np.int64)
-        space[:-1][pk[1:]] = 0
-        tot = tl + space
-        offs = np.concatenate([[0], np.cumsum(tot)[:-1]])
-        total = int(offs[-1] + tot[-1])
-        buf = np.full(total, 32, dtype=np.uint8)
-        # gather word bytes
-        idx_tok = np.repeat(np.arange(nw), tl)
-        within = np.arange(int(tl.sum())) - np.repeat(np.cumsum(tl) - tl, tl)
-        buf[offs[idx_tok] + within] = flat[all_starts[tok][idx_tok] + within]
-        take = min(total, nbytes - pos)
-        out[pos:pos + take] = buf[:take]
+        page_id += int(rng.integers(1, 40))
+        page_len = int(min(200000, max(600, rng.lognormal(9.0, 1.1))))
+        topic = rng.integers(0, nwords, 300)
+        title = flat[all_starts[topic[0]]: all_starts[topic[0]] + all_lens[topic[0]]].tobytes()
+        hdr = (b"  <page>\n    <title>" + title.capitalize() + b"</title>\n    <id>%d</id>\n    <revision>\n"
+               b"      <id>%d</id>\n      <timestamp>200%d-%02d-%02dT%02d:%02d:%02dZ</timestamp>\n"
+               b"      <contributor>\n        <username>" % (page_id, page_id * 7 + 13, rng.integers(2, 7),
+                                                              rng.integers(1, 13), rng.integers(1, 29), rng.integers(0, 24),
+                                                              rng.integers(0, 60), rng.integers(0, 60))
+               + flat[all_starts[topic[1]]: all_starts[topic[1]] + all_lens[topic[1]]].tobytes()
+               + b"</username>\n        <id>%d</id>\n      </contributor>\n      <text xml:space=\"preserve\">" % rng.integers(1, 99999))
+        parts = [np.frombuffer(hdr, dtype=np.uint8)]
+        made = len(hdr)
+        # page-level mixture of section kinds
+        kind_p = rng.dirichlet([4.0, 0.7, 0.5, 0.6, 0.25])
+        while made < page_len:
+            kind = _SECTION_KINDS[int(rng.choice(5, p=kind_p))]
+            sec_len = int(min(page_len - made + 200, max(200, rng.lognormal(7.3, 0.9))))
+            nw = sec_len // 5 + 8
+            r = np.searchsorted(cdf, rng.random(nw))
+            ids = np.minimum(r, nwords - 1)
+            tsel = rng.random(nw) < (0.45 if kind != "foreign" else 0.2)
+            ids[tsel] = topic[rng.integers(0, len(topic), int(tsel.sum()))]
+            tok = ids.copy()
+            space = np.ones(nw, dtype=np.int64)
+            u = rng.random(nw)
+            if kind in ("prose", "foreign"):
+                mk = u < 0.02
+                pk = (u >= 0.02) & (u < 0.14)
+                tok[mk] = nwords + rng.integers(0, n_markup, int(mk.sum()))
+                tok[pk] = nwords + n_markup + rng.choice(n_punct, int(pk.sum()), p=_punct_p(n_punct))
+                space[:-1][pk[1:]] = 0
+                buf = _tokens_to_bytes(tok, space, flat, all_starts, all_lens)
+                if kind == "foreign":
+                    buf = foreign_map[buf]
+            elif kind == "links":
+                # "* [[word word]]\n" lists
+                nl = nw // 3
+                w = _tokens_to_bytes(tok[: nl * 2], np.tile([1, 0], nl), flat, all_starts, all_lens)
+                lines = []
+                o = 0
+                l2 = (all_lens[tok[: nl * 2]] + np.tile([1, 0], nl)).reshape(nl, 2).sum(1)
+                for ln in l2[: min(nl, 400)]:
+                    lines.append(b"* [[" + w[o:o + ln].tobytes() + b"]]\n")
+                    o += ln
+                buf = np.frombuffer(b"".join(lines), dtype=np.uint8)
+            elif kind == "table":
+                rows = min(300, nw // 4)
+                cells = rng.integers(0, 100000, (rows, 3))
+                words = _tokens_to_bytes(tok[:rows], np.zeros(rows, dtype=np.int64), flat, all_starts, all_lens)
+                wl = all_lens[tok[:rows]]
+                o = 0
+                lines = [b"{| class=\"wikitable\"\n"]
+                for i in range(rows):
+                    lines.append(b"|-\n| %d || %d.%d || " % (cells[i, 0], cells[i, 1] % 1000, cells[i, 2] % 10)
+                                 + words[o:o + wl[i]].tobytes() + b"\n")
+                    o += wl[i]
+                lines.append(b"|}\n")
+                buf = np.frombuffer(b"".join(lines), dtype=np.uint8)
+            else:  # refs
+                nr = min(120, nw // 8)
+                w = _tokens_to_bytes(tok[: nr * 4], np.zeros(nr * 4, dtype=np.int64), flat, all_starts, all_lens)
+                wl = all_lens[tok[: nr * 4]].reshape(nr, 4)
+                o = 0
+                lines = []
+                for i in range(nr):
+                    a0, a1, a2, a3 = (int(x) for x in wl[i])
+                    lines.append(b"<ref>{{cite web|url=http://www." + w[o:o + a0].tobytes() + b".com/" + w[o + a0:o + a0 + a1].tobytes()
+                                 + b"|title=" + w[o + a0 + a1:o + a0 + a1 + a2].tobytes().capitalize() + b" "
+                                 + w[o + a0 + a1 + a2:o + a0 + a1 + a2 + a3].tobytes()
+                                 + b"|accessdate=200%d-%02d-%02d}}</ref>\n" % (rng.integers(2, 7), rng.integers(1, 13), rng.integers(1, 29)))
+                    o += a0 + a1 + a2 + a3
+                buf = np.frombuffer(b"".join(lines), dtype=np.uint8)
+            buf = buf[:sec_len]
+            parts.append(buf)
+            made += len(buf)
+            if rng.random() < 0.5:
+                head = b"\n\n== " + flat[all_starts[topic[2]]: all_starts[topic[2]] + all_lens[topic[2]]].tobytes().capitalize() + b" ==\n"
+                parts.append(np.frombuffer(head, dtype=np.uint8))
+                made += len(head)
+        parts.append(np.frombuffer(b"</text>\n    </revision>\n  </page>\n", dtype=np.uint8))
+        page = np.concatenate(parts)
+        take = min(len(page), nbytes - pos)
+        out[pos:pos + take] = page[:take]
         pos += take
     return out[:nbytes].tobytes()
 

@@ -19,8 +19,9 @@
 
 namespace zb {
 
+struct RingEnt { double c; uint32_t len; uint32_t pad; };   // cost (float-representable) + best incoming length
 struct DpStage {                       // forward-DP working set
-  uint2 ring[512];                     // {cost as float bits, best incoming length} per target
+  RingEnt ring[512];                   // per target position, indexed mod 512
   uint32_t runs[3][32 * kRunSlots];    // TMA-staged run lists, 3 groups of 32 positions
   uint8_t dsx[3][32 * 32];             // TMA-staged first-round distance symbols
 };
@@ -56,6 +57,38 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+// predicated 16-byte store of a ring entry {cost, len}
+__device__ __forceinline__ void sts_ring_if(uint32_t a, double c, uint32_t len, bool p) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q st.shared.v2.b64 [%0], {%1, %2}; }" ::"r"(a),
+               "l"(__double_as_longlong(c)), "l"((long long)len), "r"((uint32_t)p)
+               : "memory");
+}
+__device__ __forceinline__ void sts_f64_if(uint32_t a, double c, bool p) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.f64 [%0], %1; }" ::"r"(a), "d"(c), "r"((uint32_t)p) : "memory");
+}
+// (double)(float)x for 0 <= x < 3e38 outside the float-denormal range: round-to-nearest-even on
+// the 29 low mantissa bits, in integer arithmetic (keeps the conversion pipe off the cost chain)
+__device__ __forceinline__ double round_to_f32(double x) {
+  long long b = __double_as_longlong(x);
+  b += 0x0FFFFFFFLL + ((b >> 29) & 1);
+  b &= ~0x1FFFFFFFLL;
+  return __longlong_as_double(b);
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -262,15 +295,22 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
     // ------------------------------------------------------------------ forward DP
     // Push form.  c_j lives in a register: c_{j+1} = min(pending[j+1], literal from j), where
     // pending[j+1] was completed two steps earlier, so the loop-carried chain is one DADD, one
-    // compare and one rounding.  Run lists / first-round distance symbols arrive through
+    // compare and an integer rounding.  Costs sit in the ring as doubles that are exactly
+    // float-representable (the reference stores floats and widens them on every use,
+    // squeeze.c:222,278-300).  The per-source pushes only depend on c_j and are written branch-free
+    // so they interleave with the chain.  Run lists / first-round distance symbols arrive through
     // cp.async.bulk (TMA) two groups of 32 positions ahead.
-    const uint32_t kInf = __float_as_uint((float)1e30);
-    for (int t = lane; t < 512; t += 32) s.u.dp.ring[t] = make_uint2(kInf, 0u);
+    const double kInfD = (double)(float)1e30;  // ZOPFLI_LARGE_FLOAT stored to float, squeeze.c:243
+    for (int t = lane; t < 512; t += 32) { s.u.dp.ring[t].c = kInfD; s.u.dp.ring[t].len = 0; }
     __syncwarp();
-    if (lane == 0) s.u.dp.ring[0].x = 0u;
+    if (lane == 0) s.u.dp.ring[0].c = 0.0;
     __syncwarp();
     {
       const uint32_t ngroups = (nb + 31) >> 5;
+      const uint32_t ring_a = smem_u32(&s.u.dp.ring[0]);
+      const uint32_t t0_a = smem_u32(&s.t0[0]) + lane * 8;
+      const uint32_t ll_a = smem_u32(&s.llcost[0]);
+      const uint32_t dsx_a = smem_u32(&s.u.dp.dsx[0][0]) + lane;
       auto issue_group = [&](uint32_t g, uint32_t seq) {  // lane 0
         const uint32_t cnt = nb - g * 32 < 32u ? nb - g * 32 : 32u;
         const uint32_t st = seq % 3, bytes = cnt * 32;
@@ -288,10 +328,12 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
         if (ngroups > 1) issue_group(1, seq_base + 1);
       }
       uint32_t pk_cur = 0, pk_next = load_scalars(0);
-      uint32_t skip_left = 0, cur_st = 0;
+      uint32_t skip_left = 0, cur_st = 0, dsx_row = 0;
       bool just_finished = false;
-      double cj = 0.0;
-      float pend_n = (float)1e30;  // pending[1]
+      double cj = 0.0, pend1 = kInfD;  // pending[1]
+      uint32_t pkn = __shfl_sync(0xffffffffu, pk_next, 0);
+      double ll_n = lds_f64(ll_a + (pkn & 255u) * 8);
+      const uint32_t k0 = 3 + lane;
       for (uint32_t j = 0; j < nb; j++) {
         const uint32_t jl = j & 31;
         if (jl == 0) {
@@ -302,79 +344,83 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
           if (lane == 0 && g + 2 < ngroups) issue_group(g + 2, seq + 2);
           pk_cur = pk_next;
           pk_next = load_scalars(j + 32);
-          if (j > 0) la[j - 32 + lane] = (uint16_t)s.u.dp.ring[(j - 32 + lane) & 511].y;
+          if (j > 0) la[j - 32 + lane] = (uint16_t)s.u.dp.ring[(j - 32 + lane) & 511].len;
+          dsx_row = dsx_a + cur_st * 1024;
         }
-        const float pend1 = pend_n;
-        pend_n = __uint_as_float(s.u.dp.ring[(j + 2) & 511].x);   // complete: sources <= j-1 are done
-        if (lane == 0) s.u.dp.ring[(j + 259) & 511].x = kInf;     // target j+259 is first touched at j+1
-        const uint32_t pk = __shfl_sync(0xffffffffu, pk_cur, jl);
+        const uint32_t pk = pkn;
+        const double llb = ll_n;
+        // pending[j+2] is complete (sources <= j-1 are done) and untouched by this step
+        const double pend_n = lds_f64(ring_a + ((j + 2) & 511) * 16);
+        sts_f64_if(ring_a + ((j + 259) & 511) * 16, kInfD, lane == 0);  // target j+259: first touched at j+1
         // long-run shortcut squeeze.c:251-271 (candidate flag precomputed by k_match)
         if ((pk & ((uint32_t)kShortcutFlag << 8)) && skip_left == 0 && !just_finished) skip_left = kMaxMatch;
+        double cnext;
         if (skip_left > 0) {
-          if (lane == 0) s.u.dp.ring[(j + kMaxMatch) & 511] = make_uint2(__float_as_uint((float)(cj + cost258)), (uint32_t)kMaxMatch);
+          sts_ring_if(ring_a + ((j + kMaxMatch) & 511) * 16, round_to_f32(cj + cost258), (uint32_t)kMaxMatch, lane == 0);
           skip_left--;
           just_finished = skip_left == 0;
-          __syncwarp();
-          cj = (double)pend1;  // a skipped source contributes no literal edge
-          continue;
-        }
-        just_finished = false;
-        // literal squeeze.c:277-284 (every lane computes the same values)
-        const double lit = s.llcost[pk & 255u] + cj;
-        const bool take = lit < (double)pend1;
-        const float cnf = take ? (float)lit : pend1;
-        if (take && lane == 0) s.u.dp.ring[(j + 1) & 511] = make_uint2(__float_as_uint(cnf), 1u);
-        // lengths squeeze.c:286-302; first round: lane l owns length 3+l
-        const double mc = mincost + cj;
-        const uint32_t room = nb - j;
-        {
-          const uint32_t ds = s.u.dp.dsx[cur_st][jl * 32 + lane];
-          const uint32_t k = 3 + lane;
-          if (ds != 0xffu && k <= room) {
-            const uint32_t tg = (j + k) & 511;
-            const float pend = __uint_as_float(s.u.dp.ring[tg].x);
-            const double nc = s.t0[ds * 32 + lane] + cj;
-            if (!((double)pend <= mc) && nc < (double)pend) s.u.dp.ring[tg] = make_uint2(__float_as_uint((float)nc), k);
+          cnext = pend1;  // a skipped source contributes no literal edge
+        } else {
+          just_finished = false;
+          // literal squeeze.c:277-284 (every lane computes the same values)
+          const double lit = llb + cj;
+          const bool take = lit < pend1;
+          cnext = take ? round_to_f32(lit) : pend1;
+          sts_ring_if(ring_a + ((j + 1) & 511) * 16, cnext, 1u, take && lane == 0);
+          // lengths squeeze.c:286-302; first round: lane l owns length 3+l
+          const double mc = mincost + cj;
+          const uint32_t room = nb - j;
+          {
+            const uint32_t ds = lds_u8(dsx_row + jl * 32);
+            const uint32_t tga = ring_a + ((j + k0) & 511) * 16;
+            const double pend = lds_f64(tga);
+            const double nc = lds_f64(t0_a + (ds < 30u ? ds : 0u) * 256) + cj;
+            const bool ok = (ds != 0xffu) & (k0 <= room) & !(pend <= mc) & (nc < pend);
+            sts_ring_if(tga, round_to_f32(nc), k0, ok);
           }
-        }
-        const uint32_t ml = (pk >> 8) & 0x7fffu;
-        if (ml > 34u) {  // further rounds: run-list lookup
-          const uint32_t kend = ml < room ? ml : room;
-          const uint4* st4 = (const uint4*)&s.u.dp.runs[cur_st][jl * kRunSlots];
-          const uint4 ea = st4[0], eb = st4[1];
-          const bool ovf = (eb.w & kOverflowBit) != 0;
-          for (uint32_t k = 35 + lane; k <= kend; k += 32) {
-            uint32_t e = eb.w;
-            if (ovf) {
-              e = 0;
-              if (k > run_len(eb.z)) {
-                uint32_t off = eb.w & ~kOverflowBit, cnt = b.ovf[off];
-                for (uint32_t r = 0; r < cnt; r++) { uint32_t x = b.ovf[off + 1 + r]; if (run_len(x) >= k) { e = x; break; } }
+          const uint32_t ml = (pk >> 8) & 0x7fffu;
+          if (ml > 34u) {  // further rounds: run-list lookup
+            const uint32_t kend = ml < room ? ml : room;
+            const uint4* st4 = (const uint4*)&s.u.dp.runs[cur_st][jl * kRunSlots];
+            const uint4 ea = st4[0], eb = st4[1];
+            const bool ovf = (eb.w & kOverflowBit) != 0;
+            for (uint32_t k = 35 + lane; k <= kend; k += 32) {
+              uint32_t e = eb.w;
+              if (ovf) {
+                e = 0;
+                if (k > run_len(eb.z)) {
+                  uint32_t off = eb.w & ~kOverflowBit, cnt = b.ovf[off];
+                  for (uint32_t r = 0; r < cnt; r++) { uint32_t x = b.ovf[off + 1 + r]; if (run_len(x) >= k) { e = x; break; } }
+                }
               }
+              if (k <= run_len(eb.z)) e = eb.z;
+              if (k <= run_len(eb.y)) e = eb.y;
+              if (k <= run_len(eb.x)) e = eb.x;
+              if (k <= run_len(ea.w)) e = ea.w;
+              if (k <= run_len(ea.z)) e = ea.z;
+              if (k <= run_len(ea.y)) e = ea.y;
+              if (k <= run_len(ea.x)) e = ea.x;
+              const uint32_t tga = ring_a + ((j + k) & 511) * 16;
+              const double pend = lds_f64(tga);
+              if (pend <= mc) continue;  // squeeze.c:293
+              const int dsym = (int)run_dsym(e);
+              double nc = (double)(length_extra_bits((int)k) + dist_symbol_extra_bits(dsym)) + s.lencost[k] + s.dcost[dsym];
+              nc = nc + cj;
+              sts_ring_if(tga, round_to_f32(nc), k, nc < pend);
             }
-            if (k <= run_len(eb.z)) e = eb.z;
-            if (k <= run_len(eb.y)) e = eb.y;
-            if (k <= run_len(eb.x)) e = eb.x;
-            if (k <= run_len(ea.w)) e = ea.w;
-            if (k <= run_len(ea.z)) e = ea.z;
-            if (k <= run_len(ea.y)) e = ea.y;
-            if (k <= run_len(ea.x)) e = ea.x;
-            const uint32_t tg = (j + k) & 511;
-            const float pend = __uint_as_float(s.u.dp.ring[tg].x);
-            if ((double)pend <= mc) continue;  // squeeze.c:293
-            const int dsym = (int)run_dsym(e);
-            double nc = (double)(length_extra_bits((int)k) + dist_symbol_extra_bits(dsym)) + s.lencost[k] + s.dcost[dsym];
-            nc = nc + cj;
-            if (nc < (double)pend) s.u.dp.ring[tg] = make_uint2(__float_as_uint((float)nc), k);
           }
         }
         __syncwarp();
-        cj = (double)cnf;
+        // operands of the next step's chain
+        pkn = __shfl_sync(0xffffffffu, jl == 31 ? pk_next : pk_cur, (j + 1) & 31);
+        ll_n = lds_f64(ll_a + (pkn & 255u) * 8);
+        cj = cnext;
+        pend1 = pend_n;
       }
       seq_base += ngroups;
       // flush the tail of length_array, entries [from, nb]
       const uint32_t from = (nb & 31u) == 0 ? nb - 32 : (nb & ~31u);
-      for (uint32_t t = from + lane; t <= nb; t += 32) la[t] = (uint16_t)s.u.dp.ring[t & 511].y;
+      for (uint32_t t = from + lane; t <= nb; t += 32) la[t] = (uint16_t)s.u.dp.ring[t & 511].len;
       __syncwarp();
     }
 
