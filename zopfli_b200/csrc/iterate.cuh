@@ -21,9 +21,10 @@ namespace zb {
 
 struct RingEnt { double c; uint32_t len; uint32_t pad; };   // cost (float-representable) + best incoming length
 struct DpStage {                       // forward-DP working set
-  RingEnt ring[512];                   // per target position, indexed mod 512
-  uint32_t runs[3][32 * kRunSlots];    // TMA-staged run lists, 3 groups of 32 positions
-  uint8_t dsx[3][32 * 32];             // TMA-staged first-round distance symbols
+  RingEnt ring[512];                   // pending costs of targets >= j+35 (long edges only), mod 512
+  uint32_t runs[4][32 * kRunSlots];    // TMA-staged run lists, ring of 4 groups of 32 positions
+  uint8_t dsx[4][32 * 32];             // TMA-staged first-round distance symbols (128-row ring)
+  double gl[64];                       // literal cost of the byte at each position (2 groups)
 };
 struct CostStage {                     // block-size working set
   uint32_t cnt2[320];                  // RLE-smoothed copies (ll: [0,288), d: [288,320))
@@ -33,13 +34,13 @@ struct IterSmem {
   double llcost[kNumLL];   // ll_symbols
   double dcost[kNumD];     // d_symbols
   double lencost[260];     // llcost[length_symbol(k)]
-  double t0[30 * 32];      // first-round edge costs: t0[dsym*32 + l] = cost(3+l, dist of dsym)
+  double t0[31 * 32];      // first-round edge costs: t0[dsym*32 + l] = cost(3+l, dist of dsym); row 30 = +inf
   union __align__(16) {
     DpStage dp;
     CostStage cs;
     uint16_t win[1024];    // trace-back window
   } u;
-  __align__(8) uint64_t mbar[3];
+  __align__(8) uint64_t mbar[4];
   uint32_t hist[320];
   uint32_t stats[320], last[320], bests[320];
 };
@@ -216,11 +217,11 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
   int curbuf = 0, bestbuf = 1;
   uint32_t flags = 0;
   if (lane == 0) {
-    for (int i = 0; i < 3; i++) mbar_init(&s.mbar[i], 1);
+    for (int i = 0; i < 4; i++) mbar_init(&s.mbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint32_t seq_base = 0;  // running group sequence number: stage = seq % 3, parity = (seq / 3) & 1
+  uint32_t seq_base = 0;  // running group sequence number: stage = seq & 3, parity = (seq >> 2) & 1
 
   // ---- initial statistics: greedy parse (squeeze.c:481-482) or the fixed tree (:125-140) ----
   if (!fixed) {
@@ -260,9 +261,9 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
     // ------------------------------------------------------------------ model constants
     for (int k = lane; k < 260; k += 32) s.lencost[k] = k >= 3 && k <= 258 ? s.llcost[length_symbol(k)] : 0.0;
     __syncwarp();
-    for (int i = lane; i < 30 * 32; i += 32) {  // GetCostStat squeeze.c:146-157 for lengths 3..34
+    for (int i = lane; i < 31 * 32; i += 32) {  // GetCostStat squeeze.c:146-157 for lengths 3..34
       const int ds = i >> 5, k = 3 + (i & 31);
-      s.t0[i] = (double)(length_extra_bits(k) + dist_symbol_extra_bits(ds)) + s.lencost[k] + s.dcost[ds];
+      s.t0[i] = ds < 30 ? (double)(length_extra_bits(k) + dist_symbol_extra_bits(ds)) + s.lencost[k] + s.dcost[ds] : 1e300;
     }
     __syncwarp();
     double mincost;
@@ -293,95 +294,126 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
     ZB_TICK(0);
 
     // ------------------------------------------------------------------ forward DP
-    // Push form.  c_j lives in a register: c_{j+1} = min(pending[j+1], literal from j), where
-    // pending[j+1] was completed two steps earlier, so the loop-carried chain is one DADD, one
-    // compare and an integer rounding.  Costs sit in the ring as doubles that are exactly
-    // float-representable (the reference stores floats and widens them on every use,
-    // squeeze.c:222,278-300).  The per-source pushes only depend on c_j and are written branch-free
-    // so they interleave with the chain.  Run lists / first-round distance symbols arrive through
-    // cp.async.bulk (TMA) two groups of 32 positions ahead.
+    // Push form with a REGISTER WINDOW.  At step j lane l holds the pending cost (and the length
+    // that produced it) of target j+3+l, complete for sources < j.  Source j relaxes all 32 of them
+    // at once (lane l owns length 3+l), lane 0's value -- now complete for every length edge --
+    // leaves the window to meet the literal edge two steps later, and the window shifts down by
+    // one lane.  The short edges therefore never touch memory; only edges longer than 34
+    // (rare outside byte runs) go through a shared-memory ring whose entry joins the window at
+    // lane 31 when its target comes within reach.  Costs are doubles that are exactly
+    // float-representable: the reference stores floats and widens them on every use
+    // (squeeze.c:222,278-300); rounding is done in integer arithmetic.  Relaxation order per
+    // target is source order, as in the reference, so ties resolve identically.
     const double kInfD = (double)(float)1e30;  // ZOPFLI_LARGE_FLOAT stored to float, squeeze.c:243
     for (int t = lane; t < 512; t += 32) { s.u.dp.ring[t].c = kInfD; s.u.dp.ring[t].len = 0; }
     __syncwarp();
-    if (lane == 0) s.u.dp.ring[0].c = 0.0;
-    __syncwarp();
     {
+      const uint32_t full = 0xffffffffu;
       const uint32_t ngroups = (nb + 31) >> 5;
       const uint32_t ring_a = smem_u32(&s.u.dp.ring[0]);
       const uint32_t t0_a = smem_u32(&s.t0[0]) + lane * 8;
-      const uint32_t ll_a = smem_u32(&s.llcost[0]);
+      const uint32_t gl_a = smem_u32(&s.u.dp.gl[0]);
       const uint32_t dsx_a = smem_u32(&s.u.dp.dsx[0][0]) + lane;
+      const uint32_t k0 = 3 + lane;
       auto issue_group = [&](uint32_t g, uint32_t seq) {  // lane 0
         const uint32_t cnt = nb - g * 32 < 32u ? nb - g * 32 : 32u;
-        const uint32_t st = seq % 3, bytes = cnt * 32;
+        const uint32_t st = seq & 3, bytes = cnt * 32;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&s.mbar[st], bytes * 2);
         bulk_g2s(s.u.dp.dsx[st], dsx_g + (size_t)g * 1024, bytes, &s.mbar[st]);
         bulk_g2s(s.u.dp.runs[st], runs_g + (size_t)g * 256, bytes, &s.mbar[st]);
       };
-      auto load_scalars = [&](uint32_t j0) -> uint32_t {  // (mlen16 << 8) | byte of position j0+lane
-        const uint32_t p = j0 + lane;
-        return p < nb ? ((uint32_t)mlen[p] << 8) | in[p] : 0u;
+      // staging buffer and barrier of group g are both (seq_base + g) & 3; sequence numbers run on
+      // without gaps across iterations so every barrier completes one phase per use
+      const uint32_t joff = (seq_base & 3u) * 32u;  // row-ring offset of this iteration's row 0
+      // per-group scalars: mlen16 (lane-distributed) and literal costs staged in shared memory
+      uint32_t mk_cur = 0, mk_next = 0;      // mlen16 of position 32g+lane for the current / next group
+      uint32_t flag_cur = 0, flag_next = 0;  // ballot: position needs the general path (shortcut flag or mlen > 34)
+      auto acquire = [&](uint32_t g, uint32_t seq) {  // make group g readable; all lanes
+        mbar_wait(&s.mbar[seq & 3], (seq >> 2) & 1);
+        const uint32_t p = g * 32 + lane;
+        uint32_t m16 = 0;
+        double lc = 0.0;
+        if (p < nb) { m16 = mlen[p]; lc = s.llcost[in[p]]; }
+        s.u.dp.gl[(g & 1) * 32 + lane] = lc;
+        mk_next = m16;
+        flag_next = __ballot_sync(full, (m16 & kShortcutFlag) != 0 || (m16 & 0x7fffu) > 34u);
+        __syncwarp();
       };
       if (lane == 0) {
         issue_group(0, seq_base);
         if (ngroups > 1) issue_group(1, seq_base + 1);
+        if (ngroups > 2) issue_group(2, seq_base + 2);
       }
-      uint32_t pk_cur = 0, pk_next = load_scalars(0);
-      uint32_t skip_left = 0, cur_st = 0, dsx_row = 0;
+      acquire(0, seq_base);
+      mk_cur = mk_next; flag_cur = flag_next;
+      // register window and pipeline state
+      double w = kInfD; uint32_t wl = 0;               // pending(j+3+lane)
+      double e1c = kInfD, e2c = kInfD; uint32_t e1l = 0, e2l = 0;  // pending(j+2), pending(j+1)
+      double cj = 0.0;
+      uint32_t mylen = 0;                                // final length of position 32g+lane
+      uint32_t dirty_until = 0;                          // largest target that has a ring entry
+      uint32_t skip_left = 0;
       bool just_finished = false;
-      double cj = 0.0, pend1 = kInfD;  // pending[1]
-      uint32_t pkn = __shfl_sync(0xffffffffu, pk_next, 0);
-      double ll_n = lds_f64(ll_a + (pkn & 255u) * 8);
-      const uint32_t k0 = 3 + lane;
+      // operand prefetch pipeline: tv = t0 row value for step j, ds_n = dsx of row j+1
+      uint32_t ds_n = min(lds_u8(dsx_a + (joff & 127u) * 32), kNoEdge);
+      double tv = lds_f64(t0_a + ds_n * 256);
+      ds_n = nb > 1 ? min(lds_u8(dsx_a + ((1 + joff) & 127u) * 32), kNoEdge) : kNoEdge;
+      double llb = lds_f64(gl_a);
       for (uint32_t j = 0; j < nb; j++) {
         const uint32_t jl = j & 31;
-        if (jl == 0) {
-          const uint32_t g = j >> 5, seq = seq_base + g;
-          cur_st = seq % 3;
-          mbar_wait(&s.mbar[cur_st], (seq / 3) & 1);
-          __syncwarp();
-          if (lane == 0 && g + 2 < ngroups) issue_group(g + 2, seq + 2);
-          pk_cur = pk_next;
-          pk_next = load_scalars(j + 32);
-          if (j > 0) la[j - 32 + lane] = (uint16_t)s.u.dp.ring[(j - 32 + lane) & 511].len;
-          dsx_row = dsx_a + cur_st * 1024;
+        if (jl == 0 && j > 0) { mk_cur = mk_next; flag_cur = flag_next; }
+        if (jl == 28) {  // get the next group ready two steps before its rows are prefetched
+          const uint32_t g1 = (j >> 5) + 1;
+          if (g1 < ngroups) {
+            acquire(g1, seq_base + g1);
+            if (lane == 0 && g1 + 2 < ngroups) issue_group(g1 + 2, seq_base + g1 + 2);
+          } else {
+            flag_next = 0; mk_next = 0;
+          }
         }
-        const uint32_t pk = pkn;
-        const double llb = ll_n;
-        // pending[j+2] is complete (sources <= j-1 are done) and untouched by this step
-        const double pend_n = lds_f64(ring_a + ((j + 2) & 511) * 16);
-        sts_f64_if(ring_a + ((j + 259) & 511) * 16, kInfD, lane == 0);  // target j+259: first touched at j+1
-        // long-run shortcut squeeze.c:251-271 (candidate flag precomputed by k_match)
-        if ((pk & ((uint32_t)kShortcutFlag << 8)) && skip_left == 0 && !just_finished) skip_left = kMaxMatch;
-        double cnext;
-        if (skip_left > 0) {
-          sts_ring_if(ring_a + ((j + kMaxMatch) & 511) * 16, round_to_f32(cj + cost258), (uint32_t)kMaxMatch, lane == 0);
-          skip_left--;
-          just_finished = skip_left == 0;
-          cnext = pend1;  // a skipped source contributes no literal edge
-        } else {
-          just_finished = false;
+        if (jl == 31) la[j - 31 + lane] = (uint16_t)mylen;  // positions j-31..j are final
+        // prefetch operands of step j+1 (rows beyond the block read stale staging: harmless,
+        // those steps do not exist)
+        const double tv_n = lds_f64(t0_a + ds_n * 256);
+        const uint32_t ds_nn = min(lds_u8(dsx_a + ((j + 2 + joff) & 127) * 32), kNoEdge);  // clamp: rows past the block are stale
+        const double llb_n = lds_f64(gl_a + ((j + 1) & 63) * 8);
+        const bool general = ((flag_cur >> jl) & 1u) | (skip_left != 0) | just_finished | (j + 35 <= dirty_until);
+        double cnext; uint32_t lfin;
+        bool relax = true;
+        uint32_t ml = 0;
+        if (general) {
+          const uint32_t m16 = __shfl_sync(full, mk_cur, jl);
+          ml = m16 & 0x7fffu;
+          // long-run shortcut squeeze.c:251-271 (candidate flag precomputed by k_match)
+          if ((m16 & kShortcutFlag) && skip_left == 0 && !just_finished) skip_left = kMaxMatch;
+          if (skip_left > 0) {
+            // costs[j+258] = costs[j] + cost(258,1), unconditionally; no literal, no other edge
+            sts_ring_if(ring_a + ((j + kMaxMatch) & 511) * 16, round_to_f32(cj + cost258), (uint32_t)kMaxMatch, lane == 0);
+            if (j + kMaxMatch > dirty_until) dirty_until = j + kMaxMatch;
+            skip_left--;
+            just_finished = skip_left == 0;
+            relax = false;
+          } else {
+            just_finished = false;
+          }
+        }
+        if (relax) {
           // literal squeeze.c:277-284 (every lane computes the same values)
           const double lit = llb + cj;
-          const bool take = lit < pend1;
-          cnext = take ? round_to_f32(lit) : pend1;
-          sts_ring_if(ring_a + ((j + 1) & 511) * 16, cnext, 1u, take && lane == 0);
-          // lengths squeeze.c:286-302; first round: lane l owns length 3+l
+          const bool take = lit < e2c;
+          cnext = take ? round_to_f32(lit) : e2c;
+          lfin = take ? 1u : e2l;
+          // lengths 3..34 squeeze.c:286-302: lane l owns length 3+l
+          const double nc = tv + cj;
           const double mc = mincost + cj;
-          const uint32_t room = nb - j;
-          {
-            const uint32_t ds = lds_u8(dsx_row + jl * 32);
-            const uint32_t tga = ring_a + ((j + k0) & 511) * 16;
-            const double pend = lds_f64(tga);
-            const double nc = lds_f64(t0_a + (ds < 30u ? ds : 0u) * 256) + cj;
-            const bool ok = (ds != 0xffu) & (k0 <= room) & !(pend <= mc) & (nc < pend);
-            sts_ring_if(tga, round_to_f32(nc), k0, ok);
-          }
-          const uint32_t ml = (pk >> 8) & 0x7fffu;
-          if (ml > 34u) {  // further rounds: run-list lookup
+          const bool ok = !(w <= mc) & (nc < w);
+          w = ok ? round_to_f32(nc) : w;
+          wl = ok ? k0 : wl;
+          if (ml > 34u) {  // longer lengths: run-list lookup, pushed into the ring
+            const uint32_t room = nb - j;
             const uint32_t kend = ml < room ? ml : room;
-            const uint4* st4 = (const uint4*)&s.u.dp.runs[cur_st][jl * kRunSlots];
+            const uint4* st4 = (const uint4*)&s.u.dp.runs[((j >> 5) + seq_base) & 3][jl * kRunSlots];
             const uint4 ea = st4[0], eb = st4[1];
             const bool ovf = (eb.w & kOverflowBit) != 0;
             for (uint32_t k = 35 + lane; k <= kend; k += 32) {
@@ -404,23 +436,41 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
               const double pend = lds_f64(tga);
               if (pend <= mc) continue;  // squeeze.c:293
               const int dsym = (int)run_dsym(e);
-              double nc = (double)(length_extra_bits((int)k) + dist_symbol_extra_bits(dsym)) + s.lencost[k] + s.dcost[dsym];
-              nc = nc + cj;
-              sts_ring_if(tga, round_to_f32(nc), k, nc < pend);
+              double nc2 = (double)(length_extra_bits((int)k) + dist_symbol_extra_bits(dsym)) + s.lencost[k] + s.dcost[dsym];
+              nc2 = nc2 + cj;
+              sts_ring_if(tga, round_to_f32(nc2), k, nc2 < pend);
             }
+            if (j + kend > dirty_until) dirty_until = j + kend;
+          }
+        } else {
+          cnext = e2c;  // a skipped source contributes no literal edge
+          lfin = e2l;
+        }
+        if (lane == ((j + 1) & 31)) mylen = lfin;  // length_array[j+1]
+        // the window moves on: lane 0 leaves, lane 31 receives target j+35
+        const double xc = __shfl_sync(full, w, 0);
+        const uint32_t xl = __shfl_sync(full, wl, 0);
+        w = __shfl_down_sync(full, w, 1);
+        wl = __shfl_down_sync(full, wl, 1);
+        double inc = kInfD; uint32_t inl = 0;
+        if (general) {
+          __syncwarp();
+          if (j + 35 <= dirty_until) {  // ring entry of target j+35 (complete: its sources are <= j)
+            const uint32_t ra = ring_a + ((j + 35) & 511) * 16;
+            inc = lds_f64(ra);
+            inl = lds_u32(ra + 8);
+            sts_f64_if(ra, kInfD, lane == 31);  // free the slot for target j+35+512
+            __syncwarp();
           }
         }
-        __syncwarp();
-        // operands of the next step's chain
-        pkn = __shfl_sync(0xffffffffu, jl == 31 ? pk_next : pk_cur, (j + 1) & 31);
-        ll_n = lds_f64(ll_a + (pkn & 255u) * 8);
+        if (lane == 31) { w = inc; wl = inl; }
+        e2c = e1c; e2l = e1l; e1c = xc; e1l = xl;
         cj = cnext;
-        pend1 = pend_n;
+        tv = tv_n; ds_n = ds_nn; llb = llb_n;
       }
       seq_base += ngroups;
-      // flush the tail of length_array, entries [from, nb]
-      const uint32_t from = (nb & 31u) == 0 ? nb - 32 : (nb & ~31u);
-      for (uint32_t t = from + lane; t <= nb; t += 32) la[t] = (uint16_t)s.u.dp.ring[t & 511].len;
+      // flush the last (partial) group of length_array: positions 32*(nb>>5) .. nb
+      if (lane <= (nb & 31u)) la[(nb & ~31u) + lane] = (uint16_t)mylen;
       __syncwarp();
     }
 

@@ -29,6 +29,7 @@
 namespace zb {
 
 constexpr uint16_t kShortcutFlag = 0x8000;
+constexpr uint32_t kNoEdge = 30;       // dsx value for "no match of this length" (row 30 of the cost table is +inf)
 constexpr int kRunSlots = 8;           // table slots per position (cache.c:30-33 keeps 8 too)
 constexpr uint32_t kOverflowBit = 0x80000000u;
 constexpr int kSameTile = 1024;        // tile of the run-length pre-pass
@@ -83,8 +84,9 @@ struct Batch {
   uint16_t* mlen;   // [npos] longest length or 0 (optimal segments only); bit 15 = long-run
                     // shortcut candidate (squeeze.c:251-257 condition, a pure function of position)
   uint32_t* runs;   // [npos][kRunSlots]
-  uint8_t* dsx;     // [npos][32] distance symbol of the shortest-distance match of length 3+l,
-                    // 0xff if longer than the longest match (the DP's 32-wide first round)
+  uint8_t* dsx;     // [npos][32] distance symbol of the shortest-distance match of length 3+l, or
+                    // kNoEdge if 3+l exceeds the longest match / the block end (the DP's 32-wide
+                    // register window works on these)
   uint32_t* ovf;    // overflow arena: [count, entries...]
   uint32_t* ovf_used;
   uint32_t ovf_cap;
@@ -446,8 +448,8 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
       }
       {  // first-round distance symbols: lane l serves length 3+l
         const uint32_t k = 3 + lane;
-        uint32_t v = 0xff;
-        if (nruns && k <= best) {
+        uint32_t v = kNoEdge;
+        if (nruns && k <= best) {  // best <= inend - pos, so edges never leave the block
           for (uint32_t r = 0; r < nruns; r++) { uint32_t e = myruns[r]; if (run_len(e) >= k) { v = run_dsym(e); break; } }
         }
         b.dsx[o * 32 + lane] = (uint8_t)v;
