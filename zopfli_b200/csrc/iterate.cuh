@@ -351,7 +351,8 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       double w = kInfD; uint32_t wl = 0;               // pending(j+3+lane)
       double e1c = kInfD, e2c = kInfD; uint32_t e1l = 0, e2l = 0;  // pending(j+2), pending(j+1)
       double cj = 0.0;
-      uint32_t mylen = 0;                                // final length of position 32g+lane
+      uint32_t lfin_prev = 0;                            // length_array[j], recorded one step late
+      uint32_t mylen = 0;                                // length_array[32g+lane] of the current group
       uint32_t dirty_until = 0;                          // largest target that has a ring entry
       uint32_t skip_left = 0;
       bool just_finished = false;
@@ -360,36 +361,76 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       double tv = lds_f64(t0_a + ds_n * 256);
       ds_n = nb > 1 ? min(lds_u8(dsx_a + ((1 + joff) & 127u) * 32), kNoEdge) : kNoEdge;
       double llb = lds_f64(gl_a);
-      for (uint32_t j = 0; j < nb; j++) {
-        const uint32_t jl = j & 31;
-        if (jl == 0 && j > 0) { mk_cur = mk_next; flag_cur = flag_next; }
-        if (jl == 28) {  // get the next group ready two steps before its rows are prefetched
-          const uint32_t g1 = (j >> 5) + 1;
-          if (g1 < ngroups) {
-            acquire(g1, seq_base + g1);
-            if (lane == 0 && g1 + 2 < ngroups) issue_group(g1 + 2, seq_base + g1 + 2);
-          } else {
-            flag_next = 0; mk_next = 0;
-          }
+      // keep the shared-memory base addresses opaque so they stay in registers
+      uint32_t t0_r = t0_a, gl_r = gl_a, dsx_r = dsx_a, ring_r = ring_a;
+      asm volatile("" : "+r"(t0_r), "+r"(gl_r), "+r"(dsx_r), "+r"(ring_r));
+
+      // one step of the common case: no shortcut, no length > 34 at this position, no ring entry
+      // coming due.  Straight-line code: chain (cj -> cnext), window relax, window shift, operand
+      // prefetch for the next step.
+#define ZB_DP_FAST_STEP(J)                                                                        \
+      {                                                                                           \
+        const uint32_t j_ = (J);                                                                  \
+        const double tv_n_ = lds_f64(t0_r + ds_n * 256);                                          \
+        const uint32_t ds_nn_ = min(lds_u8(dsx_r + ((j_ + 2 + joff) & 127) * 32), kNoEdge);       \
+        const double llb_n_ = lds_f64(gl_r + ((j_ + 1) & 63) * 8);                                \
+        if (lane == (j_ & 31)) mylen = lfin_prev;                                                 \
+        const double lit_ = llb + cj;                                                             \
+        const bool take_ = lit_ < e2c;                                                            \
+        const double cnext_ = take_ ? round_to_f32(lit_) : e2c;                                   \
+        lfin_prev = take_ ? 1u : e2l;                                                             \
+        const double nc_ = tv + cj;                                                               \
+        const double mc_ = mincost + cj;                                                          \
+        const bool ok_ = !(w <= mc_) & (nc_ < w);                                                 \
+        w = ok_ ? round_to_f32(nc_) : w;                                                          \
+        wl = ok_ ? k0 : wl;                                                                       \
+        const double xc_ = __shfl_sync(full, w, 0);                                               \
+        const uint32_t xl_ = __shfl_sync(full, wl, 0);                                            \
+        w = __shfl_down_sync(full, w, 1);                                                         \
+        wl = __shfl_down_sync(full, wl, 1);                                                       \
+        if (lane == 31) { w = kInfD; wl = 0; }                                                    \
+        e2c = e1c; e2l = e1l; e1c = xc_; e1l = xl_;                                               \
+        cj = cnext_;                                                                              \
+        tv = tv_n_; ds_n = ds_nn_; llb = llb_n_;                                                  \
+      }
+
+      for (uint32_t g = 0; g < ngroups; g++) {
+        const uint32_t j0 = g * 32;
+        // ---- group start (uniform): flush, rotate, look ahead ----
+        if (g > 0) {
+          la[j0 - 32 + lane] = (uint16_t)mylen;  // positions of group g-1; position j0-1's length
+          // is still in lfin_prev?  no: it was recorded at step j0-1+... see below
+          mk_cur = mk_next; flag_cur = flag_next;
         }
-        if (jl == 31) la[j - 31 + lane] = (uint16_t)mylen;  // positions j-31..j are final
-        // prefetch operands of step j+1 (rows beyond the block read stale staging: harmless,
-        // those steps do not exist)
-        const double tv_n = lds_f64(t0_a + ds_n * 256);
-        const uint32_t ds_nn = min(lds_u8(dsx_a + ((j + 2 + joff) & 127) * 32), kNoEdge);  // clamp: rows past the block are stale
-        const double llb_n = lds_f64(gl_a + ((j + 1) & 63) * 8);
-        const bool general = ((flag_cur >> jl) & 1u) | (skip_left != 0) | just_finished | (j + 35 <= dirty_until);
-        double cnext; uint32_t lfin;
-        bool relax = true;
-        uint32_t ml = 0;
-        if (general) {
+        if (g + 1 < ngroups) {
+          acquire(g + 1, seq_base + g + 1);
+          if (lane == 0 && g + 3 < ngroups) issue_group(g + 3, seq_base + g + 3);
+        } else {
+          flag_next = 0; mk_next = 0;
+        }
+        const bool fast = flag_cur == 0 && skip_left == 0 && !just_finished && j0 + 35 > dirty_until && j0 + 32 <= nb;
+        if (fast) {
+#pragma unroll 4
+          for (uint32_t jl = 0; jl < 32; jl++) ZB_DP_FAST_STEP(j0 + jl)
+          continue;
+        }
+        // ---- general group: per-step checks ----
+        const uint32_t jend = j0 + 32 < nb ? j0 + 32 : nb;
+        for (uint32_t j = j0; j < jend; j++) {
+          const uint32_t jl = j & 31;
+          const double tv_n = lds_f64(t0_r + ds_n * 256);
+          const uint32_t ds_nn = min(lds_u8(dsx_r + ((j + 2 + joff) & 127) * 32), kNoEdge);
+          const double llb_n = lds_f64(gl_r + ((j + 1) & 63) * 8);
+          if (lane == jl) mylen = lfin_prev;
           const uint32_t m16 = __shfl_sync(full, mk_cur, jl);
-          ml = m16 & 0x7fffu;
+          const uint32_t ml = m16 & 0x7fffu;
+          double cnext;
+          bool relax = true;
           // long-run shortcut squeeze.c:251-271 (candidate flag precomputed by k_match)
           if ((m16 & kShortcutFlag) && skip_left == 0 && !just_finished) skip_left = kMaxMatch;
           if (skip_left > 0) {
             // costs[j+258] = costs[j] + cost(258,1), unconditionally; no literal, no other edge
-            sts_ring_if(ring_a + ((j + kMaxMatch) & 511) * 16, round_to_f32(cj + cost258), (uint32_t)kMaxMatch, lane == 0);
+            sts_ring_if(ring_r + ((j + kMaxMatch) & 511) * 16, round_to_f32(cj + cost258), (uint32_t)kMaxMatch, lane == 0);
             if (j + kMaxMatch > dirty_until) dirty_until = j + kMaxMatch;
             skip_left--;
             just_finished = skip_left == 0;
@@ -397,81 +438,84 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
           } else {
             just_finished = false;
           }
-        }
-        if (relax) {
-          // literal squeeze.c:277-284 (every lane computes the same values)
-          const double lit = llb + cj;
-          const bool take = lit < e2c;
-          cnext = take ? round_to_f32(lit) : e2c;
-          lfin = take ? 1u : e2l;
-          // lengths 3..34 squeeze.c:286-302: lane l owns length 3+l
-          const double nc = tv + cj;
-          const double mc = mincost + cj;
-          const bool ok = !(w <= mc) & (nc < w);
-          w = ok ? round_to_f32(nc) : w;
-          wl = ok ? k0 : wl;
-          if (ml > 34u) {  // longer lengths: run-list lookup, pushed into the ring
-            const uint32_t room = nb - j;
-            const uint32_t kend = ml < room ? ml : room;
-            const uint4* st4 = (const uint4*)&s.u.dp.runs[((j >> 5) + seq_base) & 3][jl * kRunSlots];
-            const uint4 ea = st4[0], eb = st4[1];
-            const bool ovf = (eb.w & kOverflowBit) != 0;
-            for (uint32_t k = 35 + lane; k <= kend; k += 32) {
-              uint32_t e = eb.w;
-              if (ovf) {
-                e = 0;
-                if (k > run_len(eb.z)) {
-                  uint32_t off = eb.w & ~kOverflowBit, cnt = b.ovf[off];
-                  for (uint32_t r = 0; r < cnt; r++) { uint32_t x = b.ovf[off + 1 + r]; if (run_len(x) >= k) { e = x; break; } }
+          if (relax) {
+            // literal squeeze.c:277-284 (every lane computes the same values)
+            const double lit = llb + cj;
+            const bool take = lit < e2c;
+            cnext = take ? round_to_f32(lit) : e2c;
+            lfin_prev = take ? 1u : e2l;
+            // lengths 3..34 squeeze.c:286-302: lane l owns length 3+l
+            const double nc = tv + cj;
+            const double mc = mincost + cj;
+            const bool ok = !(w <= mc) & (nc < w);
+            w = ok ? round_to_f32(nc) : w;
+            wl = ok ? k0 : wl;
+            if (ml > 34u) {  // longer lengths: run-list lookup, pushed into the ring
+              const uint32_t room = nb - j;
+              const uint32_t kend = ml < room ? ml : room;
+              const uint4* st4 = (const uint4*)&s.u.dp.runs[((j >> 5) + seq_base) & 3][jl * kRunSlots];
+              const uint4 ea = st4[0], eb = st4[1];
+              const bool ovf = (eb.w & kOverflowBit) != 0;
+              for (uint32_t k = 35 + lane; k <= kend; k += 32) {
+                uint32_t e = eb.w;
+                if (ovf) {
+                  e = 0;
+                  if (k > run_len(eb.z)) {
+                    uint32_t off = eb.w & ~kOverflowBit, cnt = b.ovf[off];
+                    for (uint32_t r = 0; r < cnt; r++) { uint32_t x = b.ovf[off + 1 + r]; if (run_len(x) >= k) { e = x; break; } }
+                  }
                 }
+                if (k <= run_len(eb.z)) e = eb.z;
+                if (k <= run_len(eb.y)) e = eb.y;
+                if (k <= run_len(eb.x)) e = eb.x;
+                if (k <= run_len(ea.w)) e = ea.w;
+                if (k <= run_len(ea.z)) e = ea.z;
+                if (k <= run_len(ea.y)) e = ea.y;
+                if (k <= run_len(ea.x)) e = ea.x;
+                const uint32_t tga = ring_r + ((j + k) & 511) * 16;
+                const double pend = lds_f64(tga);
+                if (pend <= mc) continue;  // squeeze.c:293
+                const int dsym = (int)run_dsym(e);
+                double nc2 = (double)(length_extra_bits((int)k) + dist_symbol_extra_bits(dsym)) + s.lencost[k] + s.dcost[dsym];
+                nc2 = nc2 + cj;
+                sts_ring_if(tga, round_to_f32(nc2), k, nc2 < pend);
               }
-              if (k <= run_len(eb.z)) e = eb.z;
-              if (k <= run_len(eb.y)) e = eb.y;
-              if (k <= run_len(eb.x)) e = eb.x;
-              if (k <= run_len(ea.w)) e = ea.w;
-              if (k <= run_len(ea.z)) e = ea.z;
-              if (k <= run_len(ea.y)) e = ea.y;
-              if (k <= run_len(ea.x)) e = ea.x;
-              const uint32_t tga = ring_a + ((j + k) & 511) * 16;
-              const double pend = lds_f64(tga);
-              if (pend <= mc) continue;  // squeeze.c:293
-              const int dsym = (int)run_dsym(e);
-              double nc2 = (double)(length_extra_bits((int)k) + dist_symbol_extra_bits(dsym)) + s.lencost[k] + s.dcost[dsym];
-              nc2 = nc2 + cj;
-              sts_ring_if(tga, round_to_f32(nc2), k, nc2 < pend);
+              if (j + kend > dirty_until) dirty_until = j + kend;
             }
-            if (j + kend > dirty_until) dirty_until = j + kend;
+          } else {
+            cnext = e2c;  // a skipped source contributes no literal edge
+            lfin_prev = e2l;
           }
-        } else {
-          cnext = e2c;  // a skipped source contributes no literal edge
-          lfin = e2l;
-        }
-        if (lane == ((j + 1) & 31)) mylen = lfin;  // length_array[j+1]
-        // the window moves on: lane 0 leaves, lane 31 receives target j+35
-        const double xc = __shfl_sync(full, w, 0);
-        const uint32_t xl = __shfl_sync(full, wl, 0);
-        w = __shfl_down_sync(full, w, 1);
-        wl = __shfl_down_sync(full, wl, 1);
-        double inc = kInfD; uint32_t inl = 0;
-        if (general) {
+          // the window moves on: lane 0 leaves, lane 31 receives target j+35
+          const double xc = __shfl_sync(full, w, 0);
+          const uint32_t xl = __shfl_sync(full, wl, 0);
+          w = __shfl_down_sync(full, w, 1);
+          wl = __shfl_down_sync(full, wl, 1);
+          double inc = kInfD; uint32_t inl = 0;
           __syncwarp();
           if (j + 35 <= dirty_until) {  // ring entry of target j+35 (complete: its sources are <= j)
-            const uint32_t ra = ring_a + ((j + 35) & 511) * 16;
+            const uint32_t ra = ring_r + ((j + 35) & 511) * 16;
             inc = lds_f64(ra);
             inl = lds_u32(ra + 8);
             sts_f64_if(ra, kInfD, lane == 31);  // free the slot for target j+35+512
             __syncwarp();
           }
+          if (lane == 31) { w = inc; wl = inl; }
+          e2c = e1c; e2l = e1l; e1c = xc; e1l = xl;
+          cj = cnext;
+          tv = tv_n; ds_n = ds_nn; llb = llb_n;
         }
-        if (lane == 31) { w = inc; wl = inl; }
-        e2c = e1c; e2l = e1l; e1c = xc; e1l = xl;
-        cj = cnext;
-        tv = tv_n; ds_n = ds_nn; llb = llb_n;
       }
-      seq_base += ngroups;
-      // flush the last (partial) group of length_array: positions 32*(nb>>5) .. nb
-      if (lane <= (nb & 31u)) la[(nb & ~31u) + lane] = (uint16_t)mylen;
+#undef ZB_DP_FAST_STEP
+      // length_array of the last group (positions 32*(ngroups-1) ..) and of position nb
+      {
+        const uint32_t jb = (ngroups - 1) * 32;  // first position of the last group
+        if (jb + lane < nb) la[jb + lane] = (uint16_t)mylen;
+        if (lane == 0) la[nb] = (uint16_t)lfin_prev;
+        // when nb is a multiple of 32 the slot of lane 0 above belongs to position jb, fine
+      }
       __syncwarp();
+      seq_base += ngroups;
     }
 
     ZB_TICK(1);
