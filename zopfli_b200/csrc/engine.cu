@@ -228,7 +228,7 @@ struct Engine::Impl {
       dsx.ensure(L.npos * 32 + 64);
       ovf.ensure((size_t)ovf_cap * 4);
       la.ensure((L.npos + ns) * 2 + 64);
-      path.ensure((L.npos + ns) * 2 + 64);
+      path.ensure((L.npos + ns) * 4 + 64);
       ensure_log();
     }
     Batch b;
@@ -254,7 +254,7 @@ struct Engine::Impl {
     b.ovf_used = counters.as<uint32_t>();
     b.ovf_cap = ovf_cap;
     b.la = la.as<uint16_t>();
-    b.path = path.as<uint16_t>();
+    b.path = path.as<uint32_t>();
     b.st_ll[0] = st[0].as<uint16_t>();
     b.st_d[0] = st[1].as<uint16_t>();
     b.st_ll[1] = st[2].as<uint16_t>();

@@ -38,7 +38,7 @@ struct IterSmem {
   union __align__(16) {
     DpStage dp;
     CostStage cs;
-    uint16_t win[1024];    // trace-back window
+    uint16_t win[8192];    // trace-back window
   } u;
   __align__(8) uint64_t mbar[4];
   uint32_t hist[320];
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
     return;
   }
   uint16_t* la = b.la + sd.pos_off + seg;
-  uint16_t* path = b.path + sd.pos_off + seg;
+  uint32_t* psym = b.path + sd.pos_off + seg;  // traced symbols: (start position << 9) | length
   const uint8_t* in = b.in + sd.instart;
   const uint16_t* sameg = b.same_g + sd.instart;
   const uint16_t* mlen = b.mlen + sd.pos_off;
@@ -520,21 +520,44 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
 
     ZB_TICK(1);
     // ------------------------------------------------------------------ trace back
-    uint32_t cursor = nb + 1;  // path[cursor .. nb+1) holds the symbols in order
+    // lane 0 chases length_array backwards inside shared-memory windows that the whole warp
+    // refills with 4-byte loads; each symbol is emitted as (start position << 9 | length)
+    uint32_t cursor = nb + 1;  // psym[cursor .. nb+1) holds the symbols in order
     {
       uint32_t idx = nb;
+      const uint32_t win_a = smem_u32(&s.u.win[0]);
+      const bool la_odd = (((uintptr_t)la) >> 1) & 1;  // make 4-byte loads aligned
       while (idx > 0) {
-        const uint32_t wlo = idx >= 1024u ? idx - 1023u : 0u;
-        for (uint32_t t = lane; t <= idx - wlo; t += 32) s.u.win[t] = la[wlo + t];
+        // window covers la[wlo .. idx], wlo chosen so that &la[wlo] is 4-byte aligned
+        uint32_t wlo = idx >= 8184u ? idx - 8183u : 0u;
+        if (((wlo & 1u) != 0) != la_odd) wlo = wlo > 0 ? wlo - 1 : 0;  // align (or start at 0)
+        const uint32_t cnt = idx - wlo + 1;
+        if ((((uintptr_t)(la + wlo)) & 3) == 0) {
+          const uint32_t* src = (const uint32_t*)(la + wlo);
+          uint32_t* dst = (uint32_t*)&s.u.win[0];
+          for (uint32_t t = lane; t < (cnt + 1) / 2; t += 32) dst[t] = src[t];
+        } else {
+          for (uint32_t t = lane; t < cnt; t += 32) s.u.win[t] = la[wlo + t];
+        }
         __syncwarp();
         if (lane == 0) {
-          while (idx > 0 && idx >= wlo) {
-            uint32_t l = s.u.win[idx - wlo];
-            if (l == 0 || l > idx) { l = 1; flags |= 2; }  // corrupted chain guard (never expected)
-            path[--cursor] = (uint16_t)l;
-            idx -= l;
-            if (idx < wlo) break;
+          uint32_t i = idx;
+          // one step of the chase; lengths are clamped to [1, i] so a corrupted chain cannot hang
+#define ZB_TRACE_STEP()                                                                     \
+          {                                                                                 \
+            uint32_t l_;                                                                    \
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(l_) : "r"(win_a + (i - wlo) * 2)); \
+            l_ = max(l_, 1u);                                                               \
+            l_ = min(l_, i);                                                                \
+            i -= l_;                                                                        \
+            psym[--cursor] = (i << 9) | l_;                                                 \
           }
+          while (i >= wlo + 4 * 258) {  // four steps cannot leave the window
+            ZB_TRACE_STEP() ZB_TRACE_STEP() ZB_TRACE_STEP() ZB_TRACE_STEP()
+          }
+          while (i > 0 && i >= wlo) ZB_TRACE_STEP()
+#undef ZB_TRACE_STEP
+          idx = i;
         }
         idx = __shfl_sync(0xffffffffu, idx, 0);
         cursor = __shfl_sync(0xffffffffu, cursor, 0);
@@ -550,33 +573,51 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
     uint16_t* cd = b.st_d[curbuf] + sd.pos_off;
     for (int i = lane; i < 320; i += 32) s.hist[i] = 0;
     __syncwarp();
-    {
-      uint32_t posbase = 0;
-      for (uint32_t base = 0; base < nsym; base += 32) {
-        const uint32_t t = base + lane;
-        const bool act = t < nsym;
-        const uint32_t len = act ? path[cursor + t] : 0;
-        const uint32_t step = act ? (len >= (uint32_t)kMinMatch ? len : 1u) : 0u;
-        uint32_t incl = step;
+    for (uint32_t base = 0; base < nsym; base += 128) {
+      uint32_t e[4];
+      uint4 ra[4], rc[4];
+      uint32_t by[4];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= (uint32_t)d) incl += o;
-        }
-        if (act) {
-          const uint32_t pj = posbase + incl - step;
-          if (len >= (uint32_t)kMinMatch) {
-            const uint32_t dist = table_dist(b, sd.pos_off + pj, len);
-            cl[t] = (uint16_t)len; cd[t] = (uint16_t)dist;
-            atomicAdd(&s.hist[length_symbol((int)len)], 1u);
-            atomicAdd(&s.hist[288 + dist_symbol((int)dist)], 1u);
-          } else {
-            const uint32_t by = in[pj];
-            cl[t] = (uint16_t)by; cd[t] = 0;
-            atomicAdd(&s.hist[by], 1u);
+      for (int u = 0; u < 4; u++) {
+        const uint32_t t = base + u * 32 + lane;
+        e[u] = t < nsym ? psym[cursor + t] : 1u;  // dummy literal at position 0 for the tail
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t len = e[u] & 511u, pj = e[u] >> 9;
+        const uint4* r4 = (const uint4*)(b.runs + (sd.pos_off + pj) * kRunSlots);
+        if (len >= (uint32_t)kMinMatch) { ra[u] = r4[0]; rc[u] = r4[1]; by[u] = 0; }
+        else { ra[u] = make_uint4(0, 0, 0, 0); rc[u] = ra[u]; by[u] = in[pj]; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t t = base + u * 32 + lane;
+        if (t >= nsym) continue;
+        const uint32_t len = e[u] & 511u;
+        if (len >= (uint32_t)kMinMatch) {
+          const uint4 a = ra[u], c = rc[u];
+          uint32_t x = c.w;
+          if (c.w & kOverflowBit) {
+            x = 0;
+            if (len > run_len(c.z)) {
+              const uint32_t off = c.w & ~kOverflowBit, cnt = b.ovf[off];
+              for (uint32_t i = 0; i < cnt; i++) { uint32_t y = b.ovf[off + 1 + i]; if (run_len(y) >= len) { x = y; break; } }
+            }
           }
+          if (len <= run_len(c.z)) x = c.z;
+          if (len <= run_len(c.y)) x = c.y;
+          if (len <= run_len(c.x)) x = c.x;
+          if (len <= run_len(a.w)) x = a.w;
+          if (len <= run_len(a.z)) x = a.z;
+          if (len <= run_len(a.y)) x = a.y;
+          if (len <= run_len(a.x)) x = a.x;
+          cl[t] = (uint16_t)len; cd[t] = (uint16_t)run_dist(x);
+          atomicAdd(&s.hist[length_symbol((int)len)], 1u);
+          atomicAdd(&s.hist[288 + run_dsym(x)], 1u);
+        } else {
+          cl[t] = (uint16_t)by[u]; cd[t] = 0;
+          atomicAdd(&s.hist[by[u]], 1u);
         }
-        posbase += __shfl_sync(0xffffffffu, incl, 31);
       }
     }
     __syncwarp();

@@ -92,7 +92,7 @@ struct Batch {
   uint32_t ovf_cap;
   // parse state
   uint16_t* la;     // [npos + nsegs] length_array, nb+1 per segment (offset pos_off + seg)
-  uint16_t* path;   // [npos + nsegs]
+  uint32_t* path;   // [npos + nsegs] traced symbols (start position << 9 | length), filled from the end
   uint16_t* st_ll[3];
   uint16_t* st_d[3];
   JobState* jobs;
@@ -480,21 +480,27 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
 // distance of the shortest-distance match of length >= len at parse position (table lookup,
 // this is what FollowPath's limited search returns, squeeze.c:367)
 __device__ __forceinline__ uint32_t table_dist(const Batch& b, uint64_t o, uint32_t len) {
-  const uint32_t* r = b.runs + o * kRunSlots;
-#pragma unroll
-  for (int i = 0; i < kRunSlots - 1; i++) {
-    uint32_t e = r[i];
-    if (run_len(e) >= len) return run_dist(e);
+  const uint4* r4 = (const uint4*)(b.runs + o * kRunSlots);
+  const uint4 a = r4[0], c = r4[1];  // two independent 16-byte loads
+  uint32_t e = c.w;
+  if (c.w & kOverflowBit) {
+    e = 0;
+    if (len > run_len(c.z)) {
+      const uint32_t off = c.w & ~kOverflowBit, cnt = b.ovf[off];
+      for (uint32_t i = 0; i < cnt; i++) {
+        uint32_t x = b.ovf[off + 1 + i];
+        if (run_len(x) >= len) { e = x; break; }
+      }
+    }
   }
-  uint32_t e = r[kRunSlots - 1];
-  if (!(e & kOverflowBit)) return run_dist(e);
-  uint32_t off = e & ~kOverflowBit;
-  uint32_t cnt = b.ovf[off];
-  for (uint32_t i = 0; i < cnt; i++) {
-    uint32_t x = b.ovf[off + 1 + i];
-    if (run_len(x) >= len) return run_dist(x);
-  }
-  return 0;
+  if (len <= run_len(c.z)) e = c.z;
+  if (len <= run_len(c.y)) e = c.y;
+  if (len <= run_len(c.x)) e = c.x;
+  if (len <= run_len(a.w)) e = a.w;
+  if (len <= run_len(a.z)) e = a.z;
+  if (len <= run_len(a.y)) e = a.y;
+  if (len <= run_len(a.x)) e = a.x;
+  return run_dist(e);
 }
 
 // ---------------------------------------------------------------------------------------------
