@@ -290,6 +290,26 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       mincost = (double)(length_extra_bits(bl) + dist_symbol_extra_bits(dsym)) + s.lencost[bl < 3 ? 3 : bl] + s.dcost[dsym];
       (void)first_dist_of_symbol;
     }
+    // squeeze.c:293 skips an edge when costs[j+k] <= mincost + costs[j].  That is a pure
+    // optimisation exactly when mincost <= every edge cost the model can produce (then
+    // cost + c_j >= mincost + c_j by monotonicity of rounding and the edge could not win anyway).
+    // Check it for all 256 x 30 (length, distance symbol) pairs; if it ever fails, the fast path
+    // is disabled for this iteration and every edge goes through the explicit test.
+    bool skip_noop;
+    {
+      double mn = 1e300;
+      for (int k = 3 + (int)lane; k < 259; k += 32) {
+        const int lb = length_extra_bits(k);
+        const double lc = s.lencost[k];
+        for (int ds = 0; ds < 30; ds++) {
+          const double c = (double)(lb + dist_symbol_extra_bits(ds)) + lc + s.dcost[ds];
+          mn = c < mn ? c : mn;
+        }
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, mn, d); mn = o < mn ? o : mn; }
+      skip_noop = mincost <= mn;
+    }
     const double cost258 = (double)(0 + 0) + s.lencost[258] + s.dcost[0];  // costmodel(258, 1)
     ZB_TICK(0);
 
@@ -311,10 +331,7 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       const uint32_t full = 0xffffffffu;
       const uint32_t ngroups = (nb + 31) >> 5;
       const uint32_t ring_a = smem_u32(&s.u.dp.ring[0]);
-      const uint32_t t0_a = smem_u32(&s.t0[0]) + lane * 8;
       const uint32_t gl_a = smem_u32(&s.u.dp.gl[0]);
-      const uint32_t dsx_a = smem_u32(&s.u.dp.dsx[0][0]) + lane;
-      const uint32_t k0 = 3 + lane;
       auto issue_group = [&](uint32_t g, uint32_t seq) {  // lane 0
         const uint32_t cnt = nb - g * 32 < 32u ? nb - g * 32 : 32u;
         const uint32_t st = seq & 3, bytes = cnt * 32;
@@ -347,8 +364,11 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       }
       acquire(0, seq_base);
       mk_cur = mk_next; flag_cur = flag_next;
-      // register window and pipeline state
-      double w = kInfD; uint32_t wl = 0;               // pending(j+3+lane)
+      // register window and pipeline state.  Lane l owns the targets t == l (mod 32): at step j
+      // it holds pending(t) for the one such t in [j+3, j+34] and relaxes it with length
+      // k = t - j = 3 + col, col = (l - j - 3) mod 32.  Nothing moves between lanes; the lane
+      // whose target is j+3 (col 0) hands its completed value to the chain and takes on j+35.
+      double w = kInfD; uint32_t wl = 0;
       double e1c = kInfD, e2c = kInfD; uint32_t e1l = 0, e2l = 0;  // pending(j+2), pending(j+1)
       double cj = 0.0;
       uint32_t lfin_prev = 0;                            // length_array[j], recorded one step late
@@ -356,23 +376,24 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       uint32_t dirty_until = 0;                          // largest target that has a ring entry
       uint32_t skip_left = 0;
       bool just_finished = false;
-      // operand prefetch pipeline: tv = t0 row value for step j, ds_n = dsx of row j+1
-      uint32_t ds_n = min(lds_u8(dsx_a + (joff & 127u) * 32), kNoEdge);
-      double tv = lds_f64(t0_a + ds_n * 256);
-      ds_n = nb > 1 ? min(lds_u8(dsx_a + ((1 + joff) & 127u) * 32), kNoEdge) : kNoEdge;
-      double llb = lds_f64(gl_a);
       // keep the shared-memory base addresses opaque so they stay in registers
-      uint32_t t0_r = t0_a, gl_r = gl_a, dsx_r = dsx_a, ring_r = ring_a;
+      uint32_t t0_r = smem_u32(&s.t0[0]), gl_r = gl_a, dsx_r = smem_u32(&s.u.dp.dsx[0][0]), ring_r = ring_a;
       asm volatile("" : "+r"(t0_r), "+r"(gl_r), "+r"(dsx_r), "+r"(ring_r));
+      // operand prefetch pipeline: tv = edge cost for step j, ds_n = distance symbol for step j+1
+      uint32_t col = (lane - 3u) & 31u;                  // column of step 0
+      uint32_t ds_n = min(lds_u8(dsx_r + ((joff & 127u) * 32) + col), kNoEdge);
+      double tv = lds_f64(t0_r + ds_n * 256 + col * 8);
+      ds_n = nb > 1 ? min(lds_u8(dsx_r + (((1 + joff) & 127u) * 32) + ((col - 1u) & 31u)), kNoEdge) : kNoEdge;
+      double llb = lds_f64(gl_a);
 
       // one step of the common case: no shortcut, no length > 34 at this position, no ring entry
-      // coming due.  Straight-line code: chain (cj -> cnext), window relax, window shift, operand
-      // prefetch for the next step.
+      // coming due, and the squeeze.c:293 test proven redundant.  Straight-line code.
 #define ZB_DP_FAST_STEP(J)                                                                        \
       {                                                                                           \
         const uint32_t j_ = (J);                                                                  \
-        const double tv_n_ = lds_f64(t0_r + ds_n * 256);                                          \
-        const uint32_t ds_nn_ = min(lds_u8(dsx_r + ((j_ + 2 + joff) & 127) * 32), kNoEdge);       \
+        const uint32_t c1_ = (col - 1u) & 31u, c2_ = (col - 2u) & 31u;                            \
+        const double tv_n_ = lds_f64(t0_r + ds_n * 256 + c1_ * 8);                                \
+        const uint32_t ds_nn_ = min(lds_u8(dsx_r + ((j_ + 2 + joff) & 127) * 32 + c2_), kNoEdge); \
         const double llb_n_ = lds_f64(gl_r + ((j_ + 1) & 63) * 8);                                \
         if (lane == (j_ & 31)) mylen = lfin_prev;                                                 \
         const double lit_ = llb + cj;                                                             \
@@ -380,26 +401,25 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
         const double cnext_ = take_ ? round_to_f32(lit_) : e2c;                                   \
         lfin_prev = take_ ? 1u : e2l;                                                             \
         const double nc_ = tv + cj;                                                               \
-        const double mc_ = mincost + cj;                                                          \
-        const bool ok_ = !(w <= mc_) & (nc_ < w);                                                 \
-        w = ok_ ? round_to_f32(nc_) : w;                                                          \
-        wl = ok_ ? k0 : wl;                                                                       \
-        const double xc_ = __shfl_sync(full, w, 0);                                               \
-        const uint32_t xl_ = __shfl_sync(full, wl, 0);                                            \
-        w = __shfl_down_sync(full, w, 1);                                                         \
-        wl = __shfl_down_sync(full, wl, 1);                                                       \
-        if (lane == 31) { w = kInfD; wl = 0; }                                                    \
+        double rn_ = round_to_f32(nc_);                                                           \
+        asm volatile("" : "+d"(rn_));                                                             \
+        const bool ok_ = nc_ < w;                                                                 \
+        w = ok_ ? rn_ : w;                                                                        \
+        wl = ok_ ? col + 3u : wl;                                                                 \
+        const uint32_t src_ = (j_ + 3) & 31;                                                      \
+        const double xc_ = __shfl_sync(full, w, src_);                                            \
+        const uint32_t xl_ = __shfl_sync(full, wl, src_);                                         \
+        if (col == 0) { w = kInfD; wl = 0; }                                                      \
         e2c = e1c; e2l = e1l; e1c = xc_; e1l = xl_;                                               \
         cj = cnext_;                                                                              \
-        tv = tv_n_; ds_n = ds_nn_; llb = llb_n_;                                                  \
+        tv = tv_n_; ds_n = ds_nn_; llb = llb_n_; col = c1_;                                       \
       }
 
       for (uint32_t g = 0; g < ngroups; g++) {
         const uint32_t j0 = g * 32;
-        // ---- group start (uniform): flush, rotate, look ahead ----
+        // ---- group start (uniform): flush the previous group's lengths, rotate, look ahead ----
         if (g > 0) {
-          la[j0 - 32 + lane] = (uint16_t)mylen;  // positions of group g-1; position j0-1's length
-          // is still in lfin_prev?  no: it was recorded at step j0-1+... see below
+          la[j0 - 32 + lane] = (uint16_t)mylen;
           mk_cur = mk_next; flag_cur = flag_next;
         }
         if (g + 1 < ngroups) {
@@ -408,7 +428,7 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
         } else {
           flag_next = 0; mk_next = 0;
         }
-        const bool fast = flag_cur == 0 && skip_left == 0 && !just_finished && j0 + 35 > dirty_until && j0 + 32 <= nb;
+        const bool fast = skip_noop && flag_cur == 0 && skip_left == 0 && !just_finished && j0 + 35 > dirty_until && j0 + 32 <= nb;
         if (fast) {
 #pragma unroll 4
           for (uint32_t jl = 0; jl < 32; jl++) ZB_DP_FAST_STEP(j0 + jl)
@@ -418,8 +438,9 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
         const uint32_t jend = j0 + 32 < nb ? j0 + 32 : nb;
         for (uint32_t j = j0; j < jend; j++) {
           const uint32_t jl = j & 31;
-          const double tv_n = lds_f64(t0_r + ds_n * 256);
-          const uint32_t ds_nn = min(lds_u8(dsx_r + ((j + 2 + joff) & 127) * 32), kNoEdge);
+          const uint32_t c1 = (col - 1u) & 31u, c2 = (col - 2u) & 31u;
+          const double tv_n = lds_f64(t0_r + ds_n * 256 + c1 * 8);
+          const uint32_t ds_nn = min(lds_u8(dsx_r + ((j + 2 + joff) & 127) * 32 + c2), kNoEdge);
           const double llb_n = lds_f64(gl_r + ((j + 1) & 63) * 8);
           if (lane == jl) mylen = lfin_prev;
           const uint32_t m16 = __shfl_sync(full, mk_cur, jl);
@@ -444,12 +465,12 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
             const bool take = lit < e2c;
             cnext = take ? round_to_f32(lit) : e2c;
             lfin_prev = take ? 1u : e2l;
-            // lengths 3..34 squeeze.c:286-302: lane l owns length 3+l
+            // lengths 3..34 squeeze.c:286-302: this lane's length is 3 + col
             const double nc = tv + cj;
             const double mc = mincost + cj;
             const bool ok = !(w <= mc) & (nc < w);
             w = ok ? round_to_f32(nc) : w;
-            wl = ok ? k0 : wl;
+            wl = ok ? col + 3u : wl;
             if (ml > 34u) {  // longer lengths: run-list lookup, pushed into the ring
               const uint32_t room = nb - j;
               const uint32_t kend = ml < room ? ml : room;
@@ -486,33 +507,32 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
             cnext = e2c;  // a skipped source contributes no literal edge
             lfin_prev = e2l;
           }
-          // the window moves on: lane 0 leaves, lane 31 receives target j+35
-          const double xc = __shfl_sync(full, w, 0);
-          const uint32_t xl = __shfl_sync(full, wl, 0);
-          w = __shfl_down_sync(full, w, 1);
-          wl = __shfl_down_sync(full, wl, 1);
+          // target j+3 is complete for every length edge: hand it to the chain; its lane takes
+          // on target j+35, whose ring entry (edges longer than 34) is complete as well
+          const uint32_t src = (j + 3) & 31;
+          const double xc = __shfl_sync(full, w, src);
+          const uint32_t xl = __shfl_sync(full, wl, src);
           double inc = kInfD; uint32_t inl = 0;
           __syncwarp();
-          if (j + 35 <= dirty_until) {  // ring entry of target j+35 (complete: its sources are <= j)
+          if (j + 35 <= dirty_until) {
             const uint32_t ra = ring_r + ((j + 35) & 511) * 16;
             inc = lds_f64(ra);
             inl = lds_u32(ra + 8);
-            sts_f64_if(ra, kInfD, lane == 31);  // free the slot for target j+35+512
+            sts_f64_if(ra, kInfD, lane == 0);  // free the slot for target j+35+512
             __syncwarp();
           }
-          if (lane == 31) { w = inc; wl = inl; }
+          if (col == 0) { w = inc; wl = inl; }
           e2c = e1c; e2l = e1l; e1c = xc; e1l = xl;
           cj = cnext;
-          tv = tv_n; ds_n = ds_nn; llb = llb_n;
+          tv = tv_n; ds_n = ds_nn; llb = llb_n; col = c1;
         }
       }
 #undef ZB_DP_FAST_STEP
       // length_array of the last group (positions 32*(ngroups-1) ..) and of position nb
       {
-        const uint32_t jb = (ngroups - 1) * 32;  // first position of the last group
+        const uint32_t jb = (ngroups - 1) * 32;
         if (jb + lane < nb) la[jb + lane] = (uint16_t)mylen;
         if (lane == 0) la[nb] = (uint16_t)lfin_prev;
-        // when nb is a multiple of 32 the slot of lane 0 above belongs to position jb, fine
       }
       __syncwarp();
       seq_base += ngroups;
