@@ -143,9 +143,12 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
     // ---- stage B: split search ----
     parallel_for(nm, [&](size_t m) {
       Master& mb = M[m];
+      double ta = now_ms();
       mb.greedy.append(res.ll.data() + res.off[m], res.d.data() + res.off[m], res.size[m], mb.ms);
       mb.greedy.finalize();
+      double tb = now_ms();
       std::vector<size_t> lp = block_split_lz77(make_cost(mb.greedy), mb.greedy.size(), maxblocks);
+      if (getenv("ZOPFLI_B200_DEBUG")) fprintf(stderr, "stageB mb %zu: build %.1f ms split %.1f ms (%zu syms)\n", m, tb - ta, now_ms() - tb, mb.greedy.size());
       mb.cuts.push_back(mb.ms);
       for (size_t p : lp) mb.cuts.push_back(mb.greedy.pos[p]);  // blocksplitter.c:303-313
       mb.cuts.push_back(mb.me);
@@ -190,6 +193,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
   parallel_for(nm, [&](size_t m) {
     Master& mb = M[m];
     DynScratch s;
+    double ta = now_ms();
     uint64_t totalcost = 0;
     const size_t nblocks = mb.blockstores.size();
     std::vector<size_t> points;
@@ -200,6 +204,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
     }
     mb.blockstores.clear();
     mb.lz77.finalize();
+    double tb = now_ms();
     if (opt->blocksplitting && points.size() > 1) {  // deflate.c:872-893
       std::vector<size_t> p2 = block_split_lz77(make_cost(mb.lz77), mb.lz77.size(), maxblocks);
       uint64_t totalcost2 = 0;
@@ -210,6 +215,8 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
       if (totalcost2 < totalcost) points = p2;
     }
     mb.points = points;
+    double tc = now_ms();
+    if (getenv("ZOPFLI_B200_DEBUG")) fprintf(stderr, "stageD mb %zu: build %.1f ms split2 %.1f ms\n", m, tb - ta, tc - tb);
     for (size_t i = 0; i <= points.size(); i++) {  // AddLZ77BlockAutoType deflate.c:747-800
       FinalBlock fb;
       fb.lstart = i == 0 ? 0 : points[i - 1];
