@@ -47,6 +47,11 @@ int ZopfliB200MatchTable(const unsigned char* in, size_t insize, size_t instart,
  * (deflate.c:569-608), evaluated on the device (where=1) or by the host code (where=0). */
 uint64_t ZopfliB200DynamicBlockBits(const uint32_t* hist320, int where);
 
+/* ZopfliCalculateBlockSizeAutoType (deflate.h:85-86) of nreq symbol ranges of one LZ77 store,
+ * evaluated on the device (k_split_eval) -- the splitter's cost oracle. */
+int ZopfliB200DeviceAutoTypeBits(const unsigned short* litlens, const unsigned short* dists, size_t n,
+                                 size_t nreq, const size_t* lstart, const size_t* lend, uint64_t* out);
+
 /* Host logic seams (no GPU needed): ZopfliBlockSplitLZ77 (blocksplitter.h:42-45) and
  * ZopfliCalculateBlockSize[AutoType] (deflate.h:79-86) over an explicit symbol list whose first
  * symbol starts at byte 0 of `in`. */
@@ -93,6 +98,7 @@ typedef struct ZopfliB200Stats {
   double ms_host_split, ms_host_emit, ms_host_other, ms_total;
   uint64_t launches, match_positions, iterate_positions, iterate_steps, h2d_bytes, d2h_bytes;
   uint64_t cyc_sum[6], cyc_max[6], max_block_positions; /* k_iterate phase cycles, see engine.hpp */
+  double ms_split; uint64_t split_evals, split_rounds;  /* device split-cost service */
 } ZopfliB200Stats;
 void ZopfliB200GetStats(ZopfliB200Stats* out);
 void ZopfliB200ResetStats(void);

@@ -12,6 +12,7 @@
 
 #include "../../oracle/zopfli_oracle.h"
 #include "../../zopfli_b200/csrc/engine.hpp"
+#include "../../zopfli_b200/csrc/lz77_store.hpp"
 
 namespace zb {
 
@@ -60,5 +61,22 @@ void Engine::match_table(uint64_t, uint64_t, std::vector<uint16_t>&, std::vector
                          std::vector<uint16_t>&, std::vector<uint16_t>&, std::vector<uint16_t>&,
                          std::vector<uint16_t>&) {}
 uint64_t Engine::device_block_bits(const uint32_t*) { return 0; }
+
+// split service of the mock: the product's own HOST estimators (lz77_store.hpp), so the batched
+// scheduler (batched_split.hpp) is exercised on CPU exactly as the driver uses it
+static std::vector<zb::Lz77Store> g_split_stores;
+void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vector<uint64_t>& off,
+                         const std::vector<uint32_t>& size) {
+  g_split_stores.clear();
+  g_split_stores.resize(off.size());
+  for (size_t i = 0; i < off.size(); i++) {
+    g_split_stores[i].append(ll + off[i], d + off[i], size[i], 0);
+    g_split_stores[i].finalize();
+  }
+}
+void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs) {
+  static thread_local DynScratch s;
+  for (size_t i = 0; i < n; i++) costs[i] = auto_type_bits(g_split_stores[reqs[i].store], reqs[i].lstart, reqs[i].lend, s);
+}
 
 }  // namespace zb

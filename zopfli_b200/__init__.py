@@ -35,7 +35,8 @@ class Stats(C.Structure):
                                            "ms_host_split", "ms_host_emit", "ms_host_other", "ms_total")] + \
                [(n, C.c_uint64) for n in ("launches", "match_positions", "iterate_positions",
                                           "iterate_steps", "h2d_bytes", "d2h_bytes")] + \
-               [("cyc_sum", C.c_uint64 * 6), ("cyc_max", C.c_uint64 * 6), ("max_block_positions", C.c_uint64)]
+               [("cyc_sum", C.c_uint64 * 6), ("cyc_max", C.c_uint64 * 6), ("max_block_positions", C.c_uint64),
+                ("ms_split", C.c_double), ("split_evals", C.c_uint64), ("split_rounds", C.c_uint64)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n.startswith("cyc_") else getattr(self, n)) for n, _ in self._fields_}
@@ -43,7 +44,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["ZopfliInitOptions", "ZopfliCompress", "ZopfliDeflate", "ZopfliDeflatePart",
            "ZopfliGzipCompress", "ZopfliZlibCompress", "ZopfliB200LZ77", "ZopfliB200LZ77Batch",
-           "ZopfliB200MatchTable", "ZopfliB200DynamicBlockBits", "ZopfliB200HostBlockSplitLZ77",
+           "ZopfliB200MatchTable", "ZopfliB200DynamicBlockBits", "ZopfliB200DeviceAutoTypeBits", "ZopfliB200HostBlockSplitLZ77",
            "ZopfliB200HostBlockSize", "ZopfliB200HostEmitBlock", "ZopfliB200HostLengthLimited",
            "ZopfliB200DeflateSpan", "ZopfliB200AppendSpan", "ZopfliB200Crc32", "ZopfliB200Crc32Combine", "ZopfliB200CompressDevice",
            "ZopfliB200GetStats", "ZopfliB200ResetStats", "ZopfliB200SetStream", "ZopfliB200Device",
@@ -84,6 +85,7 @@ class Library:
         L.ZopfliB200LZ77.argtypes = [vp, sz, sz, sz, C.c_int, C.c_int, vp, vp, sz, C.POINTER(sz)]
         L.ZopfliB200LZ77Batch.argtypes = [vp, sz, sz, vp, vp, C.c_int, C.c_int, vp, vp, sz, vp, vp, vp]
         L.ZopfliB200MatchTable.argtypes = [vp, sz, sz, sz, vp, vp, vp, vp, vp, vp]
+        L.ZopfliB200DeviceAutoTypeBits.argtypes = [vp, vp, sz, sz, vp, vp, vp]
         L.ZopfliB200DynamicBlockBits.argtypes = [vp, C.c_int]
         L.ZopfliB200DynamicBlockBits.restype = C.c_uint64
         L.ZopfliB200HostBlockSplitLZ77.argtypes = [vp, vp, vp, sz, sz, vp, sz]
@@ -199,6 +201,16 @@ class Library:
     def dynamic_block_bits(self, hist320, device=False):
         h = np.ascontiguousarray(hist320, np.uint32)
         return int(self.lib.ZopfliB200DynamicBlockBits(h.ctypes.data, 1 if device else 0))
+
+    def device_auto_type_bits(self, litlens, dists, lstart, lend):
+        ll = np.ascontiguousarray(litlens, np.uint16)
+        dd = np.ascontiguousarray(dists, np.uint16)
+        a = np.ascontiguousarray(lstart, np.uint64)
+        b = np.ascontiguousarray(lend, np.uint64)
+        out = np.zeros(len(a), np.uint64)
+        self.lib.ZopfliB200DeviceAutoTypeBits(ll.ctypes.data, dd.ctypes.data, len(ll), len(a), a.ctypes.data,
+                                              b.ctypes.data, out.ctypes.data)
+        return out
 
     def host_block_split_lz77(self, litlens, dists, maxblocks=15):
         ll = np.ascontiguousarray(litlens, np.uint16)

@@ -363,6 +363,18 @@ uint64_t ZopfliB200DynamicBlockBits(const uint32_t* hist320, int where) {
   return dynamic_block_bits(hist320, nullptr, nullptr, s);
 }
 
+int ZopfliB200DeviceAutoTypeBits(const unsigned short* litlens, const unsigned short* dists, size_t n, size_t nreq,
+                                 const size_t* lstart, const size_t* lend, uint64_t* out) {
+  Engine& e = Engine::get();
+  std::vector<uint64_t> off{0};
+  std::vector<uint32_t> size{(uint32_t)n};
+  e.split_begin(litlens, dists, off, size);
+  std::vector<Engine::SplitReq> r(nreq);
+  for (size_t i = 0; i < nreq; i++) r[i] = {0u, (uint32_t)lstart[i], (uint32_t)lend[i]};
+  e.split_eval(r.data(), nreq, out);
+  return 0;
+}
+
 size_t ZopfliB200HostBlockSplitLZ77(const unsigned char* in, const unsigned short* litlens,
                                     const unsigned short* dists, size_t n, size_t maxblocks, size_t* points,
                                     size_t cap) {
@@ -424,6 +436,7 @@ void ZopfliB200GetStats(ZopfliB200Stats* o) {
   o->iterate_steps = e.iterate_steps; o->h2d_bytes = e.h2d_bytes; o->d2h_bytes = e.d2h_bytes;
   for (int k = 0; k < 6; k++) { o->cyc_sum[k] = e.cyc_sum[k]; o->cyc_max[k] = e.cyc_max[k]; }
   o->max_block_positions = e.max_block_positions;
+  o->ms_split = e.ms_split; o->split_evals = e.split_evals; o->split_rounds = e.split_rounds;
 }
 
 void ZopfliB200ResetStats(void) {

@@ -19,6 +19,7 @@
 #include <chrono>
 #include <thread>
 
+#include "batched_split.hpp"
 #include "emit.hpp"
 #include "engine.hpp"
 #include "host_split.hpp"
@@ -90,6 +91,23 @@ RangeCostFn make_cost(const Lz77Store& st) {
   };
 }
 
+bool host_split_forced() {
+  static int v = [] { const char* e = getenv("ZOPFLI_B200_HOST_SPLIT"); return e && atoi(e) ? 1 : 0; }();
+  return v != 0;
+}
+
+// ZopfliBlockSplitLZ77 for many stores at once, split costs priced by the device (k_split_eval)
+std::vector<std::vector<size_t>> device_block_split(Engine& eng, const uint16_t* ll, const uint16_t* d,
+                                                    const std::vector<uint64_t>& off, const std::vector<uint32_t>& size,
+                                                    size_t maxblocks) {
+  eng.split_begin(ll, d, off, size);
+  std::vector<size_t> sizes(size.begin(), size.end());
+  return batched_block_split(sizes, maxblocks, [&](const std::vector<EvalReq>& r, std::vector<uint64_t>& c) {
+    static_assert(sizeof(EvalReq) == sizeof(Engine::SplitReq), "layout");
+    eng.split_eval(reinterpret_cast<const Engine::SplitReq*>(r.data()), r.size(), c.data());
+  });
+}
+
 void stored_pieces(size_t a, size_t b, bool final, std::vector<Piece>& out) {
   Piece p;
   p.stored = true;
@@ -140,21 +158,36 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
     eng.parse(pr, res);
     double t1 = now_ms();
     g_host_times.other += t1 - t0;
-    // ---- stage B: split search ----
+    // ---- stage B: split search (costs on the device, decisions on the host) ----
+    std::vector<std::vector<size_t>> lps;
+    if (!host_split_forced()) {
+      std::vector<uint64_t> off(nm);
+      for (size_t m = 0; m < nm; m++) off[m] = res.off[m];
+      lps = device_block_split(eng, res.ll.data(), res.d.data(), off, res.size, maxblocks);
+    }
     parallel_for(nm, [&](size_t m) {
       Master& mb = M[m];
-      double ta = now_ms();
-      mb.greedy.append(res.ll.data() + res.off[m], res.d.data() + res.off[m], res.size[m], mb.ms);
-      mb.greedy.finalize();
-      double tb = now_ms();
-      std::vector<size_t> lp = block_split_lz77(make_cost(mb.greedy), mb.greedy.size(), maxblocks);
-      if (getenv("ZOPFLI_B200_DEBUG")) fprintf(stderr, "stageB mb %zu: build %.1f ms split %.1f ms (%zu syms)\n", m, tb - ta, now_ms() - tb, mb.greedy.size());
+      std::vector<size_t> lp;
+      if (host_split_forced()) {
+        mb.greedy.append(res.ll.data() + res.off[m], res.d.data() + res.off[m], res.size[m], mb.ms);
+        mb.greedy.finalize();
+        lp = block_split_lz77(make_cost(mb.greedy), mb.greedy.size(), maxblocks);
+      } else {
+        lp = lps[m];
+      }
+      // LZ77 indices -> byte positions (blocksplitter.c:303-313)
+      const uint16_t* ll = res.ll.data() + res.off[m];
+      const uint16_t* dd = res.d.data() + res.off[m];
       mb.cuts.push_back(mb.ms);
-      for (size_t p : lp) mb.cuts.push_back(mb.greedy.pos[p]);  // blocksplitter.c:303-313
+      size_t pos = mb.ms, k = 0;
+      for (size_t i = 0; i < res.size[m] && k < lp.size(); i++) {
+        if (lp[k] == i) { mb.cuts.push_back(pos); k++; }
+        pos += dd[i] == 0 ? 1 : ll[i];
+      }
       mb.cuts.push_back(mb.me);
       if (opt->verbose) {
         fprintf(stderr, "block split points: ");
-        for (size_t p : lp) fprintf(stderr, "%d ", (int)mb.greedy.pos[p]);
+        for (size_t c = 1; c + 1 < mb.cuts.size(); c++) fprintf(stderr, "%d ", (int)mb.cuts[c]);
         fprintf(stderr, "\n");
       }
       mb.greedy.clear();
@@ -190,33 +223,55 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
 
   // ---- stage D: second split attempt and block types ----
   std::vector<std::vector<ParseRange>> fixed_req(nm);
-  parallel_for(nm, [&](size_t m) {
+  std::vector<uint64_t> totalcost(nm, 0);
+  std::vector<std::vector<size_t>> first_points(nm);
+  parallel_for(nm, [&](size_t m) {  // D1: concatenate the blocks, cost of the first split
     Master& mb = M[m];
     DynScratch s;
-    double ta = now_ms();
-    uint64_t totalcost = 0;
     const size_t nblocks = mb.blockstores.size();
-    std::vector<size_t> points;
     for (size_t i = 0; i < nblocks; i++) {
-      totalcost += auto_type_bits(mb.blockstores[i], 0, mb.blockstores[i].size(), s);  // deflate.c:862
+      totalcost[m] += auto_type_bits(mb.blockstores[i], 0, mb.blockstores[i].size(), s);  // deflate.c:862
       mb.lz77.append(mb.blockstores[i]);
-      if (i + 1 < nblocks) points.push_back(mb.lz77.size());
+      if (i + 1 < nblocks) first_points[m].push_back(mb.lz77.size());
     }
     mb.blockstores.clear();
     mb.lz77.finalize();
-    double tb = now_ms();
-    if (opt->blocksplitting && points.size() > 1) {  // deflate.c:872-893
-      std::vector<size_t> p2 = block_split_lz77(make_cost(mb.lz77), mb.lz77.size(), maxblocks);
+  });
+  std::vector<std::vector<size_t>> second(nm);
+  std::vector<char> want2(nm, 0);
+  for (size_t m = 0; m < nm; m++) want2[m] = opt->blocksplitting && first_points[m].size() > 1;  // deflate.c:872
+  if (!host_split_forced()) {
+    std::vector<uint64_t> off;
+    std::vector<uint32_t> size;
+    std::vector<size_t> who;
+    uint64_t total = 0;
+    for (size_t m = 0; m < nm; m++)
+      if (want2[m]) { who.push_back(m); off.push_back(total); size.push_back((uint32_t)M[m].lz77.size()); total += M[m].lz77.size(); }
+    if (!who.empty()) {
+      std::vector<uint16_t> fll(total), fd(total);
+      parallel_for(who.size(), [&](size_t k) {
+        const Lz77Store& st = M[who[k]].lz77;
+        memcpy(fll.data() + off[k], st.litlens.data(), st.size() * 2);
+        memcpy(fd.data() + off[k], st.dists.data(), st.size() * 2);
+      });
+      std::vector<std::vector<size_t>> r = device_block_split(eng, fll.data(), fd.data(), off, size, maxblocks);
+      for (size_t k = 0; k < who.size(); k++) second[who[k]] = r[k];
+    }
+  }
+  parallel_for(nm, [&](size_t m) {  // D2
+    Master& mb = M[m];
+    DynScratch s;
+    std::vector<size_t> points = first_points[m];
+    if (want2[m]) {  // deflate.c:872-893
+      std::vector<size_t> p2 = host_split_forced() ? block_split_lz77(make_cost(mb.lz77), mb.lz77.size(), maxblocks) : second[m];
       uint64_t totalcost2 = 0;
       for (size_t i = 0; i <= p2.size(); i++) {
         size_t a = i == 0 ? 0 : p2[i - 1], b = i == p2.size() ? mb.lz77.size() : p2[i];
         totalcost2 += auto_type_bits(mb.lz77, a, b, s);
       }
-      if (totalcost2 < totalcost) points = p2;
+      if (totalcost2 < totalcost[m]) points = p2;
     }
     mb.points = points;
-    double tc = now_ms();
-    if (getenv("ZOPFLI_B200_DEBUG")) fprintf(stderr, "stageD mb %zu: build %.1f ms split2 %.1f ms\n", m, tb - ta, tc - tb);
     for (size_t i = 0; i <= points.size(); i++) {  // AddLZ77BlockAutoType deflate.c:747-800
       FinalBlock fb;
       fb.lstart = i == 0 ? 0 : points[i - 1];

@@ -15,6 +15,7 @@
 
 #include "iterate.cuh"
 #include "kernels.cuh"
+#include "split.cuh"
 
 namespace zb {
 
@@ -51,7 +52,7 @@ __global__ void k_test_block_bits(Batch b, const uint32_t* hist, uint64_t* out) 
   __syncwarp();
   if (lane == 0) s.hist[256] = 1;
   __syncwarp();
-  uint64_t r = warp_dynamic_bits(s, b.scratch, lane);
+  uint64_t r = warp_dynamic_bits(s.hist, s.u.cs, b.scratch, lane);
   if (lane == 0) *out = r;
 }
 
@@ -76,6 +77,10 @@ struct Engine::Impl {
   // batch arenas
   DevBuf segs, keywork, poswork, order, hv, hv2, idx1, idx2, rank1, rank2, bkt1, bkt2, ld, mlen, runs, dsx,
       ovf, la, path, st[4], jobs, scratch, out_ll, out_d, counters, logtab, misc;
+  // split service
+  DevBuf sp_ll, sp_d, sp_llsym, sp_dsym, sp_pos, sp_snaps, sp_stores, sp_work, sp_evals, sp_out, sp_scratch;
+  std::vector<SplitStoreDesc> sp_desc;
+  SplitBatch sp_batch;
   uint32_t ovf_cap = 1u << 22;
   std::thread log_thread;
   std::vector<double> log_host;
@@ -483,6 +488,87 @@ void Engine::match_table(uint64_t instart, uint64_t inend, std::vector<uint16_t>
       }
     }
   }
+}
+
+void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vector<uint64_t>& off,
+                         const std::vector<uint32_t>& size) {
+  std::lock_guard<std::mutex> g(p_->mu);
+  Impl& m = *p_;
+  CK(cudaSetDevice(m.dev));
+  const size_t ns = off.size();
+  uint64_t total = 0, nsnap_total = 0;
+  for (size_t i = 0; i < ns; i++) total = std::max<uint64_t>(total, off[i] + size[i]);
+  m.sp_desc.resize(ns);
+  std::vector<SnapWork> work;
+  for (size_t i = 0; i < ns; i++) {
+    SplitStoreDesc& sd = m.sp_desc[i];
+    sd.sym_off = off[i];
+    sd.n = size[i];
+    sd.nsnap = size[i] / kSnap + 1;
+    sd.snap_off = nsnap_total;
+    nsnap_total += sd.nsnap;
+    for (uint32_t c = 0; c * kSnap < size[i]; c++) work.push_back({(uint32_t)i, c});
+  }
+  m.sp_ll.ensure(total * 2 + 64);
+  m.sp_d.ensure(total * 2 + 64);
+  m.sp_llsym.ensure(total * 2 + 64);
+  m.sp_dsym.ensure(total + 64);
+  m.sp_pos.ensure((total + ns + 1) * 4 + 64);
+  m.sp_snaps.ensure(nsnap_total * 320 * 4 + 64);
+  m.tic();
+  if (total) {
+    CK(cudaMemcpyAsync(m.sp_ll.p, ll, total * 2, cudaMemcpyHostToDevice, m.stream));
+    CK(cudaMemcpyAsync(m.sp_d.p, d, total * 2, cudaMemcpyHostToDevice, m.stream));
+  }
+  m.upload(m.sp_stores, m.sp_desc);
+  m.upload(m.sp_work, work);
+  SplitBatch& b = m.sp_batch;
+  b.ll = m.sp_ll.as<uint16_t>();
+  b.d = m.sp_d.as<uint16_t>();
+  b.llsym = m.sp_llsym.as<uint16_t>();
+  b.dsym = m.sp_dsym.as<uint8_t>();
+  b.pos = m.sp_pos.as<uint32_t>();
+  b.snaps = m.sp_snaps.as<uint32_t>();
+  b.stores = m.sp_stores.as<SplitStoreDesc>();
+  b.scratch = nullptr;
+  for (size_t i = 0; i < ns; i++)
+    if (size[i]) k_split_prep_sym<<<(size[i] + 255) / 256, 256, 0, m.stream>>>(b, (uint32_t)i);
+  if (ns) k_split_prep_pos<<<(unsigned)ns, 1024, 0, m.stream>>>(b);
+  if (!work.empty())
+    k_split_prep_snap<<<(unsigned)((work.size() + 7) / 8), 256, 0, m.stream>>>(b, m.sp_work.as<SnapWork>(), (uint32_t)work.size());
+  if (ns) k_split_prep_prefix<<<(unsigned)ns, 320, 0, m.stream>>>(b);
+  CK(cudaGetLastError());
+  m.toc(m.st_acc.ms_split);
+  m.st_acc.launches += ns + 3;
+  m.st_acc.h2d_bytes += total * 4;
+}
+
+void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs) {
+  std::lock_guard<std::mutex> g(p_->mu);
+  Impl& m = *p_;
+  CK(cudaSetDevice(m.dev));
+  if (n == 0) return;
+  const size_t kChunk = 32768;  // scratch is per evaluation: bound it
+  m.sp_scratch.ensure(std::min(n, kChunk) * kIterScratch);
+  m.sp_evals.ensure(n * sizeof(SplitEval) + 64);
+  m.sp_out.ensure(n * 8 + 64);
+  std::vector<SplitEval> ev(n);
+  for (size_t i = 0; i < n; i++) ev[i] = {reqs[i].store, reqs[i].lstart, reqs[i].lend, 0};
+  m.tic();
+  CK(cudaMemcpyAsync(m.sp_evals.p, ev.data(), n * sizeof(SplitEval), cudaMemcpyHostToDevice, m.stream));
+  SplitBatch b = m.sp_batch;
+  b.scratch = m.sp_scratch.as<uint8_t>();
+  for (size_t o = 0; o < n; o += kChunk) {
+    const size_t c = std::min(kChunk, n - o);
+    k_split_eval<<<(unsigned)((c + kEvalWarps - 1) / kEvalWarps), kEvalWarps * 32, 0, m.stream>>>(
+        b, m.sp_evals.as<SplitEval>() + o, (uint32_t)c, m.sp_out.as<uint64_t>() + o);
+    m.st_acc.launches++;
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(costs, m.sp_out.p, n * 8, cudaMemcpyDeviceToHost, m.stream));
+  m.toc(m.st_acc.ms_split);
+  m.st_acc.split_evals += n;
+  m.st_acc.split_rounds++;
 }
 
 uint64_t Engine::device_block_bits(const uint32_t* hist320) {

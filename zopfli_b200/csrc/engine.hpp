@@ -21,7 +21,8 @@ struct ParseResult {        // symbols of range i: [off[i], off[i]+size[i]) in l
 };
 
 struct EngineStats {  // accumulated since the last reset; times from CUDA events on the engine stream
-  double ms_same, ms_keys, ms_scan, ms_scatter, ms_match, ms_greedy, ms_iterate, ms_pack, ms_h2d, ms_d2h;
+  double ms_same, ms_keys, ms_scan, ms_scatter, ms_match, ms_greedy, ms_iterate, ms_pack, ms_h2d, ms_d2h, ms_split;
+  uint64_t split_evals, split_rounds;
   uint64_t launches;
   uint64_t match_positions, iterate_positions, iterate_steps;  // steps = positions x iterations
   uint64_t h2d_bytes, d2h_bytes;
@@ -49,6 +50,14 @@ class Engine {
                    std::vector<uint16_t>& same, std::vector<uint16_t>& hv, std::vector<uint16_t>& hv2);
   // test seam: device-side exact dynamic block size of a 320-bin histogram
   uint64_t device_block_bits(const uint32_t* hist320);
+
+  // Split-cost service (ZopfliCalculateBlockSizeAutoType over symbol ranges, deflate.c:610-621):
+  // split_begin uploads n stores given as flat symbol arrays with per-store offset/size,
+  // split_eval prices a batch of (store, lstart, lend) ranges on the device.
+  void split_begin(const uint16_t* ll, const uint16_t* d, const std::vector<uint64_t>& off,
+                   const std::vector<uint32_t>& size);
+  struct SplitReq { uint32_t store, lstart, lend; };
+  void split_eval(const SplitReq* reqs, size_t n, uint64_t* costs);
 
   void set_stream(void* cuda_stream);  // optional: run on the caller's stream
   EngineStats stats();

@@ -136,28 +136,28 @@ __device__ bool warp_entropy(const uint32_t* cnt, int n, double* out, const Batc
 }
 
 // exact dynamic block size from s.hist (hist[256] already 1): deflate.c:569-608.
-__device__ uint64_t warp_dynamic_bits(IterSmem& s, uint8_t* scratch, uint32_t lane) {
+__device__ uint64_t warp_dynamic_bits(const uint32_t* hist, CostStage& cs, uint8_t* scratch, uint32_t lane) {
   // four length-limited code constructions side by side: lanes 0..3 run the same instruction
   // stream on (ll plain, d plain, ll smoothed, d smoothed)
   if (lane < 4) {
     const bool isd = lane & 1, smooth = lane >= 2;
     const int n = isd ? kNumD : kNumLL;
-    const uint32_t* src = s.hist + (isd ? 288 : 0);
-    uint32_t* c2 = s.u.cs.cnt2 + (isd ? 288 : 0);
+    const uint32_t* src = hist + (isd ? 288 : 0);
+    uint32_t* c2 = cs.cnt2 + (isd ? 288 : 0);
     PmBig* pb = (PmBig*)(scratch + (size_t)lane * (kIterScratch / 4));
     if (smooth) {
       for (int i = 0; i < n; i++) c2[i] = src[i];
       optimize_for_rle(n, c2, pb->good);
       src = c2;
     }
-    uint8_t* out = s.u.cs.len[smooth ? 1 : 0] + (isd ? 288 : 0);
+    uint8_t* out = cs.len[smooth ? 1 : 0] + (isd ? 288 : 0);
     length_limited<kNumLL, 15>(src, n, 15, out, pb->pm);
     if (isd) patch_distance_codes(out);
   }
   __syncwarp();
   uint32_t tsz = 0xffffffffu;
   if (lane < 16) {
-    const uint8_t* l = s.u.cs.len[lane >> 3];
+    const uint8_t* l = cs.len[lane >> 3];
     tsz = encode_tree_size(l, l + 288, (lane & 1) != 0, (lane & 2) != 0, (lane & 4) != 0);
   }
   // min over lanes 0..7 and 8..15 (deflate.c:277-290)
@@ -170,14 +170,14 @@ __device__ uint64_t warp_dynamic_bits(IterSmem& s, uint8_t* scratch, uint32_t la
   // symbol bits of both length sets (deflate.c:379-401), all lanes
   uint64_t sb0 = 0, sb1 = 0;
   for (int i = lane; i < 320; i += 32) {
-    uint32_t c = s.hist[i];
+    uint32_t c = hist[i];
     int extra;
     bool use;
     if (i < 288) { use = i < 256 || (i >= 257 && i < 286); extra = i >= 257 ? length_symbol_extra_bits(i) : 0; }
     else { use = (i - 288) < 30; extra = dist_symbol_extra_bits(i - 288); }
     if (use) {
-      sb0 += (uint64_t)(s.u.cs.len[0][i] + extra) * c;
-      sb1 += (uint64_t)(s.u.cs.len[1][i] + extra) * c;
+      sb0 += (uint64_t)(cs.len[0][i] + extra) * c;
+      sb1 += (uint64_t)(cs.len[1][i] + extra) * c;
     }
   }
 #pragma unroll
@@ -185,8 +185,8 @@ __device__ uint64_t warp_dynamic_bits(IterSmem& s, uint8_t* scratch, uint32_t la
     sb0 += __shfl_xor_sync(0xffffffffu, sb0, d);
     sb1 += __shfl_xor_sync(0xffffffffu, sb1, d);
   }
-  const uint64_t size0 = tree0 + sb0 + s.u.cs.len[0][256];
-  const uint64_t size1 = tree1 + sb1 + s.u.cs.len[1][256];
+  const uint64_t size0 = tree0 + sb0 + cs.len[0][256];
+  const uint64_t size1 = tree1 + sb1 + cs.len[1][256];
   return 3 + (size1 < size0 ? size1 : size0);  // deflate.c:553-559
 }
 
@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
     __syncwarp();
 
     // ------------------------------------------------------------------ block size, best, statistics
-    const uint64_t cost = warp_dynamic_bits(s, scratch, lane);  // squeeze.c:492
+    const uint64_t cost = warp_dynamic_bits(s.hist, s.u.cs, scratch, lane);  // squeeze.c:492
     ZB_TICK(4);
     if (cost < bestcost) {  // squeeze.c:496-501
       int t = curbuf; curbuf = bestbuf; bestbuf = t;
