@@ -496,7 +496,7 @@ void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vecto
   Impl& m = *p_;
   CK(cudaSetDevice(m.dev));
   const size_t ns = off.size();
-  uint64_t total = 0, nsnap_total = 0;
+  uint64_t total = 0, nsnap_total = 0, pos_total = 0;
   for (size_t i = 0; i < ns; i++) total = std::max<uint64_t>(total, off[i] + size[i]);
   m.sp_desc.resize(ns);
   std::vector<SnapWork> work;
@@ -507,14 +507,17 @@ void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vecto
     sd.nsnap = size[i] / kSnap + 1;
     sd.snap_off = nsnap_total;
     nsnap_total += sd.nsnap;
+    sd.pos_off = pos_total;  // independent of sym_off: stores may sit in any order in the flat arrays
+    pos_total += (uint64_t)size[i] + 1;
     for (uint32_t c = 0; c * kSnap < size[i]; c++) work.push_back({(uint32_t)i, c});
   }
   m.sp_ll.ensure(total * 2 + 64);
   m.sp_d.ensure(total * 2 + 64);
   m.sp_llsym.ensure(total * 2 + 64);
   m.sp_dsym.ensure(total + 64);
-  m.sp_pos.ensure((total + ns + 1) * 4 + 64);
+
   m.sp_snaps.ensure(nsnap_total * 320 * 4 + 64);
+  m.sp_pos.ensure(pos_total * 4 + 64);
   m.tic();
   if (total) {
     CK(cudaMemcpyAsync(m.sp_ll.p, ll, total * 2, cudaMemcpyHostToDevice, m.stream));

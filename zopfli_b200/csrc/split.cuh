@@ -17,6 +17,7 @@ constexpr uint32_t kSnap = 256;
 struct SplitStoreDesc {
   uint64_t sym_off;    // offset of this store's symbols in the flat arrays
   uint64_t snap_off;   // offset (in snapshots of 320 u32) of this store's snapshot table
+  uint64_t pos_off;    // offset of this store's n+1 byte positions in `pos`
   uint32_t n;          // symbols
   uint32_t nsnap;      // n / kSnap + 1
 };
@@ -28,7 +29,7 @@ struct SplitBatch {
   const uint16_t* d;
   uint16_t* llsym;
   uint8_t* dsym;
-  uint32_t* pos;         // byte offset of each symbol relative to its store start; [n+1] per store (sym_off + store index)
+  uint32_t* pos;         // byte offset of each symbol relative to its store start; n+1 entries at pos_off
   uint32_t* snaps;       // prefix histograms at multiples of kSnap
   const SplitStoreDesc* stores;
   uint8_t* scratch;      // per eval-warp kIterScratch bytes
@@ -49,7 +50,7 @@ __global__ void k_split_prep_pos(SplitBatch b) {
   const SplitStoreDesc sd = b.stores[store];
   __shared__ uint32_t part[1024];
   __shared__ uint32_t carry_s;
-  uint32_t* pos = b.pos + sd.sym_off + store;
+  uint32_t* pos = b.pos + sd.pos_off;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
   for (uint32_t base = 0; base < sd.n; base += 1024 * 8) {
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_split_eval(SplitBatch b, co
   const uint16_t* llsym = b.llsym + sd.sym_off;
   const uint8_t* dsym = b.dsym + sd.sym_off;
   const uint16_t* dd = b.d + sd.sym_off;
-  const uint32_t* pos = b.pos + sd.sym_off + e.store;
+  const uint32_t* pos = b.pos + sd.pos_off;
   // ---- range histogram (ZopfliLZ77GetHistogram lz77.c:189-217) ----
   for (int i = lane; i < 320; i += 32) s.hist[i] = 0;
   __syncwarp();
