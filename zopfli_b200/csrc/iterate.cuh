@@ -346,15 +346,21 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
       // per-group scalars: mlen16 (lane-distributed) and literal costs staged in shared memory
       uint32_t mk_cur = 0, mk_next = 0;      // mlen16 of position 32g+lane for the current / next group
       uint32_t flag_cur = 0, flag_next = 0;  // ballot: position needs the general path (shortcut flag or mlen > 34)
-      auto acquire = [&](uint32_t g, uint32_t seq) {  // make group g readable; all lanes
-        mbar_wait(&s.mbar[seq & 3], (seq >> 2) & 1);
+      // scalars of a group are fetched one group ahead into registers (pf_m16 / pf_byte) so that the
+      // global-load latency never sits on the DP chain
+      uint32_t pf_m16 = 0, pf_byte = 0;
+      auto prefetch_scalars = [&](uint32_t g) {
         const uint32_t p = g * 32 + lane;
-        uint32_t m16 = 0;
-        double lc = 0.0;
-        if (p < nb) { m16 = mlen[p]; lc = s.llcost[in[p]]; }
-        s.u.dp.gl[(g & 1) * 32 + lane] = lc;
+        pf_m16 = 0; pf_byte = 0;
+        if (p < nb) { pf_m16 = mlen[p]; pf_byte = in[p]; }
+      };
+      auto acquire = [&](uint32_t g, uint32_t seq) {  // make group g readable; all lanes
+        const uint32_t m16 = pf_m16;
+        s.u.dp.gl[(g & 1) * 32 + lane] = s.llcost[pf_byte];
         mk_next = m16;
         flag_next = __ballot_sync(full, (m16 & kShortcutFlag) != 0 || (m16 & 0x7fffu) > 34u);
+        prefetch_scalars(g + 1);
+        mbar_wait(&s.mbar[seq & 3], (seq >> 2) & 1);
         __syncwarp();
       };
       if (lane == 0) {
@@ -362,6 +368,7 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
         if (ngroups > 1) issue_group(1, seq_base + 1);
         if (ngroups > 2) issue_group(2, seq_base + 2);
       }
+      prefetch_scalars(0);
       acquire(0, seq_base);
       mk_cur = mk_next; flag_cur = flag_next;
       // register window and pipeline state.  Lane l owns the targets t == l (mod 32): at step j
