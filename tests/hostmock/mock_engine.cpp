@@ -38,7 +38,7 @@ void Engine::set_input_host(const uint8_t* in, size_t n) {
   p_->in.resize(n + 64, 0);
 }
 void Engine::set_input_device(const uint8_t*, size_t) {}
-void Engine::parse(const std::vector<ParseRange>& r, ParseResult& out) {
+void Engine::parse(const std::vector<ParseRange>& r, ParseResult& out, int) {
   out.off.assign(r.size(), 0);
   out.size.assign(r.size(), 0);
   out.cost.assign(r.size(), 0);
@@ -66,7 +66,7 @@ uint64_t Engine::device_block_bits(const uint32_t*) { return 0; }
 // scheduler (batched_split.hpp) is exercised on CPU exactly as the driver uses it
 static std::vector<zb::Lz77Store> g_split_stores;
 void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vector<uint64_t>& off,
-                         const std::vector<uint32_t>& size) {
+                         const std::vector<uint32_t>& size, int) {
   g_split_stores.clear();
   g_split_stores.resize(off.size());
   for (size_t i = 0; i < off.size(); i++) {
@@ -74,7 +74,7 @@ void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vecto
     g_split_stores[i].finalize();
   }
 }
-void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs) {
+void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int) {
   static thread_local DynScratch s;
   for (size_t i = 0; i < n; i++) costs[i] = auto_type_bits(g_split_stores[reqs[i].store], reqs[i].lstart, reqs[i].lend, s);
 }

@@ -163,3 +163,13 @@ def test_multi_master_block_and_spans(ref, mock):
     want = ref.compress(mix, 2, numiterations=1)
     spans = [mock.deflate_span(mix, m, m + 1, final=int(m == 1), numiterations=1) for m in range(2)]
     assert mock.splice_spans(spans)[0] == want
+
+
+def test_two_lane_finalisation_order(ref, mock, monkeypatch):
+    """Master blocks without a "giant" block are finalised while the giants' lane is still busy
+    (driver.cpp stage C); the stream must not depend on which master block finishes first."""
+    data = TXT
+    want = ref.compress(data, 2, numiterations=1)
+    for giant in (20000, 60000, 150000):   # different clean/dirty partitions of the master blocks
+        monkeypatch.setenv("ZOPFLI_B200_GIANT", str(giant))
+        assert mock.compress(data, 2, numiterations=1) == want, giant

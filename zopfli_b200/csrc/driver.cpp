@@ -99,12 +99,12 @@ bool host_split_forced() {
 // ZopfliBlockSplitLZ77 for many stores at once, split costs priced by the device (k_split_eval)
 std::vector<std::vector<size_t>> device_block_split(Engine& eng, const uint16_t* ll, const uint16_t* d,
                                                     const std::vector<uint64_t>& off, const std::vector<uint32_t>& size,
-                                                    size_t maxblocks) {
-  eng.split_begin(ll, d, off, size);
+                                                    size_t maxblocks, int lane = 1) {
+  eng.split_begin(ll, d, off, size, lane);
   std::vector<size_t> sizes(size.begin(), size.end());
   return batched_block_split(sizes, maxblocks, [&](const std::vector<EvalReq>& r, std::vector<uint64_t>& c) {
     static_assert(sizeof(EvalReq) == sizeof(Engine::SplitReq), "layout");
-    eng.split_eval(reinterpret_cast<const Engine::SplitReq*>(r.data()), r.size(), c.data());
+    eng.split_eval(reinterpret_cast<const Engine::SplitReq*>(r.data()), r.size(), c.data(), lane);
   });
 }
 
@@ -208,157 +208,200 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
         pr.push_back({M[m].cuts[i] - in_base, M[m].cuts[i + 1] - in_base, 1, opt->numiterations});
         owner.push_back({m, i});
       }
-    ParseResult res;
-    eng.parse(pr, res);
+    // The critical path of this stage is the DP chain of the largest blocks.  Giant blocks go to
+    // engine lane 0 on their own (their tables are ready within milliseconds, so their iterate
+    // kernel starts at once); everything else is prepared and parsed on lane 1 meanwhile.
+    uint64_t kGiant = 250000;
+    if (const char* e = getenv("ZOPFLI_B200_GIANT")) kGiant = strtoull(e, nullptr, 10);  // tests: force the two-lane path
+    std::vector<ParseRange> prs[2];
+    std::vector<size_t> idx[2];
+    for (size_t k = 0; k < pr.size(); k++) {
+      const int lane = (pr[k].inend - pr[k].instart >= kGiant) ? 0 : 1;
+      prs[lane].push_back(pr[k]);
+      idx[lane].push_back(k);
+    }
+    ParseResult res[2];
     for (size_t m = 0; m < nm; m++) M[m].blockstores.resize(M[m].cuts.size() - 1);
-    parallel_for(pr.size(), [&](size_t k) {
-      Master& mb = M[owner[k].first];
-      Lz77Store& st = mb.blockstores[owner[k].second];
-      st.append(res.ll.data() + res.off[k], res.d.data() + res.off[k], res.size[k], mb.cuts[owner[k].second]);
-      st.finalize();
-    });
-  }
-  double t3 = now_ms();
-  g_host_times.other += t3 - t0;
-
-  // ---- stage D: second split attempt and block types ----
-  std::vector<std::vector<ParseRange>> fixed_req(nm);
-  std::vector<uint64_t> totalcost(nm, 0);
-  std::vector<std::vector<size_t>> first_points(nm);
-  parallel_for(nm, [&](size_t m) {  // D1: concatenate the blocks, cost of the first split
-    Master& mb = M[m];
-    DynScratch s;
-    const size_t nblocks = mb.blockstores.size();
-    for (size_t i = 0; i < nblocks; i++) {
-      totalcost[m] += auto_type_bits(mb.blockstores[i], 0, mb.blockstores[i].size(), s);  // deflate.c:862
-      mb.lz77.append(mb.blockstores[i]);
-      if (i + 1 < nblocks) first_points[m].push_back(mb.lz77.size());
-    }
-    mb.blockstores.clear();
-    mb.lz77.finalize();
-  });
-  std::vector<std::vector<size_t>> second(nm);
-  std::vector<char> want2(nm, 0);
-  for (size_t m = 0; m < nm; m++) want2[m] = opt->blocksplitting && first_points[m].size() > 1;  // deflate.c:872
-  if (!host_split_forced()) {
-    std::vector<uint64_t> off;
-    std::vector<uint32_t> size;
-    std::vector<size_t> who;
-    uint64_t total = 0;
-    for (size_t m = 0; m < nm; m++)
-      if (want2[m]) { who.push_back(m); off.push_back(total); size.push_back((uint32_t)M[m].lz77.size()); total += M[m].lz77.size(); }
-    if (!who.empty()) {
-      std::vector<uint16_t> fll(total), fd(total);
-      parallel_for(who.size(), [&](size_t k) {
-        const Lz77Store& st = M[who[k]].lz77;
-        memcpy(fll.data() + off[k], st.litlens.data(), st.size() * 2);
-        memcpy(fd.data() + off[k], st.dists.data(), st.size() * 2);
+    auto adopt = [&](int lane) {  // parse results of one lane -> per-block stores
+      const ParseResult& r = res[lane];
+      parallel_for(idx[lane].size(), [&](size_t q) {
+        const size_t k = idx[lane][q];
+        Master& mb = M[owner[k].first];
+        Lz77Store& st = mb.blockstores[owner[k].second];
+        st.append(r.ll.data() + r.off[q], r.d.data() + r.off[q], r.size[q], mb.cuts[owner[k].second]);
+        st.finalize();
       });
-      std::vector<std::vector<size_t>> r = device_block_split(eng, fll.data(), fd.data(), off, size, maxblocks);
-      for (size_t k = 0; k < who.size(); k++) second[who[k]] = r[k];
-    }
-  }
-  parallel_for(nm, [&](size_t m) {  // D2
-    Master& mb = M[m];
-    DynScratch s;
-    std::vector<size_t> points = first_points[m];
-    if (want2[m]) {  // deflate.c:872-893
-      std::vector<size_t> p2 = host_split_forced() ? block_split_lz77(make_cost(mb.lz77), mb.lz77.size(), maxblocks) : second[m];
-      uint64_t totalcost2 = 0;
-      for (size_t i = 0; i <= p2.size(); i++) {
-        size_t a = i == 0 ? 0 : p2[i - 1], b = i == p2.size() ? mb.lz77.size() : p2[i];
-        totalcost2 += auto_type_bits(mb.lz77, a, b, s);
-      }
-      if (totalcost2 < totalcost[m]) points = p2;
-    }
-    mb.points = points;
-    for (size_t i = 0; i <= points.size(); i++) {  // AddLZ77BlockAutoType deflate.c:747-800
-      FinalBlock fb;
-      fb.lstart = i == 0 ? 0 : points[i - 1];
-      fb.lend = i == points.size() ? mb.lz77.size() : points[i];
-      uint32_t h[320];
-      mb.lz77.range_hist(fb.lstart, fb.lend, h);
-      fb.unc = stored_bits(mb.lz77.byte_range(fb.lstart, fb.lend));
-      fb.fixed = fixed_block_bits(h);
-      fb.dyn = dynamic_block_bits(h, nullptr, nullptr, s);
-      fb.expensive = (mb.lz77.size() < 1000) || ((double)fb.fixed <= (double)fb.dyn * 1.1);  // :760
-      if (fb.lstart == fb.lend) fb.expensive = false;
-      if (fb.expensive) {
-        size_t a = mb.lz77.pos[fb.lstart];
-        size_t b = a + mb.lz77.byte_range(fb.lstart, fb.lend);
-        fb.fixed_req = (int)fixed_req[m].size();
-        fixed_req[m].push_back({a - in_base, b - in_base, 2, 0});
-      }
-      mb.finals.push_back(fb);
-    }
-  });
-  double t4 = now_ms();
-  g_host_times.split += t4 - t3;
+    };
 
-  // ---- stage E: fixed-tree re-parses ----
-  {
-    std::vector<ParseRange> pr;
-    std::vector<size_t> base(nm, 0);
-    for (size_t m = 0; m < nm; m++) { base[m] = pr.size(); pr.insert(pr.end(), fixed_req[m].begin(), fixed_req[m].end()); }
-    if (!pr.empty()) {
-      ParseResult res;
-      eng.parse(pr, res);
-      for (size_t m = 0; m < nm; m++) {
-        M[m].fixedstores.resize(fixed_req[m].size());
-        for (size_t k = 0; k < fixed_req[m].size(); k++) {
-          size_t g = base[m] + k;
-          M[m].fixedstores[k].append(res.ll.data() + res.off[g], res.d.data() + res.off[g], res.size[g],
-                                     (size_t)pr[g].instart + in_base);
-          M[m].fixedstores[k].finalize();
+    // ---- stages D-F for a set of master blocks whose blocks are all parsed ----
+    auto finish = [&](const std::vector<size_t>& ms, int lane) {
+      const size_t nq = ms.size();
+      if (nq == 0) return;
+      double td0 = now_ms();
+      // stage D: second split attempt and block types
+      std::vector<std::vector<ParseRange>> fixed_req(nq);
+      std::vector<uint64_t> totalcost(nq, 0);
+      std::vector<std::vector<size_t>> first_points(nq);
+      parallel_for(nq, [&](size_t q) {  // D1: concatenate the blocks, cost of the first split
+        Master& mb = M[ms[q]];
+        DynScratch sc;
+        const size_t nblocks = mb.blockstores.size();
+        for (size_t i = 0; i < nblocks; i++) {
+          totalcost[q] += auto_type_bits(mb.blockstores[i], 0, mb.blockstores[i].size(), sc);  // deflate.c:862
+          mb.lz77.append(mb.blockstores[i]);
+          if (i + 1 < nblocks) first_points[q].push_back(mb.lz77.size());
+        }
+        mb.blockstores.clear();
+        mb.lz77.finalize();
+      });
+      std::vector<std::vector<size_t>> second(nq);
+      std::vector<char> want2(nq, 0);
+      for (size_t q = 0; q < nq; q++) want2[q] = opt->blocksplitting && first_points[q].size() > 1;  // deflate.c:872
+      if (!host_split_forced()) {
+        std::vector<uint64_t> off;
+        std::vector<uint32_t> size;
+        std::vector<size_t> who;
+        uint64_t total = 0;
+        for (size_t q = 0; q < nq; q++)
+          if (want2[q]) { who.push_back(q); off.push_back(total); size.push_back((uint32_t)M[ms[q]].lz77.size()); total += M[ms[q]].lz77.size(); }
+        if (!who.empty()) {
+          std::vector<uint16_t> fll(total), fd(total);
+          parallel_for(who.size(), [&](size_t k) {
+            const Lz77Store& st = M[ms[who[k]]].lz77;
+            memcpy(fll.data() + off[k], st.litlens.data(), st.size() * 2);
+            memcpy(fd.data() + off[k], st.dists.data(), st.size() * 2);
+          });
+          std::vector<std::vector<size_t>> r = device_block_split(eng, fll.data(), fd.data(), off, size, maxblocks, lane);
+          for (size_t k = 0; k < who.size(); k++) second[who[k]] = r[k];
         }
       }
-    }
-  }
-  double t5 = now_ms();
-  g_host_times.other += t5 - t4;
+      parallel_for(nq, [&](size_t q) {  // D2
+        Master& mb = M[ms[q]];
+        DynScratch sc;
+        std::vector<size_t> points = first_points[q];
+        if (want2[q]) {  // deflate.c:872-893
+          std::vector<size_t> p2 = host_split_forced() ? block_split_lz77(make_cost(mb.lz77), mb.lz77.size(), maxblocks) : second[q];
+          uint64_t totalcost2 = 0;
+          for (size_t i = 0; i <= p2.size(); i++) {
+            size_t a = i == 0 ? 0 : p2[i - 1], b = i == p2.size() ? mb.lz77.size() : p2[i];
+            totalcost2 += auto_type_bits(mb.lz77, a, b, sc);
+          }
+          if (totalcost2 < totalcost[q]) points = p2;
+        }
+        mb.points = points;
+        for (size_t i = 0; i <= points.size(); i++) {  // AddLZ77BlockAutoType deflate.c:747-800
+          FinalBlock fb;
+          fb.lstart = i == 0 ? 0 : points[i - 1];
+          fb.lend = i == points.size() ? mb.lz77.size() : points[i];
+          uint32_t h[320];
+          mb.lz77.range_hist(fb.lstart, fb.lend, h);
+          fb.unc = stored_bits(mb.lz77.byte_range(fb.lstart, fb.lend));
+          fb.fixed = fixed_block_bits(h);
+          fb.dyn = dynamic_block_bits(h, nullptr, nullptr, sc);
+          fb.expensive = (mb.lz77.size() < 1000) || ((double)fb.fixed <= (double)fb.dyn * 1.1);  // :760
+          if (fb.lstart == fb.lend) fb.expensive = false;
+          if (fb.expensive) {
+            size_t a = mb.lz77.pos[fb.lstart];
+            size_t b = a + mb.lz77.byte_range(fb.lstart, fb.lend);
+            fb.fixed_req = (int)fixed_req[q].size();
+            fixed_req[q].push_back({a - in_base, b - in_base, 2, 0});
+          }
+          mb.finals.push_back(fb);
+        }
+      });
+      double td1 = now_ms();
+      g_host_times.split += td1 - td0;
+      // stage E: fixed-tree re-parses
+      {
+        std::vector<ParseRange> prf;
+        std::vector<size_t> base(nq, 0);
+        for (size_t q = 0; q < nq; q++) { base[q] = prf.size(); prf.insert(prf.end(), fixed_req[q].begin(), fixed_req[q].end()); }
+        if (!prf.empty()) {
+          ParseResult rf;
+          eng.parse(prf, rf, lane);
+          for (size_t q = 0; q < nq; q++) {
+            Master& mb = M[ms[q]];
+            mb.fixedstores.resize(fixed_req[q].size());
+            for (size_t k = 0; k < fixed_req[q].size(); k++) {
+              size_t g = base[q] + k;
+              mb.fixedstores[k].append(rf.ll.data() + rf.off[g], rf.d.data() + rf.off[g], rf.size[g],
+                                       (size_t)prf[g].instart + in_base);
+              mb.fixedstores[k].finalize();
+            }
+          }
+        }
+      }
+      double td2 = now_ms();
+      g_host_times.other += td2 - td1;
+      // stage F: emission, one task per final block
+      std::vector<std::pair<size_t, size_t>> tasks;
+      for (size_t q = 0; q < nq; q++) {
+        M[ms[q]].pieces.resize(M[ms[q]].finals.size());
+        for (size_t i = 0; i < M[ms[q]].finals.size(); i++) tasks.push_back({ms[q], i});
+      }
+      parallel_for(tasks.size(), [&](size_t t) {
+        Master& mb = M[tasks[t].first];
+        const size_t i = tasks[t].second;
+        FinalBlock& fb = mb.finals[i];
+        Piece& p = mb.pieces[i];
+        const bool final = final_last && tasks[t].first + 1 == nm && i + 1 == mb.finals.size();
+        if (fb.lstart == fb.lend) {  // deflate.c:763-768
+          p.bits.add_bits(final ? 1 : 0, 1);
+          p.bits.add_bits(1, 2);
+          p.bits.add_bits(0, 7);
+          p.bits.flush();
+          return;
+        }
+        uint64_t fixedcost = fb.fixed;
+        const Lz77Store* fst = nullptr;
+        if (fb.expensive) {
+          fst = &mb.fixedstores[fb.fixed_req];
+          uint32_t h[320];
+          fst->range_hist(0, fst->size(), h);
+          fixedcost = fixed_block_bits(h);  // deflate.c:779
+        }
+        if (fb.unc < fixedcost && fb.unc < fb.dyn) {  // deflate.c:783-785
+          p.stored = true;
+          p.instart = mb.lz77.pos[fb.lstart];
+          p.inend = p.instart + mb.lz77.byte_range(fb.lstart, fb.lend);
+          p.final = final;
+        } else if (fixedcost < fb.dyn) {
+          if (fb.expensive) emit_compressed_block(1, final, *fst, 0, fst->size(), p.bits);
+          else emit_compressed_block(1, final, mb.lz77, fb.lstart, fb.lend, p.bits);
+        } else {
+          emit_compressed_block(2, final, mb.lz77, fb.lstart, fb.lend, p.bits);
+        }
+      });
+      g_host_times.emit += now_ms() - td2;
+    };
 
-  // ---- stage F: emission, one task per final block ----
-  std::vector<std::pair<size_t, size_t>> tasks;
-  for (size_t m = 0; m < nm; m++) {
-    M[m].pieces.resize(M[m].finals.size());
-    for (size_t i = 0; i < M[m].finals.size(); i++) tasks.push_back({m, i});
-  }
-  parallel_for(tasks.size(), [&](size_t t) {
-    Master& mb = M[tasks[t].first];
-    const size_t i = tasks[t].second;
-    FinalBlock& fb = mb.finals[i];
-    Piece& p = mb.pieces[i];
-    const bool final = final_last && tasks[t].first + 1 == nm && i + 1 == mb.finals.size();
-    if (fb.lstart == fb.lend) {  // deflate.c:763-768
-      p.bits.add_bits(final ? 1 : 0, 1);
-      p.bits.add_bits(1, 2);
-      p.bits.add_bits(0, 7);
-      p.bits.flush();
-      return;
-    }
-    uint64_t fixedcost = fb.fixed;
-    const Lz77Store* fst = nullptr;
-    if (fb.expensive) {
-      fst = &mb.fixedstores[fb.fixed_req];
-      uint32_t h[320];
-      fst->range_hist(0, fst->size(), h);
-      fixedcost = fixed_block_bits(h);  // deflate.c:779
-    }
-    if (fb.unc < fixedcost && fb.unc < fb.dyn) {  // deflate.c:783-785
-      p.stored = true;
-      p.instart = mb.lz77.pos[fb.lstart];
-      p.inend = p.instart + mb.lz77.byte_range(fb.lstart, fb.lend);
-      p.final = final;
-    } else if (fixedcost < fb.dyn) {
-      if (fb.expensive) emit_compressed_block(1, final, *fst, 0, fst->size(), p.bits);
-      else emit_compressed_block(1, final, mb.lz77, fb.lstart, fb.lend, p.bits);
+    std::vector<size_t> all_ms(nm);
+    for (size_t m = 0; m < nm; m++) all_ms[m] = m;
+    if (prs[0].empty() || prs[1].empty()) {
+      const int only = prs[0].empty() ? 1 : 0;
+      eng.parse(prs[only], res[only], 0);
+      adopt(only);
+      g_host_times.other += now_ms() - t0;
+      finish(all_ms, 1);
     } else {
-      emit_compressed_block(2, final, mb.lz77, fb.lstart, fb.lend, p.bits);
+      std::vector<char> has_giant(nm, 0);
+      for (size_t k : idx[0]) has_giant[owner[k].first] = 1;
+      std::vector<size_t> clean, dirty;
+      for (size_t m = 0; m < nm; m++) (has_giant[m] ? dirty : clean).push_back(m);
+      std::thread tg([&] { eng.parse(prs[0], res[0], 0); });
+      eng.parse(prs[1], res[1], 1);
+      adopt(1);
+      g_host_times.other += now_ms() - t0;
+      finish(clean, 1);   // overlaps the giants' DP chains still running on lane 0
+      double tw = now_ms();
+      tg.join();
+      adopt(0);
+      g_host_times.other += now_ms() - tw;
+      finish(dirty, 1);
     }
-  });
+  }
   for (size_t m = 0; m < nm; m++)
     for (auto& p : M[m].pieces) pieces.push_back(std::move(p));
-  g_host_times.emit += now_ms() - t5;
   (void)in;
 }
 

@@ -34,11 +34,13 @@ namespace {
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  cudaStream_t st = nullptr;  // owning lane's stream: allocations are stream-ordered (cudaMallocAsync),
+                              // so growing one lane's arena never synchronises the whole device
   void ensure(size_t bytes) {
     if (bytes <= cap) return;
-    if (p) CK(cudaFree(p));
+    if (p) CK(cudaFreeAsync(p, st));
     size_t want = bytes + bytes / 8 + 256;
-    CK(cudaMalloc(&p, want));
+    CK(cudaMallocAsync(&p, want, st));
     cap = want;
   }
   template <typename T>
@@ -65,30 +67,57 @@ constexpr uint32_t kLogTabN = 1u << 21;
 
 }  // namespace
 
-struct Engine::Impl {
+struct Lane {  // an independent stream + arena set; two lanes let a batch of giant blocks run beside the rest
   std::mutex mu;
-  int dev = 0;
   cudaStream_t stream = nullptr;
-  bool own_stream = true;
-  // input
-  DevBuf in_buf, same_buf, tile_first, next_tile;
-  const uint8_t* d_in = nullptr;
-  uint64_t insize = 0;
-  // batch arenas
+  cudaEvent_t ev[2];
   DevBuf segs, keywork, poswork, order, hv, hv2, idx1, idx2, rank1, rank2, bkt1, bkt2, ld, mlen, runs, dsx,
-      ovf, la, path, st[4], jobs, scratch, out_ll, out_d, counters, logtab, misc;
+      ovf, la, path, st[4], jobs, scratch, out_ll, out_d, counters, misc;
   // split service
   DevBuf sp_ll, sp_d, sp_llsym, sp_dsym, sp_pos, sp_snaps, sp_stores, sp_work, sp_evals, sp_out, sp_scratch;
   std::vector<SplitStoreDesc> sp_desc;
   SplitBatch sp_batch;
   uint32_t ovf_cap = 1u << 22;
+  EngineStats acc;
+
+  void init() {
+    memset(&acc, 0, sizeof(acc));
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev[0]));
+    CK(cudaEventCreate(&ev[1]));
+    DevBuf* all[] = {&segs, &keywork, &poswork, &order, &hv, &hv2, &idx1, &idx2, &rank1, &rank2, &bkt1, &bkt2, &ld,
+                     &mlen, &runs, &dsx, &ovf, &la, &path, &st[0], &st[1], &st[2], &st[3], &jobs, &scratch, &out_ll,
+                     &out_d, &counters, &misc, &sp_ll, &sp_d, &sp_llsym, &sp_dsym, &sp_pos, &sp_snaps, &sp_stores,
+                     &sp_work, &sp_evals, &sp_out, &sp_scratch};
+    for (DevBuf* d : all) d->st = stream;
+  }
+  void tic() { CK(cudaEventRecord(ev[0], stream)); }
+  void toc(double& a) {
+    CK(cudaEventRecord(ev[1], stream));
+    CK(cudaEventSynchronize(ev[1]));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+    a += ms;
+  }
+  template <typename T>
+  void upload(DevBuf& d, const std::vector<T>& v) {
+    d.ensure(v.size() * sizeof(T) + 16);
+    if (!v.empty()) CK(cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+  }
+};
+
+struct Engine::Impl {
+  std::mutex mu;  // input / log table / statistics
+  int dev = 0;
+  Lane lane[2];
+  // input (shared, read-only while parses run)
+  DevBuf in_buf, same_buf, tile_first, next_tile, logtab;
+  const uint8_t* d_in = nullptr;
+  uint64_t insize = 0;
   std::thread log_thread;
   std::vector<double> log_host;
   bool log_ready = false;
-  EngineStats st_acc;
-  cudaEvent_t ev[2];
-  uint8_t* pinned = nullptr;
-  size_t pinned_cap = 0;
+  EngineStats st_acc;  // input-side counters; lane counters are merged in stats()
 
   Impl() {
     memset(&st_acc, 0, sizeof(st_acc));
@@ -106,9 +135,14 @@ struct Engine::Impl {
       if (lr) dev = atoi(lr) % n;
     }
     CK(cudaSetDevice(dev));
-    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&ev[0]));
-    CK(cudaEventCreate(&ev[1]));
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = ~0ull;  // keep freed arena memory cached in the pool
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    lane[0].init();
+    lane[1].init();
+    DevBuf* shared[] = {&in_buf, &same_buf, &tile_first, &next_tile, &logtab};
+    for (DevBuf* d : shared) d->st = lane[0].stream;
     CK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
     // L[n] = log(n) * kInvLog2 with the HOST libm, exactly the two operations of tree.c:79,85
     log_thread = std::thread([this]() {
@@ -122,37 +156,30 @@ struct Engine::Impl {
     });
   }
 
-  void ensure_log() {
+  void ensure_log() {  // caller holds mu
     if (log_ready) return;
     log_thread.join();
+    Lane& l = lane[0];
     logtab.ensure(kLogTabN * sizeof(double));
-    CK(cudaMemcpyAsync(logtab.p, log_host.data(), kLogTabN * sizeof(double), cudaMemcpyHostToDevice, stream));
-    CK(cudaStreamSynchronize(stream));
+    CK(cudaMemcpyAsync(logtab.p, log_host.data(), kLogTabN * sizeof(double), cudaMemcpyHostToDevice, l.stream));
+    CK(cudaStreamSynchronize(l.stream));
     log_ready = true;
   }
 
-  void tic() { CK(cudaEventRecord(ev[0], stream)); }
-  void toc(double& acc) {
-    CK(cudaEventRecord(ev[1], stream));
-    CK(cudaEventSynchronize(ev[1]));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
-    acc += ms;
-  }
-
-  void compute_same() {
+  void compute_same() {  // caller holds mu; runs on lane 0's stream and completes before returning
     if (insize == 0) return;
+    Lane& l = lane[0];
     uint32_t ntiles = (uint32_t)((insize + kSameTile - 1) / kSameTile);
     same_buf.ensure(insize * sizeof(uint16_t) + 64);
     tile_first.ensure(ntiles * sizeof(uint32_t));
     next_tile.ensure(ntiles * sizeof(uint32_t));
-    tic();
-    k_same_tiles<<<ntiles, 256, 0, stream>>>(d_in, insize, tile_first.as<uint32_t>());
-    k_same_next_tile<<<1, 1024, 0, stream>>>(tile_first.as<uint32_t>(), ntiles, next_tile.as<uint32_t>());
-    k_same_fill<<<ntiles, 256, 0, stream>>>(d_in, insize, tile_first.as<uint32_t>(), next_tile.as<uint32_t>(),
-                                            ntiles, same_buf.as<uint16_t>());
+    l.tic();
+    k_same_tiles<<<ntiles, 256, 0, l.stream>>>(d_in, insize, tile_first.as<uint32_t>());
+    k_same_next_tile<<<1, 1024, 0, l.stream>>>(tile_first.as<uint32_t>(), ntiles, next_tile.as<uint32_t>());
+    k_same_fill<<<ntiles, 256, 0, l.stream>>>(d_in, insize, tile_first.as<uint32_t>(), next_tile.as<uint32_t>(),
+                                              ntiles, same_buf.as<uint16_t>());
     CK(cudaGetLastError());
-    toc(st_acc.ms_same);
+    l.toc(st_acc.ms_same);
     st_acc.launches += 3;
   }
 
@@ -199,104 +226,98 @@ struct Engine::Impl {
     });
   }
 
-  template <typename T>
-  void upload(DevBuf& d, const std::vector<T>& v) {
-    d.ensure(v.size() * sizeof(T) + 16);
-    if (!v.empty()) CK(cudaMemcpyAsync(d.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
-  }
-
-  // runs everything up to and including the match table; returns the Batch
-  Batch prepare(const Layout& L) {
+  // runs everything up to and including the match table on lane l; returns the Batch
+  Batch prepare(const Layout& L, Lane& l) {
     const size_t ns = L.segs.size();
-    upload(segs, L.segs);
-    upload(keywork, L.kw);
-    upload(poswork, L.pw);
-    upload(order, L.order);
-    hv.ensure(L.nkeys * 2 + 64);
-    hv2.ensure(L.nkeys * 2 + 64);
-    idx1.ensure(L.nkeys * 4 + 64);
-    idx2.ensure(L.nkeys * 4 + 64);
-    rank1.ensure(L.nkeys * 4 + 64);
-    rank2.ensure(L.nkeys * 4 + 64);
-    bkt1.ensure(ns * 32769 * 4 + 64);
-    bkt2.ensure(ns * 32769 * 4 + 64);
-    ld.ensure(L.npos * 4 + 64);
-    for (int i = 0; i < 4; i++) st[i].ensure(L.npos * 2 + 64);
-    jobs.ensure(ns * sizeof(JobState) + 64);
-    out_ll.ensure(L.npos * 2 + 64);
-    out_d.ensure(L.npos * 2 + 64);
-    counters.ensure(256);
-    scratch.ensure(std::max<size_t>(ns, 1) * kIterScratch);
+    l.upload(l.segs, L.segs);
+    l.upload(l.keywork, L.kw);
+    l.upload(l.poswork, L.pw);
+    l.upload(l.order, L.order);
+    l.hv.ensure(L.nkeys * 2 + 64);
+    l.hv2.ensure(L.nkeys * 2 + 64);
+    l.idx1.ensure(L.nkeys * 4 + 64);
+    l.idx2.ensure(L.nkeys * 4 + 64);
+    l.rank1.ensure(L.nkeys * 4 + 64);
+    l.rank2.ensure(L.nkeys * 4 + 64);
+    l.bkt1.ensure(ns * 32769 * 4 + 64);
+    l.bkt2.ensure(ns * 32769 * 4 + 64);
+    l.ld.ensure(L.npos * 4 + 64);
+    for (int i = 0; i < 4; i++) l.st[i].ensure(L.npos * 2 + 64);
+    l.jobs.ensure(ns * sizeof(JobState) + 64);
+    l.out_ll.ensure(L.npos * 2 + 64);
+    l.out_d.ensure(L.npos * 2 + 64);
+    l.counters.ensure(256);
+    l.scratch.ensure(std::max<size_t>(ns, 1) * kIterScratch);
     if (L.any_parse) {
-      mlen.ensure(L.npos * 2 + 64);
-      runs.ensure(L.npos * kRunSlots * 4 + 64);
-      dsx.ensure(L.npos * 32 + 64);
-      ovf.ensure((size_t)ovf_cap * 4);
-      la.ensure((L.npos + ns) * 2 + 64);
-      path.ensure((L.npos + ns) * 4 + 64);
-      ensure_log();
+      l.mlen.ensure(L.npos * 2 + 64);
+      l.runs.ensure(L.npos * kRunSlots * 4 + 64);
+      l.dsx.ensure(L.npos * 32 + 64);
+      l.ovf.ensure((size_t)l.ovf_cap * 4);
+      l.la.ensure((L.npos + ns) * 2 + 64);
+      l.path.ensure((L.npos + ns) * 4 + 64);
+      { std::lock_guard<std::mutex> g(mu); ensure_log(); }
     }
     Batch b;
     memset(&b, 0, sizeof(b));
     b.in = d_in;
     b.insize = insize;
     b.same_g = same_buf.as<uint16_t>();
-    b.segs = segs.as<SegDesc>();
+    b.segs = l.segs.as<SegDesc>();
     b.nsegs = (int)ns;
-    b.hv = hv.as<uint16_t>();
-    b.hv2 = hv2.as<uint16_t>();
-    b.idx1 = idx1.as<uint32_t>();
-    b.idx2 = idx2.as<uint32_t>();
-    b.rank1 = rank1.as<uint32_t>();
-    b.rank2 = rank2.as<uint32_t>();
-    b.bkt1 = bkt1.as<uint32_t>();
-    b.bkt2 = bkt2.as<uint32_t>();
-    b.ld = ld.as<uint32_t>();
-    b.mlen = mlen.as<uint16_t>();
-    b.runs = runs.as<uint32_t>();
-    b.dsx = dsx.as<uint8_t>();
-    b.ovf = ovf.as<uint32_t>();
-    b.ovf_used = counters.as<uint32_t>();
-    b.ovf_cap = ovf_cap;
-    b.la = la.as<uint16_t>();
-    b.path = path.as<uint32_t>();
-    b.st_ll[0] = st[0].as<uint16_t>();
-    b.st_d[0] = st[1].as<uint16_t>();
-    b.st_ll[1] = st[2].as<uint16_t>();
-    b.st_d[1] = st[3].as<uint16_t>();
+    b.hv = l.hv.as<uint16_t>();
+    b.hv2 = l.hv2.as<uint16_t>();
+    b.idx1 = l.idx1.as<uint32_t>();
+    b.idx2 = l.idx2.as<uint32_t>();
+    b.rank1 = l.rank1.as<uint32_t>();
+    b.rank2 = l.rank2.as<uint32_t>();
+    b.bkt1 = l.bkt1.as<uint32_t>();
+    b.bkt2 = l.bkt2.as<uint32_t>();
+    b.ld = l.ld.as<uint32_t>();
+    b.mlen = l.mlen.as<uint16_t>();
+    b.runs = l.runs.as<uint32_t>();
+    b.dsx = l.dsx.as<uint8_t>();
+    b.ovf = l.ovf.as<uint32_t>();
+    b.ovf_used = l.counters.as<uint32_t>();
+    b.ovf_cap = l.ovf_cap;
+    b.la = l.la.as<uint16_t>();
+    b.path = l.path.as<uint32_t>();
+    b.st_ll[0] = l.st[0].as<uint16_t>();
+    b.st_d[0] = l.st[1].as<uint16_t>();
+    b.st_ll[1] = l.st[2].as<uint16_t>();
+    b.st_d[1] = l.st[3].as<uint16_t>();
     b.st_ll[2] = nullptr;
     b.st_d[2] = nullptr;
-    b.jobs = jobs.as<JobState>();
-    b.scratch = scratch.as<uint8_t>();
+    b.jobs = l.jobs.as<JobState>();
+    b.scratch = l.scratch.as<uint8_t>();
     b.logtab = logtab.as<double>();
     b.logtab_n = kLogTabN;
-    b.out_ll = out_ll.as<uint16_t>();
-    b.out_d = out_d.as<uint16_t>();
-    b.out_used = counters.as<uint32_t>() + 1;
+    b.out_ll = l.out_ll.as<uint16_t>();
+    b.out_d = l.out_d.as<uint16_t>();
+    b.out_used = l.counters.as<uint32_t>() + 1;
 
-    CK(cudaMemsetAsync(bkt1.p, 0, ns * 32769 * 4, stream));
-    CK(cudaMemsetAsync(bkt2.p, 0, ns * 32769 * 4, stream));
-    CK(cudaMemsetAsync(counters.p, 0, 256, stream));
-    CK(cudaMemsetAsync(jobs.p, 0, ns * sizeof(JobState), stream));
+    CK(cudaMemsetAsync(l.bkt1.p, 0, ns * 32769 * 4, l.stream));
+    CK(cudaMemsetAsync(l.bkt2.p, 0, ns * 32769 * 4, l.stream));
+    CK(cudaMemsetAsync(l.counters.p, 0, 256, l.stream));
+    CK(cudaMemsetAsync(l.jobs.p, 0, ns * sizeof(JobState), l.stream));
     if (L.nkeys) {
-      tic();
-      k_keys<<<(unsigned)L.kw.size(), 256, 0, stream>>>(b, keywork.as<KeyWork>());
+      l.tic();
+      k_keys<<<(unsigned)L.kw.size(), 256, 0, l.stream>>>(b, l.keywork.as<KeyWork>());
       CK(cudaGetLastError());
-      toc(st_acc.ms_keys);
-      tic();
-      k_bucket_scan<<<(unsigned)(2 * ns), 1024, 0, stream>>>(b);
+      l.toc(l.acc.ms_keys);
+      l.tic();
+      k_bucket_scan<<<(unsigned)(2 * ns), 1024, 0, l.stream>>>(b);
       CK(cudaGetLastError());
-      toc(st_acc.ms_scan);
-      tic();
-      k_scatter<<<(unsigned)(2 * ns), 32, 32768 * 4, stream>>>(b);
+      l.toc(l.acc.ms_scan);
+      l.tic();
+      k_scatter<<<(unsigned)(2 * ns), 32, 32768 * 4, l.stream>>>(b);
       CK(cudaGetLastError());
-      toc(st_acc.ms_scatter);
-      tic();
-      k_match<<<(unsigned)L.pw.size(), kMatchWarps * 32, 0, stream>>>(b, poswork.as<PosWork>());
+      l.toc(l.acc.ms_scatter);
+      l.tic();
+      k_match<<<(unsigned)L.pw.size(), kMatchWarps * 32, 0, l.stream>>>(b, l.poswork.as<PosWork>());
       CK(cudaGetLastError());
-      toc(st_acc.ms_match);
-      st_acc.launches += 4;
-      st_acc.match_positions += L.npos;
+      l.toc(l.acc.ms_match);
+      l.acc.launches += 4;
+      l.acc.match_positions += L.npos;
     }
     return b;
   }
@@ -314,27 +335,51 @@ int Engine::device() const { return p_->dev; }
 void Engine::set_stream(void* s) {
   std::lock_guard<std::mutex> g(p_->mu);
   CK(cudaSetDevice(p_->dev));
-  if (s) { p_->stream = (cudaStream_t)s; p_->own_stream = false; }
+  if (s) {  // lane 0 adopts the caller's stream (bench timing with events on that stream)
+    Lane& l = p_->lane[0];
+    std::lock_guard<std::mutex> g2(l.mu);
+    l.stream = (cudaStream_t)s;
+    DevBuf* all[] = {&l.segs, &l.keywork, &l.poswork, &l.order, &l.hv, &l.hv2, &l.idx1, &l.idx2, &l.rank1, &l.rank2,
+                     &l.bkt1, &l.bkt2, &l.ld, &l.mlen, &l.runs, &l.dsx, &l.ovf, &l.la, &l.path, &l.st[0], &l.st[1],
+                     &l.st[2], &l.st[3], &l.jobs, &l.scratch, &l.out_ll, &l.out_d, &l.counters, &l.misc, &l.sp_ll,
+                     &l.sp_d, &l.sp_llsym, &l.sp_dsym, &l.sp_pos, &l.sp_snaps, &l.sp_stores, &l.sp_work, &l.sp_evals,
+                     &l.sp_out, &l.sp_scratch, &p_->in_buf, &p_->same_buf, &p_->tile_first, &p_->next_tile, &p_->logtab};
+    for (DevBuf* d : all) d->st = l.stream;
+  }
 }
 
 EngineStats Engine::stats() {
   std::lock_guard<std::mutex> g(p_->mu);
-  return p_->st_acc;
+  EngineStats r = p_->st_acc;
+  for (int k = 0; k < 2; k++) {
+    const EngineStats& a = p_->lane[k].acc;
+    r.ms_keys += a.ms_keys; r.ms_scan += a.ms_scan; r.ms_scatter += a.ms_scatter; r.ms_match += a.ms_match;
+    r.ms_greedy += a.ms_greedy; r.ms_iterate += a.ms_iterate; r.ms_pack += a.ms_pack; r.ms_d2h += a.ms_d2h;
+    r.ms_split += a.ms_split; r.split_evals += a.split_evals; r.split_rounds += a.split_rounds;
+    r.launches += a.launches; r.match_positions += a.match_positions; r.iterate_positions += a.iterate_positions;
+    r.iterate_steps += a.iterate_steps; r.h2d_bytes += a.h2d_bytes; r.d2h_bytes += a.d2h_bytes;
+    uint64_t ta = 0, tr = 0;
+    for (int i = 0; i < 6; i++) { r.cyc_sum[i] += a.cyc_sum[i]; ta += a.cyc_max[i]; tr += r.cyc_max[i]; }
+    if (ta > tr) { for (int i = 0; i < 6; i++) r.cyc_max[i] = a.cyc_max[i]; r.max_block_positions = a.max_block_positions; }
+  }
+  return r;
 }
 void Engine::reset_stats() {
   std::lock_guard<std::mutex> g(p_->mu);
   memset(&p_->st_acc, 0, sizeof(p_->st_acc));
+  for (int k = 0; k < 2; k++) memset(&p_->lane[k].acc, 0, sizeof(EngineStats));
 }
 
 void Engine::set_input_host(const uint8_t* in, size_t insize) {
   std::lock_guard<std::mutex> g(p_->mu);
   Impl& m = *p_;
+  Lane& l = m.lane[0];
   CK(cudaSetDevice(m.dev));
   m.in_buf.ensure(insize + 64);
-  m.tic();
-  CK(cudaMemsetAsync((uint8_t*)m.in_buf.p + insize, 0, 64, m.stream));
-  if (insize) CK(cudaMemcpyAsync(m.in_buf.p, in, insize, cudaMemcpyHostToDevice, m.stream));
-  m.toc(m.st_acc.ms_h2d);
+  l.tic();
+  CK(cudaMemsetAsync((uint8_t*)m.in_buf.p + insize, 0, 64, l.stream));
+  if (insize) CK(cudaMemcpyAsync(m.in_buf.p, in, insize, cudaMemcpyHostToDevice, l.stream));
+  l.toc(m.st_acc.ms_h2d);
   m.st_acc.h2d_bytes += insize;
   m.d_in = m.in_buf.as<uint8_t>();
   m.insize = insize;
@@ -354,9 +399,10 @@ void Engine::set_input_device(const uint8_t* dev_in, size_t insize) {
   m.compute_same();
 }
 
-void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out) {
-  std::lock_guard<std::mutex> g(p_->mu);
+void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out, int lane_id) {
   Impl& m = *p_;
+  Lane& l = m.lane[lane_id & 1];
+  std::lock_guard<std::mutex> g(l.mu);
   CK(cudaSetDevice(m.dev));
   const size_t ns = ranges.size();
   out.off.assign(ns, 0);
@@ -370,30 +416,30 @@ void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out) {
   std::vector<JobState> js(ns);
   uint32_t counters[2] = {0, 0};
   for (int attempt = 0;; attempt++) {
-    Batch b = m.prepare(L);
-    m.tic();
-    k_greedy<<<(unsigned)ns, 32, 0, m.stream>>>(b, 0);
+    Batch b = m.prepare(L, l);
+    l.tic();
+    k_greedy<<<(unsigned)ns, 32, 0, l.stream>>>(b, 0);
     CK(cudaGetLastError());
-    m.toc(m.st_acc.ms_greedy);
-    m.st_acc.launches++;
+    l.toc(l.acc.ms_greedy);
+    l.acc.launches++;
     if (L.any_parse) {
-      m.tic();
-      k_iterate<<<(unsigned)ns, 32, 0, m.stream>>>(b, m.order.as<uint32_t>());
+      l.tic();
+      k_iterate<<<(unsigned)ns, 32, 0, l.stream>>>(b, l.order.as<uint32_t>());
       CK(cudaGetLastError());
-      m.toc(m.st_acc.ms_iterate);
-      m.st_acc.launches++;
+      l.toc(l.acc.ms_iterate);
+      l.acc.launches++;
     }
-    m.tic();
-    k_pack<<<(unsigned)ns, 256, 0, m.stream>>>(b, L.any_parse ? 0 : 1);
+    l.tic();
+    k_pack<<<(unsigned)ns, 256, 0, l.stream>>>(b, L.any_parse ? 0 : 1);
     CK(cudaGetLastError());
-    m.toc(m.st_acc.ms_pack);
-    m.st_acc.launches++;
-    m.tic();
-    CK(cudaMemcpyAsync(js.data(), m.jobs.p, ns * sizeof(JobState), cudaMemcpyDeviceToHost, m.stream));
-    CK(cudaMemcpyAsync(counters, m.counters.p, sizeof(counters), cudaMemcpyDeviceToHost, m.stream));
-    CK(cudaStreamSynchronize(m.stream));
-    if (L.any_parse && counters[0] > m.ovf_cap) {  // run-list overflow arena too small: grow, redo
-      m.ovf_cap = counters[0] + counters[0] / 4 + 1024;
+    l.toc(l.acc.ms_pack);
+    l.acc.launches++;
+    l.tic();
+    CK(cudaMemcpyAsync(js.data(), l.jobs.p, ns * sizeof(JobState), cudaMemcpyDeviceToHost, l.stream));
+    CK(cudaMemcpyAsync(counters, l.counters.p, sizeof(counters), cudaMemcpyDeviceToHost, l.stream));
+    CK(cudaStreamSynchronize(l.stream));
+    if (L.any_parse && counters[0] > l.ovf_cap) {  // run-list overflow arena too small: grow, redo
+      l.ovf_cap = counters[0] + counters[0] / 4 + 1024;
       if (attempt > 2) { fprintf(stderr, "zopfli-b200: overflow arena did not converge\n"); abort(); }
       continue;
     }
@@ -401,11 +447,11 @@ void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out) {
     out.ll.resize(total);
     out.d.resize(total);
     if (total) {
-      CK(cudaMemcpyAsync(out.ll.data(), m.out_ll.p, (size_t)total * 2, cudaMemcpyDeviceToHost, m.stream));
-      CK(cudaMemcpyAsync(out.d.data(), m.out_d.p, (size_t)total * 2, cudaMemcpyDeviceToHost, m.stream));
+      CK(cudaMemcpyAsync(out.ll.data(), l.out_ll.p, (size_t)total * 2, cudaMemcpyDeviceToHost, l.stream));
+      CK(cudaMemcpyAsync(out.d.data(), l.out_d.p, (size_t)total * 2, cudaMemcpyDeviceToHost, l.stream));
     }
-    m.toc(m.st_acc.ms_d2h);
-    m.st_acc.d2h_bytes += (uint64_t)total * 4 + ns * sizeof(JobState);
+    l.toc(l.acc.ms_d2h);
+    l.acc.d2h_bytes += (uint64_t)total * 4 + ns * sizeof(JobState);
     break;
   }
   for (size_t i = 0; i < ns; i++) {
@@ -425,10 +471,10 @@ void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out) {
     if (js[i].flags & 2) { fprintf(stderr, "zopfli-b200: corrupted length chain in block %zu\n", i); abort(); }
     if (ranges[i].mode == 1) {
       uint64_t tot = 0, cur = 0;
-      for (int k = 0; k < 6; k++) { m.st_acc.cyc_sum[k] += js[i].cyc[k]; tot += js[i].cyc[k]; cur += m.st_acc.cyc_max[k]; }
-      if (tot > cur) { for (int k = 0; k < 6; k++) m.st_acc.cyc_max[k] = js[i].cyc[k]; m.st_acc.max_block_positions = L.segs[i].npos; }
-      m.st_acc.iterate_positions += L.segs[i].npos;
-      m.st_acc.iterate_steps += (uint64_t)L.segs[i].npos * ranges[i].numiterations;
+      for (int k = 0; k < 6; k++) { l.acc.cyc_sum[k] += js[i].cyc[k]; tot += js[i].cyc[k]; cur += l.acc.cyc_max[k]; }
+      if (tot > cur) { for (int k = 0; k < 6; k++) l.acc.cyc_max[k] = js[i].cyc[k]; l.acc.max_block_positions = L.segs[i].npos; }
+      l.acc.iterate_positions += L.segs[i].npos;
+      l.acc.iterate_steps += (uint64_t)L.segs[i].npos * ranges[i].numiterations;
     }
   }
 }
@@ -436,8 +482,9 @@ void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out) {
 void Engine::match_table(uint64_t instart, uint64_t inend, std::vector<uint16_t>& len,
                          std::vector<uint16_t>& dist, std::vector<uint16_t>& sublen,
                          std::vector<uint16_t>& same, std::vector<uint16_t>& hvv, std::vector<uint16_t>& hv2v) {
-  std::lock_guard<std::mutex> g(p_->mu);
   Impl& m = *p_;
+  Lane& l = m.lane[0];
+  std::lock_guard<std::mutex> g(l.mu);
   CK(cudaSetDevice(m.dev));
   std::vector<ParseRange> r{{instart, inend, 1, 1}};
   Impl::Layout L;
@@ -446,20 +493,20 @@ void Engine::match_table(uint64_t instart, uint64_t inend, std::vector<uint16_t>
   std::vector<uint16_t> h_mlen, h_hv, h_hv2, h_same;
   const size_t n = (size_t)(inend - instart);
   for (int attempt = 0;; attempt++) {
-    m.prepare(L);
+    m.prepare(L, l);
     uint32_t used = 0;
-    CK(cudaMemcpyAsync(&used, m.counters.p, 4, cudaMemcpyDeviceToHost, m.stream));
-    CK(cudaStreamSynchronize(m.stream));
-    if (used > m.ovf_cap) { m.ovf_cap = used + used / 4 + 1024; if (attempt > 2) abort(); continue; }
+    CK(cudaMemcpyAsync(&used, l.counters.p, 4, cudaMemcpyDeviceToHost, l.stream));
+    CK(cudaStreamSynchronize(l.stream));
+    if (used > l.ovf_cap) { l.ovf_cap = used + used / 4 + 1024; if (attempt > 2) abort(); continue; }
     h_ld.resize(n); h_runs.resize(n * kRunSlots); h_mlen.resize(n); h_ovf.resize(used + 1);
     h_hv.resize(L.nkeys); h_hv2.resize(L.nkeys); h_same.resize(n);
     if (n) {
-      CK(cudaMemcpy(h_ld.data(), m.ld.p, n * 4, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(h_runs.data(), m.runs.p, n * kRunSlots * 4, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(h_mlen.data(), m.mlen.p, n * 2, cudaMemcpyDeviceToHost));
-      if (used) CK(cudaMemcpy(h_ovf.data(), m.ovf.p, (size_t)used * 4, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(h_hv.data(), m.hv.p, L.nkeys * 2, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(h_hv2.data(), m.hv2.p, L.nkeys * 2, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h_ld.data(), l.ld.p, n * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h_runs.data(), l.runs.p, n * kRunSlots * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h_mlen.data(), l.mlen.p, n * 2, cudaMemcpyDeviceToHost));
+      if (used) CK(cudaMemcpy(h_ovf.data(), l.ovf.p, (size_t)used * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h_hv.data(), l.hv.p, L.nkeys * 2, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h_hv2.data(), l.hv2.p, L.nkeys * 2, cudaMemcpyDeviceToHost));
       CK(cudaMemcpy(h_same.data(), m.same_buf.as<uint16_t>() + instart, n * 2, cudaMemcpyDeviceToHost));
     }
     break;
@@ -491,17 +538,18 @@ void Engine::match_table(uint64_t instart, uint64_t inend, std::vector<uint16_t>
 }
 
 void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vector<uint64_t>& off,
-                         const std::vector<uint32_t>& size) {
-  std::lock_guard<std::mutex> g(p_->mu);
+                         const std::vector<uint32_t>& size, int lane_id) {
   Impl& m = *p_;
+  Lane& l = m.lane[lane_id & 1];
+  std::lock_guard<std::mutex> g(l.mu);
   CK(cudaSetDevice(m.dev));
   const size_t ns = off.size();
   uint64_t total = 0, nsnap_total = 0, pos_total = 0;
   for (size_t i = 0; i < ns; i++) total = std::max<uint64_t>(total, off[i] + size[i]);
-  m.sp_desc.resize(ns);
+  l.sp_desc.resize(ns);
   std::vector<SnapWork> work;
   for (size_t i = 0; i < ns; i++) {
-    SplitStoreDesc& sd = m.sp_desc[i];
+    SplitStoreDesc& sd = l.sp_desc[i];
     sd.sym_off = off[i];
     sd.n = size[i];
     sd.nsnap = size[i] / kSnap + 1;
@@ -511,85 +559,86 @@ void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vecto
     pos_total += (uint64_t)size[i] + 1;
     for (uint32_t c = 0; c * kSnap < size[i]; c++) work.push_back({(uint32_t)i, c});
   }
-  m.sp_ll.ensure(total * 2 + 64);
-  m.sp_d.ensure(total * 2 + 64);
-  m.sp_llsym.ensure(total * 2 + 64);
-  m.sp_dsym.ensure(total + 64);
-
-  m.sp_snaps.ensure(nsnap_total * 320 * 4 + 64);
-  m.sp_pos.ensure(pos_total * 4 + 64);
-  m.tic();
+  l.sp_ll.ensure(total * 2 + 64);
+  l.sp_d.ensure(total * 2 + 64);
+  l.sp_llsym.ensure(total * 2 + 64);
+  l.sp_dsym.ensure(total + 64);
+  l.sp_snaps.ensure(nsnap_total * 320 * 4 + 64);
+  l.sp_pos.ensure(pos_total * 4 + 64);
+  l.tic();
   if (total) {
-    CK(cudaMemcpyAsync(m.sp_ll.p, ll, total * 2, cudaMemcpyHostToDevice, m.stream));
-    CK(cudaMemcpyAsync(m.sp_d.p, d, total * 2, cudaMemcpyHostToDevice, m.stream));
+    CK(cudaMemcpyAsync(l.sp_ll.p, ll, total * 2, cudaMemcpyHostToDevice, l.stream));
+    CK(cudaMemcpyAsync(l.sp_d.p, d, total * 2, cudaMemcpyHostToDevice, l.stream));
   }
-  m.upload(m.sp_stores, m.sp_desc);
-  m.upload(m.sp_work, work);
-  SplitBatch& b = m.sp_batch;
-  b.ll = m.sp_ll.as<uint16_t>();
-  b.d = m.sp_d.as<uint16_t>();
-  b.llsym = m.sp_llsym.as<uint16_t>();
-  b.dsym = m.sp_dsym.as<uint8_t>();
-  b.pos = m.sp_pos.as<uint32_t>();
-  b.snaps = m.sp_snaps.as<uint32_t>();
-  b.stores = m.sp_stores.as<SplitStoreDesc>();
+  l.upload(l.sp_stores, l.sp_desc);
+  l.upload(l.sp_work, work);
+  SplitBatch& b = l.sp_batch;
+  b.ll = l.sp_ll.as<uint16_t>();
+  b.d = l.sp_d.as<uint16_t>();
+  b.llsym = l.sp_llsym.as<uint16_t>();
+  b.dsym = l.sp_dsym.as<uint8_t>();
+  b.pos = l.sp_pos.as<uint32_t>();
+  b.snaps = l.sp_snaps.as<uint32_t>();
+  b.stores = l.sp_stores.as<SplitStoreDesc>();
   b.scratch = nullptr;
   for (size_t i = 0; i < ns; i++)
-    if (size[i]) k_split_prep_sym<<<(size[i] + 255) / 256, 256, 0, m.stream>>>(b, (uint32_t)i);
-  if (ns) k_split_prep_pos<<<(unsigned)ns, 1024, 0, m.stream>>>(b);
+    if (size[i]) k_split_prep_sym<<<(size[i] + 255) / 256, 256, 0, l.stream>>>(b, (uint32_t)i);
+  if (ns) k_split_prep_pos<<<(unsigned)ns, 1024, 0, l.stream>>>(b);
   if (!work.empty())
-    k_split_prep_snap<<<(unsigned)((work.size() + 7) / 8), 256, 0, m.stream>>>(b, m.sp_work.as<SnapWork>(), (uint32_t)work.size());
-  if (ns) k_split_prep_prefix<<<(unsigned)ns, 320, 0, m.stream>>>(b);
+    k_split_prep_snap<<<(unsigned)((work.size() + 7) / 8), 256, 0, l.stream>>>(b, l.sp_work.as<SnapWork>(), (uint32_t)work.size());
+  if (ns) k_split_prep_prefix<<<(unsigned)ns, 320, 0, l.stream>>>(b);
   CK(cudaGetLastError());
-  m.toc(m.st_acc.ms_split);
-  m.st_acc.launches += ns + 3;
-  m.st_acc.h2d_bytes += total * 4;
+  l.toc(l.acc.ms_split);
+  l.acc.launches += ns + 3;
+  l.acc.h2d_bytes += total * 4;
 }
 
-void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs) {
-  std::lock_guard<std::mutex> g(p_->mu);
+void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lane_id) {
   Impl& m = *p_;
+  Lane& l = m.lane[lane_id & 1];
+  std::lock_guard<std::mutex> g(l.mu);
   CK(cudaSetDevice(m.dev));
   if (n == 0) return;
   const size_t kChunk = 32768;  // scratch is per evaluation: bound it
-  m.sp_scratch.ensure(std::min(n, kChunk) * kIterScratch);
-  m.sp_evals.ensure(n * sizeof(SplitEval) + 64);
-  m.sp_out.ensure(n * 8 + 64);
+  l.sp_scratch.ensure(std::min(n, kChunk) * kIterScratch);
+  l.sp_evals.ensure(n * sizeof(SplitEval) + 64);
+  l.sp_out.ensure(n * 8 + 64);
   std::vector<SplitEval> ev(n);
   for (size_t i = 0; i < n; i++) ev[i] = {reqs[i].store, reqs[i].lstart, reqs[i].lend, 0};
-  m.tic();
-  CK(cudaMemcpyAsync(m.sp_evals.p, ev.data(), n * sizeof(SplitEval), cudaMemcpyHostToDevice, m.stream));
-  SplitBatch b = m.sp_batch;
-  b.scratch = m.sp_scratch.as<uint8_t>();
+  l.tic();
+  CK(cudaMemcpyAsync(l.sp_evals.p, ev.data(), n * sizeof(SplitEval), cudaMemcpyHostToDevice, l.stream));
+  SplitBatch b = l.sp_batch;
+  b.scratch = l.sp_scratch.as<uint8_t>();
   for (size_t o = 0; o < n; o += kChunk) {
     const size_t c = std::min(kChunk, n - o);
-    k_split_eval<<<(unsigned)((c + kEvalWarps - 1) / kEvalWarps), kEvalWarps * 32, 0, m.stream>>>(
-        b, m.sp_evals.as<SplitEval>() + o, (uint32_t)c, m.sp_out.as<uint64_t>() + o);
-    m.st_acc.launches++;
+    k_split_eval<<<(unsigned)((c + kEvalWarps - 1) / kEvalWarps), kEvalWarps * 32, 0, l.stream>>>(
+        b, l.sp_evals.as<SplitEval>() + o, (uint32_t)c, l.sp_out.as<uint64_t>() + o);
+    l.acc.launches++;
   }
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(costs, m.sp_out.p, n * 8, cudaMemcpyDeviceToHost, m.stream));
-  m.toc(m.st_acc.ms_split);
-  m.st_acc.split_evals += n;
-  m.st_acc.split_rounds++;
+  CK(cudaMemcpyAsync(costs, l.sp_out.p, n * 8, cudaMemcpyDeviceToHost, l.stream));
+  l.toc(l.acc.ms_split);
+  l.acc.split_evals += n;
+  l.acc.split_rounds++;
 }
 
 uint64_t Engine::device_block_bits(const uint32_t* hist320) {
-  std::lock_guard<std::mutex> g(p_->mu);
   Impl& m = *p_;
+  Lane& l = m.lane[0];
+  std::lock_guard<std::mutex> g(l.mu);
   CK(cudaSetDevice(m.dev));
-  m.scratch.ensure(kIterScratch);
-  m.misc.ensure(320 * 4 + 64);
+  l.scratch.ensure(kIterScratch);
+  l.misc.ensure(320 * 4 + 64);
   Batch b;
   memset(&b, 0, sizeof(b));
-  b.scratch = m.scratch.as<uint8_t>();
-  CK(cudaMemcpyAsync(m.misc.p, hist320, 320 * 4, cudaMemcpyHostToDevice, m.stream));
-  uint64_t* dout = (uint64_t*)((uint8_t*)m.misc.p + 320 * 4 + 16);
-  k_test_block_bits<<<1, 32, 0, m.stream>>>(b, m.misc.as<uint32_t>(), dout);
+  b.scratch = l.scratch.as<uint8_t>();
+  CK(cudaMemcpyAsync(l.misc.p, hist320, 320 * 4, cudaMemcpyHostToDevice, l.stream));
+  uint64_t* dout = (uint64_t*)((uint8_t*)l.misc.p + 320 * 4 + 16);
+  k_test_block_bits<<<1, 32, 0, l.stream>>>(b, l.misc.as<uint32_t>(), dout);
   CK(cudaGetLastError());
   uint64_t r = 0;
-  CK(cudaMemcpyAsync(&r, dout, 8, cudaMemcpyDeviceToHost, m.stream));
-  CK(cudaStreamSynchronize(m.stream));
+  CK(cudaMemcpyAsync(&r, dout, 8, cudaMemcpyDeviceToHost, l.stream));
+  CK(cudaStreamSynchronize(l.stream));
   return r;
 }
 

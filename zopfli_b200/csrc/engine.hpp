@@ -42,7 +42,9 @@ class Engine {
   void set_input_host(const uint8_t* in, size_t insize);
   void set_input_device(const uint8_t* dev_in, size_t insize);
 
-  void parse(const std::vector<ParseRange>& ranges, ParseResult& out);
+  // `lane` (0 or 1) selects one of two independent stream + arena sets; calls on different lanes
+  // may run concurrently from different host threads (a batch of giant blocks beside the rest).
+  void parse(const std::vector<ParseRange>& ranges, ParseResult& out, int lane = 0);
 
   // test seam: raw match table of one range (length, dist, expanded sublen[259] per position)
   void match_table(uint64_t instart, uint64_t inend, std::vector<uint16_t>& len,
@@ -55,9 +57,9 @@ class Engine {
   // split_begin uploads n stores given as flat symbol arrays with per-store offset/size,
   // split_eval prices a batch of (store, lstart, lend) ranges on the device.
   void split_begin(const uint16_t* ll, const uint16_t* d, const std::vector<uint64_t>& off,
-                   const std::vector<uint32_t>& size);
+                   const std::vector<uint32_t>& size, int lane = 1);
   struct SplitReq { uint32_t store, lstart, lend; };
-  void split_eval(const SplitReq* reqs, size_t n, uint64_t* costs);
+  void split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lane = 1);
 
   void set_stream(void* cuda_stream);  // optional: run on the caller's stream
   EngineStats stats();

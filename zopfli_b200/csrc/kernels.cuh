@@ -301,20 +301,31 @@ __global__ void __launch_bounds__(32) k_scatter(Batch b) {
   const uint32_t lane = threadIdx.x;
   for (uint32_t i = lane; i < 32768; i += 32) cursor[i] = bs[i];
   __syncwarp();
-  for (uint32_t base = 0; base < sd.nkeys; base += 32) {
-    uint32_t i = base + lane;
-    bool act = i < sd.nkeys;
-    uint32_t k = act ? key[i] : 0xffffffffu;  // inactive lanes get a key no active lane has
-    uint32_t peers = __match_any_sync(0xffffffffu, k);
-    uint32_t before = __popc(peers & ((1u << lane) - 1));
-    uint32_t cur = act ? cursor[k] : 0;
-    __syncwarp();
-    if (act && before == 0) cursor[k] = cur + __popc(peers);
-    __syncwarp();
-    if (act) {
-      uint32_t d = cur + before;
-      idx[d] = i;
-      rank[i] = d;
+  // keys of 8 rounds are fetched up front so that the global-load latency is paid once per 256
+  // positions instead of once per round
+  for (uint32_t base0 = 0; base0 < sd.nkeys; base0 += 256) {
+    uint32_t kreg[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const uint32_t i = base0 + u * 32 + lane;
+      kreg[u] = i < sd.nkeys ? key[i] : 0xffffffffu;  // inactive lanes get a key no active lane has
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const uint32_t i = base0 + u * 32 + lane;
+      const bool act = i < sd.nkeys;
+      const uint32_t k = kreg[u];
+      const uint32_t peers = __match_any_sync(0xffffffffu, k);
+      const uint32_t before = __popc(peers & ((1u << lane) - 1));
+      const uint32_t cur = act ? cursor[k] : 0;
+      __syncwarp();
+      if (act && before == 0) cursor[k] = cur + __popc(peers);
+      __syncwarp();
+      if (act) {
+        const uint32_t d = cur + before;
+        idx[d] = i;
+        rank[i] = d;
+      }
     }
   }
 }
