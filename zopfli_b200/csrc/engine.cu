@@ -54,7 +54,7 @@ __global__ void k_test_block_bits(Batch b, const uint32_t* hist, uint64_t* out) 
   __syncwarp();
   if (lane == 0) s.hist[256] = 1;
   __syncwarp();
-  uint64_t r = warp_dynamic_bits(s.hist, s.u.cs, b.scratch, lane);
+  uint64_t r = warp_dynamic_bits(s.hist, s.u.cs, lane);
   if (lane == 0) *out = r;
 }
 
@@ -72,9 +72,9 @@ struct Lane {  // an independent stream + arena set; two lanes let a batch of gi
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[2];
   DevBuf segs, keywork, poswork, order, hv, hv2, idx1, idx2, rank1, rank2, bkt1, bkt2, ld, mlen, runs, dsx,
-      ovf, la, path, st[4], jobs, scratch, out_ll, out_d, counters, misc;
+      ovf, la, path, st[4], jobs, out_ll, out_d, counters, misc;
   // split service
-  DevBuf sp_ll, sp_d, sp_llsym, sp_dsym, sp_pos, sp_snaps, sp_stores, sp_work, sp_evals, sp_out, sp_scratch;
+  DevBuf sp_ll, sp_d, sp_llsym, sp_dsym, sp_pos, sp_snaps, sp_stores, sp_work, sp_evals, sp_out;
   std::vector<SplitStoreDesc> sp_desc;
   SplitBatch sp_batch;
   uint32_t ovf_cap = 1u << 22;
@@ -86,9 +86,9 @@ struct Lane {  // an independent stream + arena set; two lanes let a batch of gi
     CK(cudaEventCreate(&ev[0]));
     CK(cudaEventCreate(&ev[1]));
     DevBuf* all[] = {&segs, &keywork, &poswork, &order, &hv, &hv2, &idx1, &idx2, &rank1, &rank2, &bkt1, &bkt2, &ld,
-                     &mlen, &runs, &dsx, &ovf, &la, &path, &st[0], &st[1], &st[2], &st[3], &jobs, &scratch, &out_ll,
+                     &mlen, &runs, &dsx, &ovf, &la, &path, &st[0], &st[1], &st[2], &st[3], &jobs, &out_ll,
                      &out_d, &counters, &misc, &sp_ll, &sp_d, &sp_llsym, &sp_dsym, &sp_pos, &sp_snaps, &sp_stores,
-                     &sp_work, &sp_evals, &sp_out, &sp_scratch};
+                     &sp_work, &sp_evals, &sp_out};
     for (DevBuf* d : all) d->st = stream;
   }
   void tic() { CK(cudaEventRecord(ev[0], stream)); }
@@ -247,7 +247,6 @@ struct Engine::Impl {
     l.out_ll.ensure(L.npos * 2 + 64);
     l.out_d.ensure(L.npos * 2 + 64);
     l.counters.ensure(256);
-    l.scratch.ensure(std::max<size_t>(ns, 1) * kIterScratch);
     if (L.any_parse) {
       l.mlen.ensure(L.npos * 2 + 64);
       l.runs.ensure(L.npos * kRunSlots * 4 + 64);
@@ -288,7 +287,6 @@ struct Engine::Impl {
     b.st_ll[2] = nullptr;
     b.st_d[2] = nullptr;
     b.jobs = l.jobs.as<JobState>();
-    b.scratch = l.scratch.as<uint8_t>();
     b.logtab = logtab.as<double>();
     b.logtab_n = kLogTabN;
     b.out_ll = l.out_ll.as<uint16_t>();
@@ -341,9 +339,9 @@ void Engine::set_stream(void* s) {
     l.stream = (cudaStream_t)s;
     DevBuf* all[] = {&l.segs, &l.keywork, &l.poswork, &l.order, &l.hv, &l.hv2, &l.idx1, &l.idx2, &l.rank1, &l.rank2,
                      &l.bkt1, &l.bkt2, &l.ld, &l.mlen, &l.runs, &l.dsx, &l.ovf, &l.la, &l.path, &l.st[0], &l.st[1],
-                     &l.st[2], &l.st[3], &l.jobs, &l.scratch, &l.out_ll, &l.out_d, &l.counters, &l.misc, &l.sp_ll,
+                     &l.st[2], &l.st[3], &l.jobs, &l.out_ll, &l.out_d, &l.counters, &l.misc, &l.sp_ll,
                      &l.sp_d, &l.sp_llsym, &l.sp_dsym, &l.sp_pos, &l.sp_snaps, &l.sp_stores, &l.sp_work, &l.sp_evals,
-                     &l.sp_out, &l.sp_scratch, &p_->in_buf, &p_->same_buf, &p_->tile_first, &p_->next_tile, &p_->logtab};
+                     &l.sp_out, &p_->in_buf, &p_->same_buf, &p_->tile_first, &p_->next_tile, &p_->logtab};
     for (DevBuf* d : all) d->st = l.stream;
   }
 }
@@ -580,7 +578,6 @@ void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vecto
   b.pos = l.sp_pos.as<uint32_t>();
   b.snaps = l.sp_snaps.as<uint32_t>();
   b.stores = l.sp_stores.as<SplitStoreDesc>();
-  b.scratch = nullptr;
   for (size_t i = 0; i < ns; i++)
     if (size[i]) k_split_prep_sym<<<(size[i] + 255) / 256, 256, 0, l.stream>>>(b, (uint32_t)i);
   if (ns) k_split_prep_pos<<<(unsigned)ns, 1024, 0, l.stream>>>(b);
@@ -600,7 +597,6 @@ void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lan
   CK(cudaSetDevice(m.dev));
   if (n == 0) return;
   const size_t kChunk = 32768;  // scratch is per evaluation: bound it
-  l.sp_scratch.ensure(std::min(n, kChunk) * kIterScratch);
   l.sp_evals.ensure(n * sizeof(SplitEval) + 64);
   l.sp_out.ensure(n * 8 + 64);
   std::vector<SplitEval> ev(n);
@@ -608,7 +604,6 @@ void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lan
   l.tic();
   CK(cudaMemcpyAsync(l.sp_evals.p, ev.data(), n * sizeof(SplitEval), cudaMemcpyHostToDevice, l.stream));
   SplitBatch b = l.sp_batch;
-  b.scratch = l.sp_scratch.as<uint8_t>();
   for (size_t o = 0; o < n; o += kChunk) {
     const size_t c = std::min(kChunk, n - o);
     k_split_eval<<<(unsigned)((c + kEvalWarps - 1) / kEvalWarps), kEvalWarps * 32, 0, l.stream>>>(
@@ -627,11 +622,9 @@ uint64_t Engine::device_block_bits(const uint32_t* hist320) {
   Lane& l = m.lane[0];
   std::lock_guard<std::mutex> g(l.mu);
   CK(cudaSetDevice(m.dev));
-  l.scratch.ensure(kIterScratch);
   l.misc.ensure(320 * 4 + 64);
   Batch b;
   memset(&b, 0, sizeof(b));
-  b.scratch = l.scratch.as<uint8_t>();
   CK(cudaMemcpyAsync(l.misc.p, hist320, 320 * 4, cudaMemcpyHostToDevice, l.stream));
   uint64_t* dout = (uint64_t*)((uint8_t*)l.misc.p + 320 * 4 + 16);
   k_test_block_bits<<<1, 32, 0, l.stream>>>(b, l.misc.as<uint32_t>(), dout);

@@ -26,9 +26,17 @@ struct DpStage {                       // forward-DP working set
   uint8_t dsx[4][32 * 32];             // TMA-staged first-round distance symbols (128-row ring)
   double gl[64];                       // literal cost of the byte at each position (2 groups)
 };
+struct WarpPm {                        // warp-wide package-merge working set (warp_length_limited)
+  uint32_t key[kNumLL];                // active symbols sorted by (weight << 9 | symbol)
+  uint32_t pk[kNumLL];                 // package weights of the level being built
+  uint32_t row[2][2 * kNumLL];         // item weights of the previous / current level
+  uint32_t mask[15][(2 * kNumLL + 31) / 32];  // bit = item is a leaf
+};
 struct CostStage {                     // block-size working set
   uint32_t cnt2[320];                  // RLE-smoothed copies (ll: [0,288), d: [288,320))
   uint8_t len[2][320];                 // code lengths: set 0 plain, set 1 smoothed
+  uint8_t good[320];                   // OptimizeHuffmanForRle marks
+  WarpPm pm;
 };
 struct IterSmem {
   double llcost[kNumLL];   // ll_symbols
@@ -135,25 +143,162 @@ __device__ bool warp_entropy(const uint32_t* cnt, int n, double* out, const Batc
   return __all_sync(0xffffffffu, ok);
 }
 
-// exact dynamic block size from s.hist (hist[256] already 1): deflate.c:569-608.
-__device__ uint64_t warp_dynamic_bits(const uint32_t* hist, CostStage& cs, uint8_t* scratch, uint32_t lane) {
-  // four length-limited code constructions side by side: lanes 0..3 run the same instruction
-  // stream on (ll plain, d plain, ll smoothed, d smoothed)
-  if (lane < 4) {
-    const bool isd = lane & 1, smooth = lane >= 2;
-    const int n = isd ? kNumD : kNumLL;
-    const uint32_t* src = hist + (isd ? 288 : 0);
-    uint32_t* c2 = cs.cnt2 + (isd ? 288 : 0);
-    PmBig* pb = (PmBig*)(scratch + (size_t)lane * (kIterScratch / 4));
-    if (smooth) {
-      for (int i = 0; i < n; i++) c2[i] = src[i];
-      optimize_for_rle(n, c2, pb->good);
-      src = c2;
-    }
-    uint8_t* out = cs.len[smooth ? 1 : 0] + (isd ? 288 : 0);
-    length_limited<kNumLL, 15>(src, n, 15, out, pb->pm);
-    if (isd) patch_distance_codes(out);
+// ---- ZopfliLengthLimitedCodeLengths (katajainen.c:172-262) by the whole warp ----
+// Same level-by-level package-merge as length_limited() in deflate_size.hpp (and the same tie rule:
+// a package precedes a leaf of equal weight), but every level is built as a parallel MERGE BY RANK:
+// leaf i lands at i + #{packages <= w_i}, package p at p + #{leaves < sum_p}; both counts are
+// branch-free binary searches over sorted shared-memory arrays.  The serial version walks
+// 15 x 574 items through one lane; this one needs ~15 x 9 search rounds per lane.
+template <int ITEMS>
+__device__ __forceinline__ void warp_bitonic_sort(uint32_t* keys, int ns, uint32_t lane) {
+  const uint32_t full = 0xffffffffu;
+  uint32_t v[ITEMS];
+#pragma unroll
+  for (int r = 0; r < ITEMS; r++) {
+    const int e = (int)lane * ITEMS + r;
+    v[r] = e < ns ? keys[e] : 0xffffffffu;
   }
+  constexpr int N = 32 * ITEMS;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= ITEMS) {
+        const int lj = j / ITEMS;
+        const bool lower = (lane & lj) == 0;
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+          const uint32_t o = __shfl_xor_sync(full, v[r], lj);
+          const bool asc = ((((int)lane * ITEMS + r) & k) == 0);
+          v[r] = (lower == asc) ? min(v[r], o) : max(v[r], o);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < ITEMS; r++) {
+          if ((r & j) == 0) {
+            const bool asc = ((((int)lane * ITEMS + r) & k) == 0);
+            const uint32_t a = v[r], c = v[r | j];
+            const uint32_t lo = min(a, c), hi = max(a, c);
+            v[r] = asc ? lo : hi;
+            v[r | j] = asc ? hi : lo;
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < ITEMS; r++) {
+    const int e = (int)lane * ITEMS + r;
+    if (e < ns) keys[e] = v[r];
+  }
+  __syncwarp();
+}
+
+// freq: n counts in shared memory (n <= 288, counts < 2^22); out: n code lengths, maxbits 15
+__device__ void warp_length_limited(const uint32_t* freq, int n, uint8_t* out, WarpPm& pm, uint32_t lane) {
+  const uint32_t full = 0xffffffffu;
+  int ns = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + (int)lane;
+    const uint32_t f = i < n ? freq[i] : 0u;
+    if (i < n) out[i] = 0;
+    const uint32_t bal = __ballot_sync(full, f != 0);
+    if (f) pm.key[ns + __popc(bal & ((1u << lane) - 1u))] = (f << 9) | (uint32_t)i;
+    ns += __popc(bal);
+  }
+  __syncwarp();
+  if (ns == 0) return;                                                       // katajainen.c:208-211
+  if (ns <= 2) { if ((int)lane < ns) out[pm.key[lane] & 511] = 1; __syncwarp(); return; }  // :212-222
+  if (ns > 256) warp_bitonic_sort<16>(pm.key, ns, lane);                     // :224-235
+  else if (ns > 128) warp_bitonic_sort<8>(pm.key, ns, lane);
+  else if (ns > 32) warp_bitonic_sort<4>(pm.key, ns, lane);
+  else warp_bitonic_sort<1>(pm.key, ns, lane);
+  const int maxbits = ns - 1 < 15 ? ns - 1 : 15;                             // :238-240
+  const int maxitems = 2 * ns - 2;
+  for (int i = lane; i < ns; i += 32) pm.row[0][i] = pm.key[i] >> 9;
+  __syncwarp();
+  int prevlen = ns, cur = 1;
+  for (int lev = 1; lev < maxbits; lev++, cur ^= 1) {
+    const uint32_t* prev = pm.row[cur ^ 1];
+    uint32_t* row = pm.row[cur];
+    const int npk = prevlen >> 1;
+    if (lane < (2 * kNumLL + 31) / 32) pm.mask[lev][lane] = 0;
+    for (int p = lane; p < npk; p += 32) {
+      const uint2 pr = *(const uint2*)&prev[2 * p];
+      pm.pk[p] = pr.x + pr.y;
+    }
+    __syncwarp();
+    const int tmax = ((ns > npk ? ns : npk) + 31) >> 5;
+    for (int t = 0; t < tmax; t++) {
+      const int i = (int)lane + 32 * t;
+      const bool hl = i < ns, hp = i < npk;
+      const uint32_t wl = hl ? pm.key[i] >> 9 : 0u, wp = hp ? pm.pk[i] : 0u;
+      int ub = 0, lb = 0;
+#pragma unroll
+      for (int step = 256; step; step >>= 1) {
+        const int a = ub + step, c = lb + step;
+        const uint32_t va = pm.pk[(a < npk ? a : npk) - 1];
+        const uint32_t vc = pm.key[(c < ns ? c : ns) - 1] >> 9;
+        if (a <= npk && va <= wl) ub = a;   // packages that precede leaf i: sum <= w_i
+        if (c <= ns && vc < wp) lb = c;     // leaves that precede package i: w < sum_i
+      }
+      if (hl) {
+        const int pos = i + ub;
+        if (pos < maxitems) { row[pos] = wl; atomicOr(&pm.mask[lev][pos >> 5], 1u << (pos & 31)); }
+      }
+      if (hp) {
+        const int pos = i + lb;
+        if (pos < maxitems) row[pos] = wp;
+      }
+    }
+    __syncwarp();
+    prevlen = ns + npk < maxitems ? ns + npk : maxitems;
+  }
+  // selection (ExtractBitLengths katajainen.c:145-163): rank r gets one bit per level whose
+  // selected-leaf count exceeds r
+  uint32_t cnt[9];
+#pragma unroll
+  for (int t = 0; t < 9; t++) cnt[t] = 0;
+  int need = maxitems;
+  for (int lev = maxbits - 1; lev >= 0; lev--) {
+    int c;
+    if (lev == 0) {
+      c = need < ns ? need : ns;
+    } else {
+      const uint32_t word = lane < (2 * kNumLL + 31) / 32 ? pm.mask[lev][lane] : 0u;
+      int bits = need - 32 * (int)lane;
+      bits = bits < 0 ? 0 : (bits > 32 ? 32 : bits);
+      const uint32_t m = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+      c = __popc(word & m);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(full, c, d);
+    }
+#pragma unroll
+    for (int t = 0; t < 9; t++) cnt[t] += (c > (int)lane + 32 * t) ? 1u : 0u;
+    need = 2 * (need - c);
+  }
+#pragma unroll
+  for (int t = 0; t < 9; t++) {
+    const int i = (int)lane + 32 * t;
+    if (i < ns) out[pm.key[i] & 511] = (uint8_t)cnt[t];
+  }
+  __syncwarp();
+}
+
+// exact dynamic block size from s.hist (hist[256] already 1): deflate.c:569-608.
+__device__ uint64_t warp_dynamic_bits(const uint32_t* hist, CostStage& cs, uint32_t lane) {
+  // RLE-smoothed copies of both histograms (TryOptimizeHuffmanForRle deflate.c:525-567): two
+  // serial scans side by side, then four warp-wide code constructions
+  for (int i = lane; i < 320; i += 32) cs.cnt2[i] = hist[i];
+  __syncwarp();
+  if (lane < 2) optimize_for_rle(lane ? kNumD : kNumLL, cs.cnt2 + (lane ? 288 : 0), cs.good + (lane ? 288 : 0));
+  __syncwarp();
+  warp_length_limited(hist, kNumLL, cs.len[0], cs.pm, lane);
+  warp_length_limited(hist + 288, kNumD, cs.len[0] + 288, cs.pm, lane);
+  warp_length_limited(cs.cnt2, kNumLL, cs.len[1], cs.pm, lane);
+  warp_length_limited(cs.cnt2 + 288, kNumD, cs.len[1] + 288, cs.pm, lane);
+  if (lane < 2) patch_distance_codes(cs.len[lane] + 288);
   __syncwarp();
   uint32_t tsz = 0xffffffffu;
   if (lane < 16) {
@@ -212,7 +357,6 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
   const uint16_t* mlen = b.mlen + sd.pos_off;
   const uint32_t* runs_g = b.runs + sd.pos_off * kRunSlots;
   const uint8_t* dsx_g = b.dsx + sd.pos_off * 32;
-  uint8_t* scratch = b.scratch + (size_t)seg * kIterScratch;
   const bool fixed = sd.mode == 2;
   int curbuf = 0, bestbuf = 1;
   uint32_t flags = 0;
@@ -654,7 +798,7 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
     __syncwarp();
 
     // ------------------------------------------------------------------ block size, best, statistics
-    const uint64_t cost = warp_dynamic_bits(s.hist, s.u.cs, scratch, lane);  // squeeze.c:492
+    const uint64_t cost = warp_dynamic_bits(s.hist, s.u.cs, lane);  // squeeze.c:492
     ZB_TICK(4);
     if (cost < bestcost) {  // squeeze.c:496-501
       int t = curbuf; curbuf = bestbuf; bestbuf = t;

@@ -96,7 +96,6 @@ struct Batch {
   uint16_t* st_ll[3];
   uint16_t* st_d[3];
   JobState* jobs;
-  uint8_t* scratch;          // per segment kIterScratch bytes
   const double* logtab;      // L[n] = log(n) * 1.4426950408889 (host libm), n in [0, logtab_n)
   uint32_t logtab_n;
   // packed results
@@ -105,8 +104,6 @@ struct Batch {
   uint32_t* out_used;
 };
 
-struct PmBig { PmScratch<kNumLL, 15> pm; uint8_t good[kNumLL]; };
-constexpr size_t kIterScratch = 4 * ((sizeof(PmBig) + 255) / 256 * 256);
 
 // ---------------------------------------------------------------------------------------------
 // helpers

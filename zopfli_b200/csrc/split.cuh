@@ -32,7 +32,6 @@ struct SplitBatch {
   uint32_t* pos;         // byte offset of each symbol relative to its store start; n+1 entries at pos_off
   uint32_t* snaps;       // prefix histograms at multiples of kSnap
   const SplitStoreDesc* stores;
-  uint8_t* scratch;      // per eval-warp kIterScratch bytes
 };
 
 __global__ void k_split_prep_sym(SplitBatch b, uint32_t store) {
@@ -189,8 +188,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) k_split_eval(SplitBatch b, co
   }
   if (lane == 0) s.hist[256] = 1;  // deflate.c:575
   __syncwarp();
-  uint8_t* scratch = b.scratch + (size_t)ei * kIterScratch;
-  const uint64_t dyn = warp_dynamic_bits(s.hist, s.cs, scratch, lane);
+  const uint64_t dyn = warp_dynamic_bits(s.hist, s.cs, lane);
   if (lane == 0) out[ei] = (unc < fixed && unc < dyn) ? unc : (fixed < dyn ? fixed : dyn);
 }
 
