@@ -64,9 +64,10 @@ uint64_t Engine::device_block_bits(const uint32_t*) { return 0; }
 
 // split service of the mock: the product's own HOST estimators (lz77_store.hpp), so the batched
 // scheduler (batched_split.hpp) is exercised on CPU exactly as the driver uses it
-static std::vector<zb::Lz77Store> g_split_stores;
+static std::vector<zb::Lz77Store> g_split_stores_lane[Engine::kLanes];  // one set per lane, as in the engine
 void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vector<uint64_t>& off,
-                         const std::vector<uint32_t>& size, int) {
+                         const std::vector<uint32_t>& size, int lane) {
+  std::vector<zb::Lz77Store>& g_split_stores = g_split_stores_lane[(unsigned)lane % kLanes];
   g_split_stores.clear();
   g_split_stores.resize(off.size());
   for (size_t i = 0; i < off.size(); i++) {
@@ -74,7 +75,8 @@ void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vecto
     g_split_stores[i].finalize();
   }
 }
-void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int) {
+void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lane) {
+  std::vector<zb::Lz77Store>& g_split_stores = g_split_stores_lane[(unsigned)lane % kLanes];
   static thread_local DynScratch s;
   for (size_t i = 0; i < n; i++) costs[i] = auto_type_bits(g_split_stores[reqs[i].store], reqs[i].lstart, reqs[i].lend, s);
 }

@@ -173,3 +173,38 @@ def test_two_lane_finalisation_order(ref, mock, monkeypatch):
     for giant in (20000, 60000, 150000):   # different clean/dirty partitions of the master blocks
         monkeypatch.setenv("ZOPFLI_B200_GIANT", str(giant))
         assert mock.compress(data, 2, numiterations=1) == want, giant
+
+
+def test_chunk_pipelines(ref, mock, monkeypatch):
+    """Master blocks run as independent chunk pipelines on separate engine lanes and host threads
+    (driver.cpp run_chunk); the output is the master blocks' pieces in order, whatever the chunking."""
+    data = TXT + corpus.synth_binary(900000, 3)   # 4 master blocks
+    want = ref.compress(data, 2, numiterations=1)
+    for chunks in (1, 2, 3, 4):
+        monkeypatch.setenv("ZOPFLI_B200_FORCE_CHUNKS", str(chunks))
+        monkeypatch.setenv("ZOPFLI_B200_GIANT", "60000")
+        assert mock.compress(data, 2, numiterations=1) == want, chunks
+
+
+def test_splice_many_small_parts_all_bit_phases(ref, mock):
+    """Chains of tiny ZopfliDeflatePart calls (btype 0/1/2, sizes 0..70) into one buffer: every bit
+    phase, pieces shorter than a byte, stored blocks right after partial bytes (driver.cpp splice)."""
+    import ctypes as C
+    import zlib
+    rng = np.random.default_rng(11)
+    base = (TXT[:3000] + corpus.random_bytes(800) + b"a" * 300 + TXT[5000:7000])
+    cuts = [0]
+    while cuts[-1] < len(base):
+        cuts.append(min(len(base), cuts[-1] + int(rng.integers(0, 70))))
+    types = rng.integers(0, 3, len(cuts) - 1)
+    outs = []
+    for lib in (ref.lib, mock.lib):
+        arr = np.frombuffer(base + b"\0" * 16, np.uint8)
+        o = zb.ZopfliOptions(0, 0, 1, 1, 0, 15)
+        out, n, bp = C.c_void_p(None), C.c_size_t(0), C.c_ubyte(0)
+        for i in range(len(cuts) - 1):
+            lib.ZopfliDeflatePart(C.byref(o), int(types[i]), int(i == len(cuts) - 2), arr.ctypes.data, cuts[i], cuts[i + 1],
+                                  C.byref(bp), C.byref(out), C.byref(n))
+        outs.append((C.string_at(out, n.value), bp.value))
+    assert outs[0] == outs[1]
+    assert zlib.decompress(outs[1][0], -15) == base

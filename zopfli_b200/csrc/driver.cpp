@@ -17,6 +17,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <mutex>
 #include <thread>
 
 #include "batched_split.hpp"
@@ -34,6 +35,21 @@ namespace {
 double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+std::mutex g_time_mu;
+void add_time(double& acc, double ms) {
+  std::lock_guard<std::mutex> g(g_time_mu);
+  acc += ms;
+}
+
+bool debug_on() {
+  static int v = [] { const char* e = getenv("ZOPFLI_B200_DEBUG"); return e && atoi(e) ? 1 : 0; }();
+  return v != 0;
+}
+double g_debug_t0 = 0;
+void debug_mark(int chunk, const char* what) {
+  if (debug_on()) fprintf(stderr, "[zb] %8.1f ms  chunk %d  %s\n", now_ms() - g_debug_t0, chunk, what);
 }
 
 int host_threads() {
@@ -132,7 +148,6 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
     for (size_t m = 0; m < nm; m++) stored_pieces(M[m].ms, M[m].me, final_last && m + 1 == nm, pieces);
     return;
   }
-  double t0 = now_ms();
   if (btype == 1) {  // deflate.c:829-841: one fixed-tree optimal parse per unit
     std::vector<ParseRange> pr;
     for (auto& mb : M) pr.push_back({mb.ms - in_base, mb.me - in_base, 2, 0});
@@ -149,38 +164,47 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
     return;
   }
 
+  // The master blocks are processed as a few independent chunk pipelines (stages A-F each), one
+  // host thread and one pair of engine lanes per chunk: while one chunk's split search waits on
+  // round trips or its longest DP chain is still running, the others keep the GPU busy.
+  auto run_chunk = [&](const std::vector<size_t>& cm, int lane_g, int lane_r) {
+  const size_t nc = cm.size();
+  const int cid = lane_g / 2;
+  double t0 = now_ms();
+  debug_mark(cid, "start");
   // ---- stage A: greedy parses (only needed when splitting) ----
   const size_t maxblocks = (size_t)opt->blocksplittingmax;
   if (opt->blocksplitting) {
     std::vector<ParseRange> pr;
-    for (auto& mb : M) pr.push_back({mb.ms - in_base, mb.me - in_base, 0, 0});
+    for (size_t m : cm) pr.push_back({M[m].ms - in_base, M[m].me - in_base, 0, 0});
     ParseResult res;
-    eng.parse(pr, res);
+    eng.parse(pr, res, lane_r);
     double t1 = now_ms();
-    g_host_times.other += t1 - t0;
+    debug_mark(cid, "A greedy done");
+    add_time(g_host_times.other, t1 - t0);
     // ---- stage B: split search (costs on the device, decisions on the host) ----
     std::vector<std::vector<size_t>> lps;
     if (!host_split_forced()) {
-      std::vector<uint64_t> off(nm);
-      for (size_t m = 0; m < nm; m++) off[m] = res.off[m];
-      lps = device_block_split(eng, res.ll.data(), res.d.data(), off, res.size, maxblocks);
+      std::vector<uint64_t> off(nc);
+      for (size_t q = 0; q < nc; q++) off[q] = res.off[q];
+      lps = device_block_split(eng, res.ll.data(), res.d.data(), off, res.size, maxblocks, lane_r);
     }
-    parallel_for(nm, [&](size_t m) {
-      Master& mb = M[m];
+    parallel_for(nc, [&](size_t q) {
+      Master& mb = M[cm[q]];
       std::vector<size_t> lp;
       if (host_split_forced()) {
-        mb.greedy.append(res.ll.data() + res.off[m], res.d.data() + res.off[m], res.size[m], mb.ms);
+        mb.greedy.append(res.ll.data() + res.off[q], res.d.data() + res.off[q], res.size[q], mb.ms);
         mb.greedy.finalize();
         lp = block_split_lz77(make_cost(mb.greedy), mb.greedy.size(), maxblocks);
       } else {
-        lp = lps[m];
+        lp = lps[q];
       }
       // LZ77 indices -> byte positions (blocksplitter.c:303-313)
-      const uint16_t* ll = res.ll.data() + res.off[m];
-      const uint16_t* dd = res.d.data() + res.off[m];
+      const uint16_t* ll = res.ll.data() + res.off[q];
+      const uint16_t* dd = res.d.data() + res.off[q];
       mb.cuts.push_back(mb.ms);
       size_t pos = mb.ms, k = 0;
-      for (size_t i = 0; i < res.size[m] && k < lp.size(); i++) {
+      for (size_t i = 0; i < res.size[q] && k < lp.size(); i++) {
         if (lp[k] == i) { mb.cuts.push_back(pos); k++; }
         pos += dd[i] == 0 ? 1 : ll[i];
       }
@@ -193,17 +217,18 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
       mb.greedy.clear();
     });
     double t2 = now_ms();
-    g_host_times.split += t2 - t1;
+    debug_mark(cid, "B split done");
+    add_time(g_host_times.split, t2 - t1);
     t0 = t2;
   } else {
-    for (auto& mb : M) { mb.cuts.push_back(mb.ms); mb.cuts.push_back(mb.me); }
+    for (size_t m : cm) { M[m].cuts.push_back(M[m].ms); M[m].cuts.push_back(M[m].me); }
   }
 
   // ---- stage C: optimal parse of every block ----
   {
     std::vector<ParseRange> pr;
     std::vector<std::pair<size_t, size_t>> owner;
-    for (size_t m = 0; m < nm; m++)
+    for (size_t m : cm)
       for (size_t i = 0; i + 1 < M[m].cuts.size(); i++) {
         pr.push_back({M[m].cuts[i] - in_base, M[m].cuts[i + 1] - in_base, 1, opt->numiterations});
         owner.push_back({m, i});
@@ -221,7 +246,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
       idx[lane].push_back(k);
     }
     ParseResult res[2];
-    for (size_t m = 0; m < nm; m++) M[m].blockstores.resize(M[m].cuts.size() - 1);
+    for (size_t m : cm) M[m].blockstores.resize(M[m].cuts.size() - 1);
     auto adopt = [&](int lane) {  // parse results of one lane -> per-block stores
       const ParseResult& r = res[lane];
       parallel_for(idx[lane].size(), [&](size_t q) {
@@ -310,7 +335,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
         }
       });
       double td1 = now_ms();
-      g_host_times.split += td1 - td0;
+      add_time(g_host_times.split, td1 - td0);
       // stage E: fixed-tree re-parses
       {
         std::vector<ParseRange> prf;
@@ -332,7 +357,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
         }
       }
       double td2 = now_ms();
-      g_host_times.other += td2 - td1;
+      add_time(g_host_times.other, td2 - td1);
       // stage F: emission, one task per final block
       std::vector<std::pair<size_t, size_t>> tasks;
       for (size_t q = 0; q < nq; q++) {
@@ -372,33 +397,53 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
           emit_compressed_block(2, final, mb.lz77, fb.lstart, fb.lend, p.bits);
         }
       });
-      g_host_times.emit += now_ms() - td2;
+      add_time(g_host_times.emit, now_ms() - td2);
     };
 
-    std::vector<size_t> all_ms(nm);
-    for (size_t m = 0; m < nm; m++) all_ms[m] = m;
     if (prs[0].empty() || prs[1].empty()) {
       const int only = prs[0].empty() ? 1 : 0;
-      eng.parse(prs[only], res[only], 0);
+      eng.parse(prs[only], res[only], lane_g);
       adopt(only);
-      g_host_times.other += now_ms() - t0;
-      finish(all_ms, 1);
+      add_time(g_host_times.other, now_ms() - t0);
+      finish(cm, lane_r);
     } else {
       std::vector<char> has_giant(nm, 0);
       for (size_t k : idx[0]) has_giant[owner[k].first] = 1;
       std::vector<size_t> clean, dirty;
-      for (size_t m = 0; m < nm; m++) (has_giant[m] ? dirty : clean).push_back(m);
-      std::thread tg([&] { eng.parse(prs[0], res[0], 0); });
-      eng.parse(prs[1], res[1], 1);
+      for (size_t m : cm) (has_giant[m] ? dirty : clean).push_back(m);
+      std::thread tg([&] { eng.parse(prs[0], res[0], lane_g); });
+      eng.parse(prs[1], res[1], lane_r);
+      debug_mark(cid, "C rest parsed");
       adopt(1);
-      g_host_times.other += now_ms() - t0;
-      finish(clean, 1);   // overlaps the giants' DP chains still running on lane 0
+      add_time(g_host_times.other, now_ms() - t0);
+      finish(clean, lane_r);   // overlaps the giants' DP chains still running on lane_g
+      debug_mark(cid, "D-F clean done");
       double tw = now_ms();
       tg.join();
+      debug_mark(cid, "C giants parsed");
       adopt(0);
-      g_host_times.other += now_ms() - tw;
-      finish(dirty, 1);
+      add_time(g_host_times.other, now_ms() - tw);
+      finish(dirty, lane_r);
+      debug_mark(cid, "D-F dirty done");
     }
+  }
+  };  // run_chunk
+
+  {
+    g_debug_t0 = now_ms();
+    size_t nchunks = 4;
+    if (const char* e = getenv("ZOPFLI_B200_CHUNKS")) nchunks = (size_t)atoi(e);
+    nchunks = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(nchunks, Engine::kLanes / 2), nm / 4));
+    if (nm < 8) nchunks = 1;
+    if (const char* e = getenv("ZOPFLI_B200_FORCE_CHUNKS")) nchunks = std::min<size_t>((size_t)atoi(e), std::min<size_t>(nm, Engine::kLanes / 2));  // tests
+    if (nchunks < 1) nchunks = 1;
+    std::vector<std::vector<size_t>> chunks(nchunks);
+    for (size_t m = 0; m < nm; m++) chunks[m * nchunks / nm].push_back(m);
+    std::vector<std::thread> th;
+    for (size_t c = 1; c < nchunks; c++)
+      th.emplace_back([&, c] { run_chunk(chunks[c], (int)(2 * c), (int)(2 * c + 1)); });
+    run_chunk(chunks[0], 0, 1);
+    for (auto& t : th) t.join();
   }
   for (size_t m = 0; m < nm; m++)
     for (auto& p : M[m].pieces) pieces.push_back(std::move(p));
@@ -430,67 +475,128 @@ void append_bytes(const unsigned char* src, size_t n, unsigned char** out, size_
   *outsize = ns;
 }
 
+// Every piece's bit offset follows from a prefix sum over the piece sizes, so the pieces are copied
+// (shifted by their bit phase) in parallel straight into the output buffer; only the bytes shared
+// between neighbouring pieces are merged serially.
 void splice_pieces(const std::vector<Piece>& pieces, const unsigned char* in, unsigned char* bp,
                    unsigned char** out, size_t* outsize) {
-  // local bit accumulator seeded with the partially filled last byte
-  std::vector<unsigned char> buf;
-  uint64_t acc = 0;
-  int nacc = 0;
-  bool patch_last = false;
-  if (*bp != 0 && *outsize > 0) {
-    acc = (*out)[*outsize - 1];
-    nacc = *bp;
-    patch_last = true;
-  }
-  size_t total = 16;
-  for (auto& p : pieces) total += p.stored ? (p.inend - p.instart) + 5 * ((p.inend - p.instart) / 65535 + 2) : p.bits.bytes.size() + 1;
-  buf.reserve(total);
-  auto put = [&](uint32_t v, int n) {
-    acc |= (uint64_t)v << nacc;
-    nacc += n;
-    while (nacc >= 8) { buf.push_back((unsigned char)acc); acc >>= 8; nacc -= 8; }
-  };
-  for (auto& p : pieces) {
+  const size_t np = pieces.size();
+  uint64_t bit0 = (uint64_t)*outsize * 8;
+  if (*bp != 0 && *outsize > 0) bit0 = (uint64_t)(*outsize - 1) * 8 + *bp;
+  std::vector<uint64_t> start(np + 1);
+  uint64_t pos = bit0;
+  for (size_t i = 0; i < np; i++) {
+    const Piece& p = pieces[i];
+    start[i] = pos;
     if (!p.stored) {
-      uint64_t nb = p.bits.nbits;
-      const std::vector<uint8_t>& by = p.bits.bytes;
-      size_t full = (size_t)(nb / 8);
-      if (nacc == 0) {
-        buf.insert(buf.end(), by.begin(), by.begin() + full);
-      } else {
-        for (size_t i = 0; i < full; i++) put(by[i], 8);
-      }
-      int rem = (int)(nb % 8);
-      if (rem) put(by[full] & ((1u << rem) - 1), rem);
-    } else {  // AddNonCompressedBlock deflate.c:625-663
-      size_t pos = p.instart;
+      pos += p.bits.nbits;
+    } else {  // AddNonCompressedBlock deflate.c:625-663: 3 header bits, byte align, LEN/NLEN, bytes
+      size_t q = p.instart;
       for (;;) {
         size_t bs = 65535;
-        if (pos + bs > p.inend) bs = p.inend - pos;
-        bool cur_final = pos + bs >= p.inend;
-        put((p.final && cur_final) ? 1 : 0, 1);
-        put(0, 2);
-        if (nacc > 0) { buf.push_back((unsigned char)acc); acc = 0; nacc = 0; }  // byte align
-        unsigned nlen = (~(unsigned)bs) & 0xffff;
-        buf.push_back((unsigned char)(bs % 256));
-        buf.push_back((unsigned char)((bs / 256) % 256));
-        buf.push_back((unsigned char)(nlen % 256));
-        buf.push_back((unsigned char)((nlen / 256) % 256));
-        buf.insert(buf.end(), in + pos, in + pos + bs);
-        if (cur_final) break;
-        pos += bs;
+        if (q + bs > p.inend) bs = p.inend - q;
+        pos += 3;
+        pos = (pos + 7) & ~(uint64_t)7;
+        pos += 32 + (uint64_t)bs * 8;
+        if (q + bs >= p.inend) break;
+        q += bs;
       }
     }
   }
-  unsigned char newbp = (unsigned char)nacc;
-  if (nacc > 0) buf.push_back((unsigned char)acc);
-  size_t skip = 0;
-  if (patch_last && !buf.empty()) {
-    (*out)[*outsize - 1] = buf[0];
-    skip = 1;
+  start[np] = pos;
+  const size_t oldsize = *outsize, newsize = (size_t)((pos + 7) / 8);
+  if (newsize > oldsize) {  // one append of everything (util.h:134-155 capacity rule)
+    size_t cap = oldsize == 0 ? 0 : pow2_ceil(oldsize), ncap = pow2_ceil(newsize);
+    if (oldsize == 0) *out = (unsigned char*)malloc(ncap);
+    else if (ncap != cap) *out = (unsigned char*)realloc(*out, ncap);
+    if (!*out) { fprintf(stderr, "zopfli-b200: out of memory\n"); exit(EXIT_FAILURE); }
   }
-  append_bytes(buf.data() + skip, buf.size() - skip, out, outsize);
-  *bp = newbp;
+  unsigned char* o = *out;
+  // bytes that two pieces may share: cleared first, OR-merged after the parallel copy
+  struct Edge { size_t byte; unsigned char v; };
+  std::vector<Edge> edges(np * 2 + 2, Edge{(size_t)-1, 0});
+  for (size_t i = 0; i < np; i++) {
+    const size_t fb = (size_t)(start[i] / 8), lb = (size_t)(start[i + 1] / 8);
+    if (fb >= oldsize && fb < newsize) o[fb] = 0;
+    if (lb >= oldsize && lb < newsize) o[lb] = 0;
+  }
+  parallel_for(np, [&](size_t i) {
+    const Piece& p = pieces[i];
+    const uint64_t sb = start[i], eb = start[i + 1];
+    if (sb == eb) return;
+    Edge& e0 = edges[2 * i];
+    Edge& e1 = edges[2 * i + 1];
+    if (!p.stored) {
+      const unsigned char* src = p.bits.bytes.data();
+      const uint64_t nb = p.bits.nbits;
+      const int sh = (int)(sb & 7);
+      const size_t fb = (size_t)(sb / 8);
+      // destination byte fb + k holds source bits [8k - sh, 8k - sh + 8)
+      auto src_byte = [&](size_t k) -> unsigned {  // source byte k, zero outside the piece's bits
+        if ((uint64_t)k * 8 >= nb) return 0;
+        unsigned v = src[k];
+        const uint64_t left = nb - (uint64_t)k * 8;
+        if (left < 8) v &= (1u << left) - 1;
+        return v;
+      };
+      const size_t first_full = sh ? 1 : 0;                 // first destination byte owned entirely
+      const size_t end_full = (size_t)(eb / 8) - fb;         // one past the last entirely owned byte
+      if (sh) { e0.byte = fb; e0.v = (unsigned char)(src_byte(0) << sh); }
+      if (sh == 0) {
+        if (end_full > 0) memcpy(o + fb, src, end_full);
+      } else {
+        size_t k = first_full;
+        for (; k + 8 <= end_full && (uint64_t)(k + 8) * 8 <= nb; k += 8) {  // src[k-1 .. k+7] all inside
+          uint64_t lo;
+          memcpy(&lo, src + k - 1, 8);
+          const uint64_t v = (lo >> (8 - sh)) | ((uint64_t)src[k + 7] << (56 + sh));
+          memcpy(o + fb + k, &v, 8);
+        }
+        for (; k < end_full; k++) o[fb + k] = (unsigned char)((src_byte(k - 1) >> (8 - sh)) | (src_byte(k) << sh));
+      }
+      if (eb & 7) {  // trailing partial byte
+        const size_t k = end_full;
+        unsigned v = sh ? ((k ? src_byte(k - 1) >> (8 - sh) : 0u) | (src_byte(k) << sh)) : src_byte(k);
+        if (!(sh && k == 0)) { e1.byte = fb + k; e1.v = (unsigned char)v; }  // k == 0 with sh: already in e0
+      }
+    } else {
+      uint64_t q = sb;
+      size_t ip = p.instart;
+      bool first = true;
+      for (;;) {
+        size_t bs = 65535;
+        if (ip + bs > p.inend) bs = p.inend - ip;
+        const bool cur_final = ip + bs >= p.inend;
+        const unsigned hdr = (p.final && cur_final) ? 1u : 0u;  // BFINAL, BTYPE 00
+        if (first) {
+          // header bits land in the (possibly shared) byte q/8 -- and the byte after it when the
+          // three bits straddle a byte boundary, which then belongs to this piece alone
+          const unsigned v = hdr << (q & 7);
+          e0.byte = (size_t)(q / 8); e0.v = (unsigned char)v;
+          if ((q & 7) > 5) o[q / 8 + 1] = (unsigned char)(v >> 8);
+          first = false;
+        } else {
+          o[q / 8] = (unsigned char)hdr;  // byte aligned here
+        }
+        q += 3;
+        q = (q + 7) & ~(uint64_t)7;
+        unsigned char* d = o + q / 8;
+        const unsigned nlen = (~(unsigned)bs) & 0xffff;
+        d[0] = (unsigned char)(bs % 256);
+        d[1] = (unsigned char)((bs / 256) % 256);
+        d[2] = (unsigned char)(nlen % 256);
+        d[3] = (unsigned char)((nlen / 256) % 256);
+        memcpy(d + 4, in + ip, bs);
+        q += 32 + (uint64_t)bs * 8;
+        if (cur_final) break;
+        ip += bs;
+      }
+    }
+  });
+  for (const Edge& e : edges)
+    if (e.byte != (size_t)-1) o[e.byte] |= e.v;
+  *outsize = newsize > oldsize ? newsize : oldsize;
+  *bp = (unsigned char)(pos & 7);
 }
 
 }  // namespace zb

@@ -109,7 +109,7 @@ struct Lane {  // an independent stream + arena set; two lanes let a batch of gi
 struct Engine::Impl {
   std::mutex mu;  // input / log table / statistics
   int dev = 0;
-  Lane lane[2];
+  Lane lane[Engine::kLanes];
   // input (shared, read-only while parses run)
   DevBuf in_buf, same_buf, tile_first, next_tile, logtab;
   const uint8_t* d_in = nullptr;
@@ -139,8 +139,7 @@ struct Engine::Impl {
     CK(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t keep = ~0ull;  // keep freed arena memory cached in the pool
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    lane[0].init();
-    lane[1].init();
+    for (int k = 0; k < Engine::kLanes; k++) lane[k].init();
     DevBuf* shared[] = {&in_buf, &same_buf, &tile_first, &next_tile, &logtab};
     for (DevBuf* d : shared) d->st = lane[0].stream;
     CK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
@@ -349,7 +348,7 @@ void Engine::set_stream(void* s) {
 EngineStats Engine::stats() {
   std::lock_guard<std::mutex> g(p_->mu);
   EngineStats r = p_->st_acc;
-  for (int k = 0; k < 2; k++) {
+  for (int k = 0; k < Engine::kLanes; k++) {
     const EngineStats& a = p_->lane[k].acc;
     r.ms_keys += a.ms_keys; r.ms_scan += a.ms_scan; r.ms_scatter += a.ms_scatter; r.ms_match += a.ms_match;
     r.ms_greedy += a.ms_greedy; r.ms_iterate += a.ms_iterate; r.ms_pack += a.ms_pack; r.ms_d2h += a.ms_d2h;
@@ -365,7 +364,7 @@ EngineStats Engine::stats() {
 void Engine::reset_stats() {
   std::lock_guard<std::mutex> g(p_->mu);
   memset(&p_->st_acc, 0, sizeof(p_->st_acc));
-  for (int k = 0; k < 2; k++) memset(&p_->lane[k].acc, 0, sizeof(EngineStats));
+  for (int k = 0; k < Engine::kLanes; k++) memset(&p_->lane[k].acc, 0, sizeof(EngineStats));
 }
 
 void Engine::set_input_host(const uint8_t* in, size_t insize) {
@@ -399,7 +398,7 @@ void Engine::set_input_device(const uint8_t* dev_in, size_t insize) {
 
 void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out, int lane_id) {
   Impl& m = *p_;
-  Lane& l = m.lane[lane_id & 1];
+  Lane& l = m.lane[(unsigned)lane_id % Engine::kLanes];
   std::lock_guard<std::mutex> g(l.mu);
   CK(cudaSetDevice(m.dev));
   const size_t ns = ranges.size();
@@ -422,7 +421,10 @@ void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out, int 
     l.acc.launches++;
     if (L.any_parse) {
       l.tic();
-      k_iterate<<<(unsigned)ns, 32, 0, l.stream>>>(b, l.order.as<uint32_t>());
+      // one-warp CTAs: pad shared memory so that at most four fit on an SM and every DP chain
+      // has a scheduler partition of its own (a partition mate costs the chain ~20% of its speed)
+      static const unsigned pad = [] { const char* e = getenv("ZOPFLI_B200_ITER_PAD"); return e ? (unsigned)atoi(e) : 13u * 1024u; }();
+      k_iterate<<<(unsigned)ns, 32, pad, l.stream>>>(b, l.order.as<uint32_t>());
       CK(cudaGetLastError());
       l.toc(l.acc.ms_iterate);
       l.acc.launches++;
@@ -538,7 +540,7 @@ void Engine::match_table(uint64_t instart, uint64_t inend, std::vector<uint16_t>
 void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vector<uint64_t>& off,
                          const std::vector<uint32_t>& size, int lane_id) {
   Impl& m = *p_;
-  Lane& l = m.lane[lane_id & 1];
+  Lane& l = m.lane[(unsigned)lane_id % Engine::kLanes];
   std::lock_guard<std::mutex> g(l.mu);
   CK(cudaSetDevice(m.dev));
   const size_t ns = off.size();
@@ -592,7 +594,7 @@ void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vecto
 
 void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lane_id) {
   Impl& m = *p_;
-  Lane& l = m.lane[lane_id & 1];
+  Lane& l = m.lane[(unsigned)lane_id % Engine::kLanes];
   std::lock_guard<std::mutex> g(l.mu);
   CK(cudaSetDevice(m.dev));
   if (n == 0) return;

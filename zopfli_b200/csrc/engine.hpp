@@ -42,8 +42,9 @@ class Engine {
   void set_input_host(const uint8_t* in, size_t insize);
   void set_input_device(const uint8_t* dev_in, size_t insize);
 
-  // `lane` (0 or 1) selects one of two independent stream + arena sets; calls on different lanes
-  // may run concurrently from different host threads (a batch of giant blocks beside the rest).
+  // `lane` selects one of kLanes independent stream + arena sets; calls on different lanes may run
+  // concurrently from different host threads (chunk pipelines; giant blocks beside the rest).
+  static constexpr int kLanes = 8;
   void parse(const std::vector<ParseRange>& ranges, ParseResult& out, int lane = 0);
 
   // test seam: raw match table of one range (length, dist, expanded sublen[259] per position)

@@ -353,7 +353,6 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
   uint16_t* la = b.la + sd.pos_off + seg;
   uint32_t* psym = b.path + sd.pos_off + seg;  // traced symbols: (start position << 9) | length
   const uint8_t* in = b.in + sd.instart;
-  const uint16_t* sameg = b.same_g + sd.instart;
   const uint16_t* mlen = b.mlen + sd.pos_off;
   const uint32_t* runs_g = b.runs + sd.pos_off * kRunSlots;
   const uint8_t* dsx_g = b.dsx + sd.pos_off * 32;
