@@ -512,15 +512,56 @@ __device__ __forceinline__ uint32_t table_dist(const Batch& b, uint64_t o, uint3
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_greedy: ZopfliLZ77Greedy (lz77.c:544-630) over the (len,dist) table; one warp per segment,
-// lane 0 runs the lazy-matching state machine out of shared-memory windows the warp refills.
+// k_greedy: ZopfliLZ77Greedy (lz77.c:544-630) over the (len,dist) table; one warp per segment.
+//
+// The reference's lazy-matching loop is a state machine with two kinds of state per position:
+// B(i) "at i, nothing pending" and H(j) "at j, the match found at j-1 is pending".  Everything
+// that happens between one B state and the next is a pure function of the table entries just
+// ahead (the H chain needs the score to grow by at least 2 per step, so it is at most 128 long).
+// Per window of positions the warp therefore
+//   1. evaluates that function for EVERY position as if it were a B state (32 wide): how far the
+//      next B state is and how many symbols are emitted on the way;
+//   2. lets lane 0 hop from B state to B state through that table (one shared-memory load per hop);
+//   3. re-walks the visited B states 32 wide to emit their symbols at the offsets found in 2.
+// Only step 2 is serial, and it costs one load per hop instead of the whole lazy-matching logic.
 
-constexpr int kGreedyWin = 2048;
+constexpr int kGreedyWin = 2048;    // B states evaluated per window
+constexpr int kGreedyLook = 192;    // table entries loaded past the window (H chain <= 128 steps)
+
+// walks from B(r) to the next B state.  T = (len << 16 | dist) entries, relative indexing.
+// Emit(sym_index, litlen, dist) is called for each symbol in order.  Returns the next B position.
+template <typename Emit>
+__device__ __forceinline__ uint32_t greedy_walk(const uint32_t* T, const uint8_t* by, uint32_t r, uint32_t& cnt,
+                                                Emit emit) {
+  auto score = [](uint32_t e) { return (int)(e >> 16) - ((e & 0xffffu) > 1024u ? 1 : 0); };  // lz77.c:265-271
+  auto holdable = [&](uint32_t e) { return score(e) >= kMinMatch && (e >> 16) < (uint32_t)kMaxMatch; };
+  cnt = 0;
+  uint32_t e = T[r];
+  if (!holdable(e)) {  // lz77.c:619-629
+    if (score(e) >= kMinMatch) { emit(cnt++, e >> 16, e & 0xffffu); return r + (e >> 16); }
+    emit(cnt++, (uint32_t)by[r], 0u);
+    return r + 1;
+  }
+  uint32_t j = r + 1;
+  for (;;) {  // H(j): the match at j-1 is pending (lz77.c:584-609)
+    const uint32_t ej = T[j];
+    if (score(ej) > score(e) + 1) {
+      emit(cnt++, (uint32_t)by[j - 1], 0u);         // the pending match loses: its position becomes a literal
+      if (holdable(ej)) { e = ej; j++; continue; }
+      emit(cnt++, ej >> 16, ej & 0xffffu);          // cannot be held (length 258): emitted at once
+      return j + (ej >> 16);
+    }
+    emit(cnt++, e >> 16, e & 0xffffu);              // the pending match wins
+    return j - 1 + (e >> 16);
+  }
+}
 
 __global__ void __launch_bounds__(32) k_greedy(Batch b, int buf) {
-  __shared__ uint32_t wld[kGreedyWin];
-  __shared__ uint8_t wby[kGreedyWin];
-  __shared__ uint16_t oll[1024], od[1024];
+  __shared__ uint32_t wld[kGreedyWin + kGreedyLook];
+  __shared__ uint8_t wby[kGreedyWin + kGreedyLook];
+  __shared__ uint32_t wf[kGreedyWin];      // distance to the next B state (16) | symbols emitted (16)
+  __shared__ uint32_t bl[kGreedyWin];      // visited B states: relative position (16) | output offset (16)
+  __shared__ uint16_t oll[kGreedyWin + 512], od[kGreedyWin + 512];
   const uint32_t seg = blockIdx.x, lane = threadIdx.x;
   const SegDesc sd = b.segs[seg];
   if (sd.mode == 2) {  // fixed-tree parse needs no greedy seed
@@ -531,62 +572,45 @@ __global__ void __launch_bounds__(32) k_greedy(Batch b, int buf) {
   const uint8_t* in = b.in + sd.instart;
   uint16_t* out_ll = b.st_ll[buf] + sd.pos_off;
   uint16_t* out_d = b.st_d[buf] + sd.pos_off;
-  uint32_t i = 0, nout = 0, flushed = 0;
-  uint32_t prev_length = 0, prev_match = 0;
-  int match_available = 0;
   const uint32_t n = sd.npos;
+  uint32_t i = 0, nout = 0;
   while (i < n) {
     const uint32_t wb = i;
-    const uint32_t wn = (n - wb) < (uint32_t)kGreedyWin ? (n - wb) : (uint32_t)kGreedyWin;
+    const uint32_t wn = (n - wb) < (uint32_t)(kGreedyWin + kGreedyLook) ? (n - wb) : (uint32_t)(kGreedyWin + kGreedyLook);
+    const uint32_t nchain = wn < (uint32_t)kGreedyWin ? wn : (uint32_t)kGreedyWin;
     for (uint32_t t = lane; t < wn; t += 32) { wld[t] = ld[wb + t]; wby[t] = in[wb + t]; }
     __syncwarp();
-    if (lane == 0) {
-      while (i < wb + wn && nout - flushed < 1022) {
-        uint32_t e = wld[i - wb];
-        uint32_t leng = e >> 16, dist = e & 0xffffu;
-        int lengthscore = dist > 1024 ? (int)leng - 1 : (int)leng;  // GetLengthScore lz77.c:265-271
-        int prevlengthscore = prev_match > 1024 ? (int)prev_length - 1 : (int)prev_length;
-        bool emit_normal = true;
-        if (match_available) {  // lz77.c:584-609
-          match_available = 0;
-          if (lengthscore > prevlengthscore + 1) {
-            // previous position becomes a literal; its byte is in the window unless i == wb
-            uint8_t pb = (i > wb) ? wby[i - 1 - wb] : in[i - 1];
-            oll[(nout - flushed)] = pb; od[(nout - flushed)] = 0; nout++;
-            if (lengthscore >= kMinMatch && leng < (uint32_t)kMaxMatch) {
-              match_available = 1; prev_length = leng; prev_match = dist;
-              i++;
-              emit_normal = false;
-            }
-          } else {
-            oll[(nout - flushed)] = (uint16_t)prev_length; od[(nout - flushed)] = (uint16_t)prev_match; nout++;
-            i += prev_length - 1;  // match started at i-1
-            emit_normal = false;
-          }
-        } else if (lengthscore >= kMinMatch && leng < (uint32_t)kMaxMatch) {  // lz77.c:610-615
-          match_available = 1; prev_length = leng; prev_match = dist;
-          i++;
-          emit_normal = false;
-        }
-        if (emit_normal) {  // lz77.c:619-629
-          if (lengthscore >= kMinMatch) {
-            oll[(nout - flushed)] = (uint16_t)leng; od[(nout - flushed)] = (uint16_t)dist; nout++;
-            i += leng;
-          } else {
-            oll[(nout - flushed)] = wby[i - wb]; od[(nout - flushed)] = 0; nout++;
-            i += 1;
-          }
-        }
+    for (uint32_t r = lane; r < nchain; r += 32) {  // 1: every position as a B state
+      uint32_t cnt;
+      const uint32_t nx = greedy_walk(wld, wby, r, cnt, [](uint32_t, uint32_t, uint32_t) {});
+      wf[r] = (nx - r) | (cnt << 16);
+    }
+    __syncwarp();
+    uint32_t r = 0, k = 0, off = 0;
+    if (lane == 0) {  // 2: hop through the B states that are actually reached
+      while (r < nchain) {
+        const uint32_t e = wf[r];
+        bl[k++] = r | (off << 16);
+        off += e >> 16;
+        r += e & 0xffffu;
       }
     }
-    i = __shfl_sync(0xffffffffu, i, 0);
-    nout = __shfl_sync(0xffffffffu, nout, 0);
-    match_available = __shfl_sync(0xffffffffu, match_available, 0);
-    prev_length = __shfl_sync(0xffffffffu, prev_length, 0);
-    prev_match = __shfl_sync(0xffffffffu, prev_match, 0);
+    r = __shfl_sync(0xffffffffu, r, 0);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    off = __shfl_sync(0xffffffffu, off, 0);
     __syncwarp();
-    for (uint32_t t = lane; t < nout - flushed; t += 32) { out_ll[flushed + t] = oll[t]; out_d[flushed + t] = od[t]; }
-    flushed = nout;
+    for (uint32_t q = lane; q < k; q += 32) {  // 3: emit
+      const uint32_t e = bl[q], o = e >> 16;
+      uint32_t cnt;
+      greedy_walk(wld, wby, e & 0xffffu, cnt, [&](uint32_t t, uint32_t l, uint32_t d) {
+        oll[o + t] = (uint16_t)l;
+        od[o + t] = (uint16_t)d;
+      });
+    }
+    __syncwarp();
+    for (uint32_t t = lane; t < off; t += 32) { out_ll[nout + t] = oll[t]; out_d[nout + t] = od[t]; }
+    nout += off;
+    i = wb + r;
     __syncwarp();
   }
   if (lane == 0) b.jobs[seg].greedy_size = nout;
