@@ -80,9 +80,13 @@ struct Lane {  // an independent stream + arena set; two lanes let a batch of gi
   uint32_t ovf_cap = 1u << 22;
   EngineStats acc;
 
-  void init() {
+  void init(bool high_priority) {
     memset(&acc, 0, sizeof(acc));
-    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    // even lanes carry the longest DP chains (driver.cpp stage C): their few CTAs must not queue
+    // behind the thousands of CTAs of another lane's match kernels
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, high_priority ? hi : lo));
     CK(cudaEventCreate(&ev[0]));
     CK(cudaEventCreate(&ev[1]));
     DevBuf* all[] = {&segs, &keywork, &poswork, &order, &hv, &hv2, &idx1, &idx2, &rank1, &rank2, &bkt1, &bkt2, &ld,
@@ -139,10 +143,11 @@ struct Engine::Impl {
     CK(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t keep = ~0ull;  // keep freed arena memory cached in the pool
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    for (int k = 0; k < Engine::kLanes; k++) lane[k].init();
+    for (int k = 0; k < Engine::kLanes; k++) lane[k].init((k & 1) == 0);
     DevBuf* shared[] = {&in_buf, &same_buf, &tile_first, &next_tile, &logtab};
     for (DevBuf* d : shared) d->st = lane[0].stream;
     CK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
+    CK(cudaFuncSetAttribute(k_iterate, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
     // L[n] = log(n) * kInvLog2 with the HOST libm, exactly the two operations of tree.c:79,85
     log_thread = std::thread([this]() {
       log_host.resize(kLogTabN);
@@ -423,7 +428,11 @@ void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out, int 
       l.tic();
       // one-warp CTAs: pad shared memory so that at most four fit on an SM and every DP chain
       // has a scheduler partition of its own (a partition mate costs the chain ~20% of its speed)
-      static const unsigned pad = [] { const char* e = getenv("ZOPFLI_B200_ITER_PAD"); return e ? (unsigned)atoi(e) : 13u * 1024u; }();
+      // A batch of only a few blocks (the giants of stage C) takes whole SMs: with 188 KB of padding
+      // no kernel that uses shared memory can move in beside the chain.
+      static const unsigned pad_many = [] { const char* e = getenv("ZOPFLI_B200_ITER_PAD"); return e ? (unsigned)atoi(e) : 13u * 1024u; }();
+      static const unsigned pad_few = [] { const char* e = getenv("ZOPFLI_B200_ITER_PAD_FEW"); return e ? (unsigned)atoi(e) : 188u * 1024u; }();
+      const unsigned pad = ns <= 64 ? pad_few : pad_many;
       k_iterate<<<(unsigned)ns, 32, pad, l.stream>>>(b, l.order.as<uint32_t>());
       CK(cudaGetLastError());
       l.toc(l.acc.ms_iterate);
