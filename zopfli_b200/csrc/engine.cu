@@ -147,7 +147,11 @@ struct Engine::Impl {
     DevBuf* shared[] = {&in_buf, &same_buf, &tile_first, &next_tile, &logtab};
     for (DevBuf* d : shared) d->st = lane[0].stream;
     CK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
-    CK(cudaFuncSetAttribute(k_iterate, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024));
+    {
+      cudaFuncAttributes fa;
+      CK(cudaFuncGetAttributes(&fa, k_iterate));
+      CK(cudaFuncSetAttribute(k_iterate, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
+    }
     // L[n] = log(n) * kInvLog2 with the HOST libm, exactly the two operations of tree.c:79,85
     log_thread = std::thread([this]() {
       log_host.resize(kLogTabN);
@@ -430,10 +434,11 @@ void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out, int 
       // has a scheduler partition of its own (a partition mate costs the chain ~20% of its speed)
       // A batch of only a few blocks (the giants of stage C) takes whole SMs: with 188 KB of padding
       // no kernel that uses shared memory can move in beside the chain.
-      static const unsigned pad_many = [] { const char* e = getenv("ZOPFLI_B200_ITER_PAD"); return e ? (unsigned)atoi(e) : 13u * 1024u; }();
-      static const unsigned pad_few = [] { const char* e = getenv("ZOPFLI_B200_ITER_PAD_FEW"); return e ? (unsigned)atoi(e) : 188u * 1024u; }();
+      static const unsigned static_smem = [] { cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_iterate)); return (unsigned)fa.sharedSizeBytes; }();
+      static const unsigned pad_many = [] { const char* e = getenv("ZOPFLI_B200_ITER_PAD"); return e ? (unsigned)atoi(e) : 56u * 1024u - static_smem; }();
+      static const unsigned pad_few = [] { const char* e = getenv("ZOPFLI_B200_ITER_PAD_FEW"); return e ? (unsigned)atoi(e) : 222u * 1024u - static_smem; }();
       const unsigned pad = ns <= 64 ? pad_few : pad_many;
-      k_iterate<<<(unsigned)ns, 32, pad, l.stream>>>(b, l.order.as<uint32_t>());
+      k_iterate<<<(unsigned)ns, 64, pad, l.stream>>>(b, l.order.as<uint32_t>());
       CK(cudaGetLastError());
       l.toc(l.acc.ms_iterate);
       l.acc.launches++;

@@ -19,12 +19,29 @@
 
 namespace zb {
 
-struct RingEnt { double c; uint32_t len; uint32_t pad; };   // cost (float-representable) + best incoming length
-struct DpStage {                       // forward-DP working set
-  RingEnt ring[512];                   // pending costs of targets >= j+35 (long edges only), mod 512
-  uint32_t runs[4][32 * kRunSlots];    // TMA-staged run lists, ring of 4 groups of 32 positions
-  uint8_t dsx[4][32 * 32];             // TMA-staged first-round distance symbols (128-row ring)
-  double gl[64];                       // literal cost of the byte at each position (2 groups)
+struct RingEnt { double c; uint32_t code; uint32_t pad; };  // cost (float-representable) + length code of the best edge
+// length codes (decoded by decode_len): the window records only WHICH step produced the best edge
+constexpr uint32_t kCodeLit = 0x800u;    // literal
+constexpr uint32_t kCodeLong = 0x400u;   // | length, for edges longer than 34 (shared-memory ring)
+                                         // otherwise: (source step & 31) + 3 (length = target - source, 3..34)
+__host__ __device__ __forceinline__ uint32_t decode_len(uint32_t code, uint32_t target) {
+  if (code & kCodeLit) return 1u;
+  if (code & kCodeLong) return code & 0x3ffu;
+  return ((target - code) & 31u) + 3u;
+}
+struct DpStage {                       // forward-DP working set; 4 stages of 32 positions each
+  RingEnt ring[512];                   // pending costs of targets >= j+35 (long edges only); slot (t-3) & 511
+  uint32_t runs[4][32 * kRunSlots];    // TMA-staged run lists
+  uint8_t dsx[4 * 32 * 32 + 128];      // TMA-staged first-round distance symbols, rows pre-rotated by k_match;
+                                       // the last 128 bytes mirror rows 0-3 of stage 0 (reads run 3 rows ahead)
+  double gl[4 * 32 + 2];               // literal cost of the byte at each position; [128..129] mirror [0..1] (feeder warp)
+  uint16_t mk[4][32];                  // mlen16 of each position                             (feeder warp)
+  uint16_t lac[4][32];                 // length codes of length_array[32g + l]              (DP warp -> feeder)
+  uint32_t flag[4];                    // ballot: position needs the general path            (feeder warp)
+  RingEnt xch[4];                      // pending(j+3) handed from its owner lane to all lanes: written at step j,
+                                       // loaded at step j+1, used at step j+2.  Shared memory rather than shuffles
+                                       // because the order of memory operations is the one thing the assembler keeps:
+                                       // a shuffle is sunk to just before its use and its latency lands on the chain.
 };
 struct WarpPm {                        // warp-wide package-merge working set (warp_length_limited)
   uint32_t key[kNumLL];                // active symbols sorted by (weight << 9 | symbol)
@@ -42,13 +59,16 @@ struct IterSmem {
   double llcost[kNumLL];   // ll_symbols
   double dcost[kNumD];     // d_symbols
   double lencost[260];     // llcost[length_symbol(k)]
-  double t0[31 * 32];      // first-round edge costs: t0[dsym*32 + l] = cost(3+l, dist of dsym); row 30 = +inf
+  double t0[31 * 64];      // first-round edge costs, each row twice: t0[dsym*64 + c] = cost(3 + ((c - 1) & 31), dist
+                           // of dsym) so that a lane's column (cm + 33 - step) needs no wrap; row 30 = +inf
   union __align__(16) {
     DpStage dp;
     CostStage cs;
     uint16_t win[8192];    // trace-back window
   } u;
-  __align__(8) uint64_t mbar[4];
+  __align__(8) uint64_t full[4];   // stage filled (TMA bytes + feeder scalars)
+  __align__(8) uint64_t empty[4];  // stage consumed by the DP warp
+  uint32_t go;                     // DP warp -> feeder warp: another iteration follows
   uint32_t hist[320];
   uint32_t stats[320], last[320], bests[320];
 };
@@ -98,6 +118,28 @@ __device__ __forceinline__ double round_to_f32(double x) {
   b += 0x0FFFFFFFLL + ((b >> 29) & 1);
   b &= ~0x1FFFFFFFLL;
   return __longlong_as_double(b);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cta_sync64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u16_if(uint32_t a, uint32_t v, bool p) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.u16 [%0], %1; }" ::"r"(a), "h"((unsigned short)v), "r"((uint32_t)p) : "memory");
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double c) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(c) : "memory");
+}
+// ring entry {cost, code}
+__device__ __forceinline__ void lds_ring(uint32_t a, double& c, uint32_t& code) {
+  unsigned long long x, y;
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a) : "memory");
+  c = __longlong_as_double((long long)x);
+  code = (uint32_t)y;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -196,7 +238,7 @@ __device__ __forceinline__ void warp_bitonic_sort(uint32_t* keys, int ns, uint32
 }
 
 // freq: n counts in shared memory (n <= 288, counts < 2^22); out: n code lengths, maxbits 15
-__device__ void warp_length_limited(const uint32_t* freq, int n, uint8_t* out, WarpPm& pm, uint32_t lane) {
+__device__ __noinline__ void warp_length_limited(const uint32_t* freq, int n, uint8_t* out, WarpPm& pm, uint32_t lane) {
   const uint32_t full = 0xffffffffu;
   int ns = 0;
   for (int base = 0; base < n; base += 32) {
@@ -339,15 +381,20 @@ __device__ __forceinline__ uint32_t first_dist_of_symbol(int sd) {  // squeeze.c
   return sd < 4 ? (uint32_t)sd + 1 : 1u + ((2u + (uint32_t)(sd & 1)) << (sd / 2 - 1));
 }
 
-__global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restrict__ order) {
+// Two warps per block.  Warp 0 runs the whole algorithm; warp 1 is the FEEDER of the forward DP: it
+// issues the TMA copies of the match-table rows, stages the per-position scalars (literal cost,
+// match length, general-path flags) and writes the finished length_array entries back to global
+// memory, three groups of 32 positions ahead of / behind the DP warp (full[] / empty[] mbarriers).
+// Outside the DP phase it is parked at a named barrier.
+__global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restrict__ order) {
   __shared__ IterSmem s;
-  const uint32_t seg = order[blockIdx.x], lane = threadIdx.x;
+  const uint32_t seg = order[blockIdx.x], lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   const SegDesc sd = b.segs[seg];
   if (sd.mode == 0) return;
   JobState* js = &b.jobs[seg];
   const uint32_t nb = sd.npos;
   if (nb == 0) {
-    if (lane == 0) { js->best_size = 0; js->best_buf = 0; js->best_cost = 0; js->iters_done = 0; }
+    if (threadIdx.x == 0) { js->best_size = 0; js->best_buf = 0; js->best_cost = 0; js->iters_done = 0; }
     return;
   }
   uint16_t* la = b.la + sd.pos_off + seg;
@@ -359,12 +406,64 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
   const bool fixed = sd.mode == 2;
   int curbuf = 0, bestbuf = 1;
   uint32_t flags = 0;
-  if (lane == 0) {
-    for (int i = 0; i < 4; i++) mbar_init(&s.mbar[i], 1);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
+  // the staged distance symbols index the cost table: keep every byte of the staging area <= 30
+  for (uint32_t t = threadIdx.x; t < sizeof(s.u.dp.dsx) / 4; t += 64) ((uint32_t*)&s.u.dp.dsx[0])[t] = 0;
+  __syncthreads();
   uint32_t seq_base = 0;  // running group sequence number: stage = seq & 3, parity = (seq >> 2) & 1
+  const uint32_t ngroups = (nb + 31) >> 5;
+
+  if (wid == 1) {
+    // ================================================================== feeder warp
+    for (;;) {
+      cta_sync64();  // (A) the DP warp has published go and this iteration's literal costs
+      if (*(volatile uint32_t*)&s.go == 0) break;
+      const uint32_t end = seq_base + ngroups;
+      uint32_t fed = seq_base, fl = seq_base;
+      uint32_t pf_m16 = 0, pf_byte = 0;
+      { const uint32_t p = lane; if (p < nb) { pf_m16 = mlen[p]; pf_byte = in[p]; } }
+      while (fl < end) {
+        if (fed < end && fed < fl + 4) {
+          // ---- fill stage fed & 3 with group g ----
+          const uint32_t g = fed - seq_base, st = fed & 3u;
+          const uint32_t m16 = pf_m16;
+          const double lc = s.llcost[pf_byte];
+          s.u.dp.gl[st * 32 + lane] = lc;
+          if (st == 0 && lane < 2) s.u.dp.gl[128 + lane] = lc;
+          s.u.dp.mk[st][lane] = (uint16_t)m16;
+          const uint32_t fw = __ballot_sync(0xffffffffu, (m16 & kShortcutFlag) != 0 || (m16 & 0x7fffu) > 34u);
+          if (lane == 0) s.u.dp.flag[st] = fw;
+          { const uint32_t p = (g + 1) * 32 + lane; pf_m16 = 0; pf_byte = 0; if (p < nb) { pf_m16 = mlen[p]; pf_byte = in[p]; } }
+          __syncwarp();
+          if (lane == 0) {
+            const uint32_t cnt = nb - g * 32 < 32u ? nb - g * 32 : 32u, bytes = cnt * 32;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t mirror = st == 0 ? (bytes < 128u ? bytes : 128u) : 0u;
+            mbar_expect_tx(&s.full[st], bytes * 2 + mirror);
+            bulk_g2s(&s.u.dp.dsx[st * 1024], dsx_g + (size_t)g * 1024, bytes, &s.full[st]);
+            if (mirror) bulk_g2s(&s.u.dp.dsx[4096], dsx_g + (size_t)g * 1024, mirror, &s.full[st]);
+            bulk_g2s(s.u.dp.runs[st], runs_g + (size_t)g * 256, bytes, &s.full[st]);
+          }
+          fed++;
+        } else {
+          // ---- group fl is done: write its length_array entries, which frees its stage ----
+          const uint32_t st = fl & 3u;
+          mbar_wait(&s.empty[st], (fl >> 2) & 1u);
+          const uint32_t p = (fl - seq_base) * 32 + lane;
+          if (p < nb) la[p] = (uint16_t)decode_len(s.u.dp.lac[st][lane], p);
+          __syncwarp();
+          fl++;
+        }
+      }
+      seq_base = end;
+      cta_sync64();  // (B) length_array complete
+    }
+    return;
+  }
+  // ====================================================================== DP warp (warp 0)
 
   // ---- initial statistics: greedy parse (squeeze.c:481-482) or the fixed tree (:125-140) ----
   if (!fixed) {
@@ -404,8 +503,8 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
     // ------------------------------------------------------------------ model constants
     for (int k = lane; k < 260; k += 32) s.lencost[k] = k >= 3 && k <= 258 ? s.llcost[length_symbol(k)] : 0.0;
     __syncwarp();
-    for (int i = lane; i < 31 * 32; i += 32) {  // GetCostStat squeeze.c:146-157 for lengths 3..34
-      const int ds = i >> 5, k = 3 + (i & 31);
+    for (int i = lane; i < 31 * 64; i += 32) {  // GetCostStat squeeze.c:146-157 for lengths 3..34
+      const int ds = i >> 6, k = 3 + ((i + 31) & 31);
       s.t0[i] = ds < 30 ? (double)(length_extra_bits(k) + dist_symbol_extra_bits(ds)) + s.lencost[k] + s.dcost[ds] : 1e300;
     }
     __syncwarp();
@@ -457,236 +556,217 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
     ZB_TICK(0);
 
     // ------------------------------------------------------------------ forward DP
-    // Push form with a REGISTER WINDOW.  At step j lane l holds the pending cost (and the length
-    // that produced it) of target j+3+l, complete for sources < j.  Source j relaxes all 32 of them
-    // at once (lane l owns length 3+l), lane 0's value -- now complete for every length edge --
-    // leaves the window to meet the literal edge two steps later, and the window shifts down by
-    // one lane.  The short edges therefore never touch memory; only edges longer than 34
-    // (rare outside byte runs) go through a shared-memory ring whose entry joins the window at
-    // lane 31 when its target comes within reach.  Costs are doubles that are exactly
-    // float-representable: the reference stores floats and widens them on every use
-    // (squeeze.c:222,278-300); rounding is done in integer arithmetic.  Relaxation order per
-    // target is source order, as in the reference, so ties resolve identically.
+    // Push form with a REGISTER WINDOW.  Lane l owns the targets t == l (mod 32): at step j it
+    // holds pending(t) for the one such t in [j+3, j+34], complete for sources < j, and relaxes it
+    // with length k = t - j.  The lane whose target is j+3 hands its completed value to the chain
+    // (it meets the literal edge two steps later) and takes on target j+35.  The short edges never
+    // touch memory; only edges longer than 34 (rare outside byte runs) go through a shared-memory
+    // ring whose entry joins the window when its target comes within reach.  Costs are doubles that
+    // are exactly float-representable: the reference stores floats and widens them on every use
+    // (squeeze.c:222,278-300); rounding is done in integer arithmetic.  Relaxation order per target
+    // is source order, as in the reference, so ties resolve identically.  The window keeps a
+    // length CODE (which step produced the edge), decoded when length_array is written.
     const double kInfD = (double)(float)1e30;  // ZOPFLI_LARGE_FLOAT stored to float, squeeze.c:243
-    for (int t = lane; t < 512; t += 32) { s.u.dp.ring[t].c = kInfD; s.u.dp.ring[t].len = 0; }
+    for (int t = lane; t < 512; t += 32) { s.u.dp.ring[t].c = kInfD; s.u.dp.ring[t].code = 0; }
+    if (lane < 4) { s.u.dp.xch[lane].c = kInfD; s.u.dp.xch[lane].code = 0; }
+    if (lane == 0) s.go = 1;
     __syncwarp();
+    cta_sync64();  // (A) start the feeder
     {
       const uint32_t full = 0xffffffffu;
-      const uint32_t ngroups = (nb + 31) >> 5;
-      const uint32_t ring_a = smem_u32(&s.u.dp.ring[0]);
-      const uint32_t gl_a = smem_u32(&s.u.dp.gl[0]);
-      auto issue_group = [&](uint32_t g, uint32_t seq) {  // lane 0
-        const uint32_t cnt = nb - g * 32 < 32u ? nb - g * 32 : 32u;
-        const uint32_t st = seq & 3, bytes = cnt * 32;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&s.mbar[st], bytes * 2);
-        bulk_g2s(s.u.dp.dsx[st], dsx_g + (size_t)g * 1024, bytes, &s.mbar[st]);
-        bulk_g2s(s.u.dp.runs[st], runs_g + (size_t)g * 256, bytes, &s.mbar[st]);
-      };
-      // staging buffer and barrier of group g are both (seq_base + g) & 3; sequence numbers run on
-      // without gaps across iterations so every barrier completes one phase per use
-      const uint32_t joff = (seq_base & 3u) * 32u;  // row-ring offset of this iteration's row 0
-      // per-group scalars: mlen16 (lane-distributed) and literal costs staged in shared memory
-      uint32_t mk_cur = 0, mk_next = 0;      // mlen16 of position 32g+lane for the current / next group
-      uint32_t flag_cur = 0, flag_next = 0;  // ballot: position needs the general path (shortcut flag or mlen > 34)
-      // scalars of a group are fetched one group ahead into registers (pf_m16 / pf_byte) so that the
-      // global-load latency never sits on the DP chain
-      uint32_t pf_m16 = 0, pf_byte = 0;
-      auto prefetch_scalars = [&](uint32_t g) {
-        const uint32_t p = g * 32 + lane;
-        pf_m16 = 0; pf_byte = 0;
-        if (p < nb) { pf_m16 = mlen[p]; pf_byte = in[p]; }
-      };
-      auto acquire = [&](uint32_t g, uint32_t seq) {  // make group g readable; all lanes
-        const uint32_t m16 = pf_m16;
-        s.u.dp.gl[(g & 1) * 32 + lane] = s.llcost[pf_byte];
-        mk_next = m16;
-        flag_next = __ballot_sync(full, (m16 & kShortcutFlag) != 0 || (m16 & 0x7fffu) > 34u);
-        prefetch_scalars(g + 1);
-        mbar_wait(&s.mbar[seq & 3], (seq >> 2) & 1);
-        __syncwarp();
-      };
-      if (lane == 0) {
-        issue_group(0, seq_base);
-        if (ngroups > 1) issue_group(1, seq_base + 1);
-        if (ngroups > 2) issue_group(2, seq_base + 2);
-      }
-      prefetch_scalars(0);
-      acquire(0, seq_base);
-      mk_cur = mk_next; flag_cur = flag_next;
-      // register window and pipeline state.  Lane l owns the targets t == l (mod 32): at step j
-      // it holds pending(t) for the one such t in [j+3, j+34] and relaxes it with length
-      // k = t - j = 3 + col, col = (l - j - 3) mod 32.  Nothing moves between lanes; the lane
-      // whose target is j+3 (col 0) hands its completed value to the chain and takes on j+35.
+      // shared-memory base addresses, kept opaque so they stay in registers
+      // this lane's cost-table column at step jl' of a group is t0_l - 8 jl' for jl' in [2, 33] (32, 33: steps 0, 1 of the next group)
+      uint32_t t0_l = smem_u32(&s.t0[0]) + (((lane - 3u) & 31u) + 33u) * 8u;
+      uint32_t dsx_r = smem_u32(&s.u.dp.dsx[0]) + lane, gl_r = smem_u32(&s.u.dp.gl[0]);
+      uint32_t ring_r = smem_u32(&s.u.dp.ring[0]), lac_r = smem_u32(&s.u.dp.lac[0][0]), mk_r = smem_u32(&s.u.dp.mk[0][0]);
+      asm volatile("" : "+r"(t0_l), "+r"(dsx_r), "+r"(gl_r), "+r"(ring_r), "+r"(lac_r), "+r"(mk_r));
+      const bool is_l0 = lane == 0;
       double w = kInfD; uint32_t wl = 0;
-      double e1c = kInfD, e2c = kInfD; uint32_t e1l = 0, e2l = 0;  // pending(j+2), pending(j+1)
+      double e2c = kInfD; uint32_t e2l = 0;  // pending(j+1)
+      uint32_t xch_r = smem_u32(&s.u.dp.xch[0]);
+      asm volatile("" : "+r"(xch_r));
       double cj = 0.0;
-      uint32_t lfin_prev = 0;                            // length_array[j], recorded one step late
-      uint32_t mylen = 0;                                // length_array[32g+lane] of the current group
-      uint32_t dirty_until = 0;                          // largest target that has a ring entry
+      uint32_t lfin_prev = 0;           // code of length_array[j], stored one step late
+      uint32_t dirty_until = 0;         // largest target that has a ring entry
       uint32_t skip_left = 0;
       bool just_finished = false;
-      // keep the shared-memory base addresses opaque so they stay in registers
-      uint32_t t0_r = smem_u32(&s.t0[0]), gl_r = gl_a, dsx_r = smem_u32(&s.u.dp.dsx[0][0]), ring_r = ring_a;
-      asm volatile("" : "+r"(t0_r), "+r"(gl_r), "+r"(dsx_r), "+r"(ring_r));
-      // operand prefetch pipeline: tv = edge cost for step j, ds_n = distance symbol for step j+1
-      uint32_t col = (lane - 3u) & 31u;                  // column of step 0
-      uint32_t ds_n = min(lds_u8(dsx_r + ((joff & 127u) * 32) + col), kNoEdge);
-      double tv = lds_f64(t0_r + ds_n * 256 + col * 8);
-      ds_n = nb > 1 ? min(lds_u8(dsx_r + (((1 + joff) & 127u) * 32) + ((col - 1u) & 31u)), kNoEdge) : kNoEdge;
-      double llb = lds_f64(gl_a);
+      // operand pipeline, two steps deep so that no shared-memory latency meets the cost chain:
+      // tv / tv1 = edge costs for steps j, j+1; ds2 = distance symbol for step j+2; llb / llb1 = literal costs
+      mbar_wait(&s.full[seq_base & 3u], (seq_base >> 2) & 1u);
+      double tv, tv1, llb, llb1;
+      uint32_t ds2;
+      {
+        const uint32_t d0 = dsx_r + (seq_base & 3u) * 1024, g0 = gl_r + (seq_base & 3u) * 256;
+        tv = lds_f64(t0_l + lds_u8(d0) * 512 - 32 * 8);
+        tv1 = lds_f64(t0_l + lds_u8(d0 + 32) * 512 - 33 * 8);
+        ds2 = lds_u8(d0 + 64);
+        llb = lds_f64(g0);
+        llb1 = lds_f64(g0 + 8);
+      }
 
-      // one step of the common case: no shortcut, no length > 34 at this position, no ring entry
-      // coming due, and the squeeze.c:293 test proven redundant.  Straight-line code.
-#define ZB_DP_FAST_STEP(J)                                                                        \
-      {                                                                                           \
-        const uint32_t j_ = (J);                                                                  \
-        const uint32_t c1_ = (col - 1u) & 31u, c2_ = (col - 2u) & 31u;                            \
-        const double tv_n_ = lds_f64(t0_r + ds_n * 256 + c1_ * 8);                                \
-        const uint32_t ds_nn_ = min(lds_u8(dsx_r + ((j_ + 2 + joff) & 127) * 32 + c2_), kNoEdge); \
-        const double llb_n_ = lds_f64(gl_r + ((j_ + 1) & 63) * 8);                                \
-        if (lane == (j_ & 31)) mylen = lfin_prev;                                                 \
-        const double lit_ = llb + cj;                                                             \
-        const bool take_ = lit_ < e2c;                                                            \
-        const double cnext_ = take_ ? round_to_f32(lit_) : e2c;                                   \
-        lfin_prev = take_ ? 1u : e2l;                                                             \
-        const double nc_ = tv + cj;                                                               \
-        double rn_ = round_to_f32(nc_);                                                           \
-        asm volatile("" : "+d"(rn_));                                                             \
-        const bool ok_ = nc_ < w;                                                                 \
-        w = ok_ ? rn_ : w;                                                                        \
-        wl = ok_ ? col + 3u : wl;                                                                 \
-        const uint32_t src_ = (j_ + 3) & 31;                                                      \
-        const double xc_ = __shfl_sync(full, w, src_);                                            \
-        const uint32_t xl_ = __shfl_sync(full, wl, src_);                                         \
-        if (col == 0) { w = kInfD; wl = 0; }                                                      \
-        e2c = e1c; e2l = e1l; e1c = xc_; e1l = xl_;                                               \
-        cj = cnext_;                                                                              \
-        tv = tv_n_; ds_n = ds_nn_; llb = llb_n_; col = c1_;                                       \
+      // one step of the common case: no shortcut, no length > 34 at this position, the squeeze.c:293
+      // test proven redundant.  Straight-line code in blocks of eight steps (the loop body has to
+      // stay inside the ~6 KB L0 instruction cache: a single warp cannot hide instruction fetches);
+      // U, the step within the block, is a literal, so every shared-memory address is a register
+      // plus an immediate.  RING: join/clear ring entries.
+#define ZB_DP_FAST_STEP(U, RING)                                                                            \
+      {                                                                                                     \
+        const double tv2_ = lds_f64(t0_s + ds2 * 512 - (((U) + 2) * 8));                                    \
+        const uint32_t ds3_ = lds_u8(dsx_s + (((U) + 3) * 32));                                             \
+        const double llb2_ = lds_f64(gl_s + (((U) + 2) * 8));                                               \
+        double en_c_; uint32_t en_l_;                                                                       \
+        lds_ring(xch_r + ((((U) + 3) & 3) * 16), en_c_, en_l_);   /* pending(j+2), made at step j-1 */       \
+        double inc_ = kInfD; uint32_t inl_ = 0;                                                             \
+        if (RING) { lds_ring(ring_s + (U) * 16, inc_, inl_); sts_f64_if(ring_s + (U) * 16, kInfD, is_l0); } \
+        sts_u16_if(lac_s + (U) * 2, lfin_prev, is_l0);                                                      \
+        const double lit_ = llb + cj;                                                                       \
+        double rl_ = round_to_f32(lit_);   /* rounded unconditionally, in parallel with the compare */     \
+        asm volatile("" : "+d"(rl_));                                                                       \
+        const bool take_ = lit_ < e2c;                                                                      \
+        const double cnext_ = take_ ? rl_ : e2c;                                                            \
+        lfin_prev = take_ ? kCodeLit : e2l;                                                                 \
+        const double nc_ = tv + cj;                                                                         \
+        double rn_ = round_to_f32(nc_);                                                                     \
+        asm volatile("" : "+d"(rn_));                                                                       \
+        const bool ok_ = nc_ < w;                                                                           \
+        w = ok_ ? rn_ : w;                                                                                  \
+        wl = ok_ ? sidx : wl;                                                                               \
+        const bool mine_ = lane_rot == (uint32_t)(U);   /* this lane's target is j+3: complete now */       \
+        sts_ring_if(xch_r + (((U) & 3) * 16), w, wl, mine_);                                                \
+        if (mine_) { w = inc_; wl = inl_; }                                                                 \
+        sidx++;                                                                                             \
+        e2c = en_c_; e2l = en_l_;                                                                           \
+        cj = cnext_;                                                                                        \
+        tv = tv1; tv1 = tv2_; ds2 = ds3_; llb = llb1; llb1 = llb2_;                                         \
+      }
+#define ZB_DP_FAST_8(R) ZB_DP_FAST_STEP(0, R) ZB_DP_FAST_STEP(1, R) ZB_DP_FAST_STEP(2, R) ZB_DP_FAST_STEP(3, R) \
+                        ZB_DP_FAST_STEP(4, R) ZB_DP_FAST_STEP(5, R) ZB_DP_FAST_STEP(6, R) ZB_DP_FAST_STEP(7, R)
+#define ZB_DP_FAST_GROUP(R)                                                                                 \
+      {                                                                                                     \
+        uint32_t t0_s = t0_l, dsx_s = dsx_c, gl_s = gl_c, lac_s = lac_c, ring_s = ring_c;                   \
+        uint32_t lane_rot = (lane - 3u) & 31u, sidx = 3u;   /* sidx = (step & 31) + 3: shuffle source and length code */ \
+        _Pragma("unroll 1")                                                                                 \
+        for (int sb_ = 0; sb_ < 4; sb_++) {                                                                 \
+          ZB_DP_FAST_8(R)                                                                                   \
+          t0_s -= 64; dsx_s += 256; gl_s += 64; lac_s += 16; ring_s += 128;                                 \
+          lane_rot = (lane_rot - 8u) & 31u;                                                                 \
+        }                                                                                                   \
       }
 
       for (uint32_t g = 0; g < ngroups; g++) {
-        const uint32_t j0 = g * 32;
-        // ---- group start (uniform): flush the previous group's lengths, rotate, look ahead ----
-        if (g > 0) {
-          la[j0 - 32 + lane] = (uint16_t)mylen;
-          mk_cur = mk_next; flag_cur = flag_next;
-        }
-        if (g + 1 < ngroups) {
-          acquire(g + 1, seq_base + g + 1);
-          if (lane == 0 && g + 3 < ngroups) issue_group(g + 3, seq_base + g + 3);
-        } else {
-          flag_next = 0; mk_next = 0;
-        }
-        const bool fast = skip_noop && flag_cur == 0 && skip_left == 0 && !just_finished && j0 + 35 > dirty_until && j0 + 32 <= nb;
+        const uint32_t j0 = g * 32, q = seq_base + g, st = q & 3u, stn = (q + 1) & 3u;
+        if (g + 1 < ngroups) mbar_wait(&s.full[stn], ((q + 1) >> 2) & 1u);  // the operand pipeline runs into the next group
+        const uint32_t flag_cur = s.u.dp.flag[st];
+        const uint32_t dsx_c = dsx_r + st * 1024, gl_c = gl_r + st * 256;
+        const uint32_t lac_c = lac_r + st * 64;
+        const uint32_t ring_c = ring_r + ((j0 + 32) & 511u) * 16;  // slot of target j0 + 35
+        const bool fast = skip_noop && flag_cur == 0 && skip_left == 0 && !just_finished && j0 + 32 <= nb;
         if (fast) {
-#pragma unroll 4
-          for (uint32_t jl = 0; jl < 32; jl++) ZB_DP_FAST_STEP(j0 + jl)
-          continue;
-        }
-        // ---- general group: per-step checks ----
-        const uint32_t jend = j0 + 32 < nb ? j0 + 32 : nb;
-        for (uint32_t j = j0; j < jend; j++) {
-          const uint32_t jl = j & 31;
-          const uint32_t c1 = (col - 1u) & 31u, c2 = (col - 2u) & 31u;
-          const double tv_n = lds_f64(t0_r + ds_n * 256 + c1 * 8);
-          const uint32_t ds_nn = min(lds_u8(dsx_r + ((j + 2 + joff) & 127) * 32 + c2), kNoEdge);
-          const double llb_n = lds_f64(gl_r + ((j + 1) & 63) * 8);
-          if (lane == jl) mylen = lfin_prev;
-          const uint32_t m16 = __shfl_sync(full, mk_cur, jl);
-          const uint32_t ml = m16 & 0x7fffu;
-          double cnext;
-          bool relax = true;
-          // long-run shortcut squeeze.c:251-271 (candidate flag precomputed by k_match)
-          if ((m16 & kShortcutFlag) && skip_left == 0 && !just_finished) skip_left = kMaxMatch;
-          if (skip_left > 0) {
-            // costs[j+258] = costs[j] + cost(258,1), unconditionally; no literal, no other edge
-            sts_ring_if(ring_r + ((j + kMaxMatch) & 511) * 16, round_to_f32(cj + cost258), (uint32_t)kMaxMatch, lane == 0);
-            if (j + kMaxMatch > dirty_until) dirty_until = j + kMaxMatch;
-            skip_left--;
-            just_finished = skip_left == 0;
-            relax = false;
-          } else {
-            just_finished = false;
-          }
-          if (relax) {
-            // literal squeeze.c:277-284 (every lane computes the same values)
-            const double lit = llb + cj;
-            const bool take = lit < e2c;
-            cnext = take ? round_to_f32(lit) : e2c;
-            lfin_prev = take ? 1u : e2l;
-            // lengths 3..34 squeeze.c:286-302: this lane's length is 3 + col
-            const double nc = tv + cj;
-            const double mc = mincost + cj;
-            const bool ok = !(w <= mc) & (nc < w);
-            w = ok ? round_to_f32(nc) : w;
-            wl = ok ? col + 3u : wl;
-            if (ml > 34u) {  // longer lengths: run-list lookup, pushed into the ring
-              const uint32_t room = nb - j;
-              const uint32_t kend = ml < room ? ml : room;
-              const uint4* st4 = (const uint4*)&s.u.dp.runs[((j >> 5) + seq_base) & 3][jl * kRunSlots];
-              const uint4 ea = st4[0], eb = st4[1];
-              const bool ovf = (eb.w & kOverflowBit) != 0;
-              for (uint32_t k = 35 + lane; k <= kend; k += 32) {
-                uint32_t e = eb.w;
-                if (ovf) {
-                  e = 0;
-                  if (k > run_len(eb.z)) {
-                    uint32_t off = eb.w & ~kOverflowBit, cnt = b.ovf[off];
-                    for (uint32_t r = 0; r < cnt; r++) { uint32_t x = b.ovf[off + 1 + r]; if (run_len(x) >= k) { e = x; break; } }
-                  }
-                }
-                if (k <= run_len(eb.z)) e = eb.z;
-                if (k <= run_len(eb.y)) e = eb.y;
-                if (k <= run_len(eb.x)) e = eb.x;
-                if (k <= run_len(ea.w)) e = ea.w;
-                if (k <= run_len(ea.z)) e = ea.z;
-                if (k <= run_len(ea.y)) e = ea.y;
-                if (k <= run_len(ea.x)) e = ea.x;
-                const uint32_t tga = ring_r + ((j + k) & 511) * 16;
-                const double pend = lds_f64(tga);
-                if (pend <= mc) continue;  // squeeze.c:293
-                const int dsym = (int)run_dsym(e);
-                double nc2 = (double)(length_extra_bits((int)k) + dist_symbol_extra_bits(dsym)) + s.lencost[k] + s.dcost[dsym];
-                nc2 = nc2 + cj;
-                sts_ring_if(tga, round_to_f32(nc2), k, nc2 < pend);
-              }
-              if (j + kend > dirty_until) dirty_until = j + kend;
+          if (j0 + 35 > dirty_until) ZB_DP_FAST_GROUP(false)
+          else ZB_DP_FAST_GROUP(true)
+        } else {
+          // ---- general group: per-step checks ----
+          const uint32_t jend = j0 + 32 < nb ? j0 + 32 : nb;
+          for (uint32_t j = j0; j < jend; j++) {
+            const uint32_t jl = j & 31u;
+            const double tv2 = lds_f64(t0_l + ds2 * 512 - (jl + 2) * 8);
+            const uint32_t ds3 = lds_u8(dsx_c + (jl + 3) * 32);   // rows 32.. are the next stage (or its mirror)
+            const double llb2 = lds_f64(gl_c + (jl + 2) * 8);
+            double en_c; uint32_t en_l;
+            lds_ring(xch_r + ((j + 3) & 3) * 16, en_c, en_l);  // pending(j+2), made at step j-1
+            sts_u16_if(lac_c + jl * 2, lfin_prev, is_l0);
+            const uint32_t m16 = lds_u16(mk_r + st * 64 + jl * 2);
+            const uint32_t ml = m16 & 0x7fffu;
+            double cnext;
+            bool relax = true;
+            // long-run shortcut squeeze.c:251-271 (candidate flag precomputed by k_match)
+            if ((m16 & kShortcutFlag) && skip_left == 0 && !just_finished) skip_left = kMaxMatch;
+            if (skip_left > 0) {
+              // costs[j+258] = costs[j] + cost(258,1), unconditionally; no literal, no other edge
+              sts_ring_if(ring_r + ((j + kMaxMatch - 3) & 511) * 16, round_to_f32(cj + cost258), kCodeLong | (uint32_t)kMaxMatch, lane == 0);
+              if (j + kMaxMatch > dirty_until) dirty_until = j + kMaxMatch;
+              skip_left--;
+              just_finished = skip_left == 0;
+              relax = false;
+            } else {
+              just_finished = false;
             }
-          } else {
-            cnext = e2c;  // a skipped source contributes no literal edge
-            lfin_prev = e2l;
-          }
-          // target j+3 is complete for every length edge: hand it to the chain; its lane takes
-          // on target j+35, whose ring entry (edges longer than 34) is complete as well
-          const uint32_t src = (j + 3) & 31;
-          const double xc = __shfl_sync(full, w, src);
-          const uint32_t xl = __shfl_sync(full, wl, src);
-          double inc = kInfD; uint32_t inl = 0;
-          __syncwarp();
-          if (j + 35 <= dirty_until) {
-            const uint32_t ra = ring_r + ((j + 35) & 511) * 16;
-            inc = lds_f64(ra);
-            inl = lds_u32(ra + 8);
-            sts_f64_if(ra, kInfD, lane == 0);  // free the slot for target j+35+512
+            if (relax) {
+              // literal squeeze.c:277-284 (every lane computes the same values)
+              const double lit = llb + cj;
+              const bool take = lit < e2c;
+              cnext = take ? round_to_f32(lit) : e2c;
+              lfin_prev = take ? kCodeLit : e2l;
+              // lengths 3..34 squeeze.c:286-302: this lane's length is target - j
+              const double nc = tv + cj;
+              const double mc = mincost + cj;
+              const bool ok = !(w <= mc) & (nc < w);
+              w = ok ? round_to_f32(nc) : w;
+              wl = ok ? jl + 3u : wl;
+              if (ml > 34u) {  // longer lengths: run-list lookup, pushed into the ring
+                const uint32_t room = nb - j;
+                const uint32_t kend = ml < room ? ml : room;
+                const uint4* st4 = (const uint4*)&s.u.dp.runs[st][jl * kRunSlots];
+                const uint4 ea = st4[0], eb = st4[1];
+                const bool ovf = (eb.w & kOverflowBit) != 0;
+                for (uint32_t k = 35 + lane; k <= kend; k += 32) {
+                  uint32_t e = eb.w;
+                  if (ovf) {
+                    e = 0;
+                    if (k > run_len(eb.z)) {
+                      uint32_t off = eb.w & ~kOverflowBit, cnt = b.ovf[off];
+                      for (uint32_t r = 0; r < cnt; r++) { uint32_t x = b.ovf[off + 1 + r]; if (run_len(x) >= k) { e = x; break; } }
+                    }
+                  }
+                  if (k <= run_len(eb.z)) e = eb.z;
+                  if (k <= run_len(eb.y)) e = eb.y;
+                  if (k <= run_len(eb.x)) e = eb.x;
+                  if (k <= run_len(ea.w)) e = ea.w;
+                  if (k <= run_len(ea.z)) e = ea.z;
+                  if (k <= run_len(ea.y)) e = ea.y;
+                  if (k <= run_len(ea.x)) e = ea.x;
+                  const uint32_t tga = ring_r + ((j + k - 3) & 511) * 16;
+                  const double pend = lds_f64(tga);
+                  if (pend <= mc) continue;  // squeeze.c:293
+                  const int dsym = (int)run_dsym(e);
+                  double nc2 = (double)(length_extra_bits((int)k) + dist_symbol_extra_bits(dsym)) + s.lencost[k] + s.dcost[dsym];
+                  nc2 = nc2 + cj;
+                  sts_ring_if(tga, round_to_f32(nc2), kCodeLong | k, nc2 < pend);
+                }
+                if (j + kend > dirty_until) dirty_until = j + kend;
+              }
+            } else {
+              cnext = e2c;  // a skipped source contributes no literal edge
+              lfin_prev = e2l;
+            }
+            // target j+3 is complete for every length edge: hand it to the chain; its lane takes
+            // on target j+35, whose ring entry (edges longer than 34) is complete as well
+            const uint32_t src = (j + 3) & 31;
+            sts_ring_if(xch_r + (j & 3) * 16, w, wl, lane == src);
+            double inc = kInfD; uint32_t inl = 0;
             __syncwarp();
+            if (j + 35 <= dirty_until) {
+              const uint32_t ra = ring_r + ((j + 32) & 511) * 16;
+              lds_ring(ra, inc, inl);
+              sts_f64_if(ra, kInfD, lane == 0);  // free the slot for target j+35+512
+              __syncwarp();
+            }
+            if (lane == src) { w = inc; wl = inl; }
+            e2c = en_c; e2l = en_l;
+            cj = cnext;
+            tv = tv1; tv1 = tv2; ds2 = ds3; llb = llb1; llb1 = llb2;
           }
-          if (col == 0) { w = inc; wl = inl; }
-          e2c = e1c; e2l = e1l; e1c = xc; e1l = xl;
-          cj = cnext;
-          tv = tv_n; ds_n = ds_nn; llb = llb_n; col = c1;
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.empty[st]);  // the feeder may write back lac[st] and refill the stage
       }
+#undef ZB_DP_FAST_GROUP
+#undef ZB_DP_FAST_8
 #undef ZB_DP_FAST_STEP
-      // length_array of the last group (positions 32*(ngroups-1) ..) and of position nb
-      {
-        const uint32_t jb = (ngroups - 1) * 32;
-        if (jb + lane < nb) la[jb + lane] = (uint16_t)mylen;
-        if (lane == 0) la[nb] = (uint16_t)lfin_prev;
-      }
-      __syncwarp();
+      if (lane == 0) la[nb] = (uint16_t)decode_len(lfin_prev, nb);
       seq_base += ngroups;
     }
+    cta_sync64();  // (B) the feeder has written length_array[0 .. nb)
 
     ZB_TICK(1);
     // ------------------------------------------------------------------ trace back
@@ -850,6 +930,9 @@ __global__ void __launch_bounds__(32) k_iterate(Batch b, const uint32_t* __restr
     ZB_TICK(5);
   }
 
+  if (lane == 0) s.go = 0;
+  __syncwarp();
+  cta_sync64();  // (A) releases the feeder warp for good
   if (lane == 0) {
     for (int i = 0; i < 6; i++) js->cyc[i] = (uint64_t)cyc[i];
     js->best_size = best_size;

@@ -84,7 +84,7 @@ struct Batch {
   uint16_t* mlen;   // [npos] longest length or 0 (optimal segments only); bit 15 = long-run
                     // shortcut candidate (squeeze.c:251-257 condition, a pure function of position)
   uint32_t* runs;   // [npos][kRunSlots]
-  uint8_t* dsx;     // [npos][32] distance symbol of the shortest-distance match of length 3+l, or
+  uint8_t* dsx;     // [npos][32] (row j rotated left by j+3) distance symbol of the shortest-distance match of length 3+l, or
                     // kNoEdge if 3+l exceeds the longest match / the block end (the DP's 32-wide
                     // register window works on these)
   uint32_t* ovf;    // overflow arena: [count, entries...]
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
         if (nruns && k <= best) {  // best <= inend - pos, so edges never leave the block
           for (uint32_t r = 0; r < nruns; r++) { uint32_t e = myruns[r]; if (run_len(e) >= k) { v = run_dsym(e); break; } }
         }
-        b.dsx[o * 32 + lane] = (uint8_t)v;
+        b.dsx[o * 32 + ((lane + j + 3u) & 31u)] = (uint8_t)v;  // rotated: k_iterate's lane t reads byte t of row j
       }
       uint32_t* dst = b.runs + o * kRunSlots;
       if (nruns <= (uint32_t)kRunSlots) {
