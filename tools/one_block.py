@@ -8,7 +8,7 @@ from zopfli_b200 import corpus
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 its = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 data = corpus.synth_text(n, 5)
-lib = zb.Library()
+lib = zb.Library(os.environ["ZB_LIB"]) if os.environ.get("ZB_LIB") else zb.Library()
 t = time.time()
 out = lib.compress(data, zb.ZOPFLI_FORMAT_DEFLATE, numiterations=its, blocksplitting=0)
 print("one block: %d -> %d bytes, %.3fs" % (n, len(out), time.time() - t))

@@ -573,7 +573,6 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
     __syncwarp();
     cta_sync64();  // (A) start the feeder
     {
-      const uint32_t full = 0xffffffffu;
       // shared-memory base addresses, kept opaque so they stay in registers
       // this lane's cost-table column at step jl' of a group is t0_l - 8 jl' for jl' in [2, 33] (32, 33: steps 0, 1 of the next group)
       uint32_t t0_l = smem_u32(&s.t0[0]) + (((lane - 3u) & 31u) + 33u) * 8u;
