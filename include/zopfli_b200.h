@@ -99,6 +99,7 @@ typedef struct ZopfliB200Stats {
   uint64_t launches, match_positions, iterate_positions, iterate_steps, h2d_bytes, d2h_bytes;
   uint64_t cyc_sum[6], cyc_max[6], max_block_positions; /* k_iterate phase cycles, see engine.hpp */
   double ms_split; uint64_t split_evals, split_rounds;  /* device split-cost service */
+  uint64_t iterate_launches;                             /* k_iterate launches (ms_iterate is the sum of their durations) */
 } ZopfliB200Stats;
 void ZopfliB200GetStats(ZopfliB200Stats* out);
 void ZopfliB200ResetStats(void);

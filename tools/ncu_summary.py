@@ -22,7 +22,7 @@ with open(out, "w") as f:
             f.write("%s = %s %s\n" % (h, v, u))
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(io.StringIO(src)))
-    h2, data = r[1], r[2:]
+    h2, data = r[1], [x for x in r[2:] if len(x) == len(r[1])]
     isrc, isamp, iex = h2.index("Source"), h2.index("# Samples"), h2.index("Instructions Executed")
     tot = sum(int(x[isamp]) for x in data)
     f.write("\n# hottest SASS instructions (stall samples, share of %d, times executed)\n" % tot)

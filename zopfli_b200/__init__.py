@@ -36,7 +36,8 @@ class Stats(C.Structure):
                [(n, C.c_uint64) for n in ("launches", "match_positions", "iterate_positions",
                                           "iterate_steps", "h2d_bytes", "d2h_bytes")] + \
                [("cyc_sum", C.c_uint64 * 6), ("cyc_max", C.c_uint64 * 6), ("max_block_positions", C.c_uint64),
-                ("ms_split", C.c_double), ("split_evals", C.c_uint64), ("split_rounds", C.c_uint64)]
+                ("ms_split", C.c_double), ("split_evals", C.c_uint64), ("split_rounds", C.c_uint64),
+                ("iterate_launches", C.c_uint64)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n.startswith("cyc_") else getattr(self, n)) for n, _ in self._fields_}

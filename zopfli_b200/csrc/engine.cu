@@ -362,6 +362,7 @@ EngineStats Engine::stats() {
     r.ms_keys += a.ms_keys; r.ms_scan += a.ms_scan; r.ms_scatter += a.ms_scatter; r.ms_match += a.ms_match;
     r.ms_greedy += a.ms_greedy; r.ms_iterate += a.ms_iterate; r.ms_pack += a.ms_pack; r.ms_d2h += a.ms_d2h;
     r.ms_split += a.ms_split; r.split_evals += a.split_evals; r.split_rounds += a.split_rounds;
+    r.iterate_launches += a.iterate_launches;
     r.launches += a.launches; r.match_positions += a.match_positions; r.iterate_positions += a.iterate_positions;
     r.iterate_steps += a.iterate_steps; r.h2d_bytes += a.h2d_bytes; r.d2h_bytes += a.d2h_bytes;
     uint64_t ta = 0, tr = 0;
@@ -442,6 +443,7 @@ void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out, int 
       CK(cudaGetLastError());
       l.toc(l.acc.ms_iterate);
       l.acc.launches++;
+      l.acc.iterate_launches++;
     }
     l.tic();
     k_pack<<<(unsigned)ns, 256, 0, l.stream>>>(b, L.any_parse ? 0 : 1);

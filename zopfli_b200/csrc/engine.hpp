@@ -22,7 +22,7 @@ struct ParseResult {        // symbols of range i: [off[i], off[i]+size[i]) in l
 
 struct EngineStats {  // accumulated since the last reset; times from CUDA events on the engine stream
   double ms_same, ms_keys, ms_scan, ms_scatter, ms_match, ms_greedy, ms_iterate, ms_pack, ms_h2d, ms_d2h, ms_split;
-  uint64_t split_evals, split_rounds;
+  uint64_t split_evals, split_rounds, iterate_launches;
   uint64_t launches;
   uint64_t match_positions, iterate_positions, iterate_steps;  // steps = positions x iterations
   uint64_t h2d_bytes, d2h_bytes;

@@ -64,7 +64,7 @@ struct IterSmem {
   union __align__(16) {
     DpStage dp;
     CostStage cs;
-    uint16_t win[8192];    // trace-back window
+    struct { uint16_t la[4096]; uint16_t mark[4096]; } tr;  // trace-back window: length_array slice + visit marks
   } u;
   __align__(8) uint64_t full[4];   // stage filled (TMA bytes + feeder scalars)
   __align__(8) uint64_t empty[4];  // stage consumed by the DP warp
@@ -538,19 +538,28 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
     // Check it for all 256 x 30 (length, distance symbol) pairs; if it ever fails, the fast path
     // is disabled for this iteration and every edge goes through the explicit test.
     bool skip_noop;
+    double margin_dn, margin_up;  // how far the cost can move below / above its value at a group start (see "magic" below)
     {
-      double mn = 1e300;
+      double mn = 1e300, mx = 0.0, ml = 0.0;
       for (int k = 3 + (int)lane; k < 259; k += 32) {
         const int lb = length_extra_bits(k);
         const double lc = s.lencost[k];
         for (int ds = 0; ds < 30; ds++) {
           const double c = (double)(lb + dist_symbol_extra_bits(ds)) + lc + s.dcost[ds];
           mn = c < mn ? c : mn;
+          mx = c > mx ? c : mx;
         }
       }
+      for (int i = lane; i < 256; i += 32) ml = s.llcost[i] > ml ? s.llcost[i] : ml;
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) { const double o = __shfl_xor_sync(0xffffffffu, mn, d); mn = o < mn ? o : mn; }
+      for (int d = 16; d > 0; d >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, mn, d); mn = o < mn ? o : mn;
+        const double p = __shfl_xor_sync(0xffffffffu, mx, d); mx = p > mx ? p : mx;
+        const double q = __shfl_xor_sync(0xffffffffu, ml, d); ml = q > ml ? q : ml;
+      }
       skip_noop = mincost <= mn;
+      margin_dn = 258.0 * ml + 1.0;
+      margin_up = 32.0 * ml + mx + 1.0;
     }
     const double cost258 = (double)(0 + 0) + s.lencost[258] + s.dcost[0];  // costmodel(258, 1)
     ZB_TICK(0);
@@ -587,7 +596,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
       double cj = 0.0;
       uint32_t lfin_prev = 0;           // code of length_array[j], stored one step late
       uint32_t dirty_until = 0;         // largest target that has a ring entry
-      uint32_t skip_left = 0;
+      uint32_t skip_left = 0, guard_until = 0;
       bool just_finished = false;
       // operand pipeline, two steps deep so that no shared-memory latency meets the cost chain:
       // tv / tv1 = edge costs for steps j, j+1; ds2 = distance symbol for step j+2; llb / llb1 = literal costs
@@ -608,7 +617,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
       // stay inside the ~6 KB L0 instruction cache: a single warp cannot hide instruction fetches);
       // U, the step within the block, is a literal, so every shared-memory address is a register
       // plus an immediate.  RING: join/clear ring entries.
-#define ZB_DP_FAST_STEP(U, RING)                                                                            \
+#define ZB_DP_FAST_STEP(U, RING, MAGIC)                                                                          \
       {                                                                                                     \
         const double tv2_ = lds_f64(t0_s + ds2 * 512 - (((U) + 2) * 8));                                    \
         const uint32_t ds3_ = lds_u8(dsx_s + (((U) + 3) * 32));                                             \
@@ -619,13 +628,13 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         if (RING) { lds_ring(ring_s + (U) * 16, inc_, inl_); sts_f64_if(ring_s + (U) * 16, kInfD, is_l0); } \
         sts_u16_if(lac_s + (U) * 2, lfin_prev, is_l0);                                                      \
         const double lit_ = llb + cj;                                                                       \
-        double rl_ = round_to_f32(lit_);   /* rounded unconditionally, in parallel with the compare */     \
+        double rl_ = (MAGIC) ? (lit_ + Cm) - Cm : round_to_f32(lit_);   /* unconditional: runs beside the compare */ \
         asm volatile("" : "+d"(rl_));                                                                       \
         const bool take_ = lit_ < e2c;                                                                      \
         const double cnext_ = take_ ? rl_ : e2c;                                                            \
         lfin_prev = take_ ? kCodeLit : e2l;                                                                 \
         const double nc_ = tv + cj;                                                                         \
-        double rn_ = round_to_f32(nc_);                                                                     \
+        double rn_ = (MAGIC) ? (nc_ + Cm) - Cm : round_to_f32(nc_);                                         \
         asm volatile("" : "+d"(rn_));                                                                       \
         const bool ok_ = nc_ < w;                                                                           \
         w = ok_ ? rn_ : w;                                                                                  \
@@ -638,15 +647,15 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         cj = cnext_;                                                                                        \
         tv = tv1; tv1 = tv2_; ds2 = ds3_; llb = llb1; llb1 = llb2_;                                         \
       }
-#define ZB_DP_FAST_8(R) ZB_DP_FAST_STEP(0, R) ZB_DP_FAST_STEP(1, R) ZB_DP_FAST_STEP(2, R) ZB_DP_FAST_STEP(3, R) \
-                        ZB_DP_FAST_STEP(4, R) ZB_DP_FAST_STEP(5, R) ZB_DP_FAST_STEP(6, R) ZB_DP_FAST_STEP(7, R)
-#define ZB_DP_FAST_GROUP(R)                                                                                 \
+#define ZB_DP_FAST_8(R, M) ZB_DP_FAST_STEP(0, R, M) ZB_DP_FAST_STEP(1, R, M) ZB_DP_FAST_STEP(2, R, M) ZB_DP_FAST_STEP(3, R, M) \
+                           ZB_DP_FAST_STEP(4, R, M) ZB_DP_FAST_STEP(5, R, M) ZB_DP_FAST_STEP(6, R, M) ZB_DP_FAST_STEP(7, R, M)
+#define ZB_DP_FAST_GROUP(R, M)                                                                               \
       {                                                                                                     \
         uint32_t t0_s = t0_l, dsx_s = dsx_c, gl_s = gl_c, lac_s = lac_c, ring_s = ring_c;                   \
         uint32_t lane_rot = (lane - 3u) & 31u, sidx = 3u;   /* sidx = (step & 31) + 3: shuffle source and length code */ \
         _Pragma("unroll 1")                                                                                 \
         for (int sb_ = 0; sb_ < 4; sb_++) {                                                                 \
-          ZB_DP_FAST_8(R)                                                                                   \
+          ZB_DP_FAST_8(R, M)                                                                                \
           t0_s -= 64; dsx_s += 256; gl_s += 64; lac_s += 16; ring_s += 128;                                 \
           lane_rot = (lane_rot - 8u) & 31u;                                                                 \
         }                                                                                                   \
@@ -661,8 +670,26 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         const uint32_t ring_c = ring_r + ((j0 + 32) & 511u) * 16;  // slot of target j0 + 35
         const bool fast = skip_noop && flag_cur == 0 && skip_left == 0 && !just_finished && j0 + 32 <= nb;
         if (fast) {
-          if (j0 + 35 > dirty_until) ZB_DP_FAST_GROUP(false)
-          else ZB_DP_FAST_GROUP(true)
+          // "magic" rounding: while every cost of the group provably stays inside one binade
+          // [2^k, 2^(k+1)), round-to-float is (x + C) - C with C = 1.5 * 2^(k+29) (the double grid at
+          // C is the float grid of the binade, ties to even alike) -- two DADDs instead of five
+          // dependent integer operations on the cost chain.  Costs are shortest-path distances with
+          // a literal edge at every position, so within the group they stay above
+          // c - 258 maxlit and below c + 32 maxlit (+ the largest edge for relaxed values);
+          // positions after a long-run shortcut (no literal edges there) are excluded.
+          double Cm = 0.0;
+          bool magic = false;
+          if (j0 + 35 > dirty_until && j0 >= guard_until) {
+            const long long lowb = __double_as_longlong(cj) & 0x7ff0000000000000LL;
+            const double lowd = __longlong_as_double(lowb), highd = __longlong_as_double(lowb + 0x0010000000000000LL);
+            if (lowb > 0 && cj - margin_dn >= lowd && cj + margin_up < highd) {
+              magic = true;
+              Cm = __longlong_as_double(lowb + (29LL << 52) + (1LL << 51));
+            }
+          }
+          if (magic) ZB_DP_FAST_GROUP(false, true)
+          else if (j0 + 35 > dirty_until) ZB_DP_FAST_GROUP(false, false)
+          else ZB_DP_FAST_GROUP(true, false)
         } else {
           // ---- general group: per-step checks ----
           const uint32_t jend = j0 + 32 < nb ? j0 + 32 : nb;
@@ -685,6 +712,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
               sts_ring_if(ring_r + ((j + kMaxMatch - 3) & 511) * 16, round_to_f32(cj + cost258), kCodeLong | (uint32_t)kMaxMatch, lane == 0);
               if (j + kMaxMatch > dirty_until) dirty_until = j + kMaxMatch;
               skip_left--;
+              guard_until = j + 600;
               just_finished = skip_left == 0;
               relax = false;
             } else {
@@ -769,48 +797,95 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
 
     ZB_TICK(1);
     // ------------------------------------------------------------------ trace back
-    // lane 0 chases length_array backwards inside shared-memory windows that the whole warp
-    // refills with 4-byte loads; each symbol is emitted as (start position << 9 | length)
-    uint32_t cursor = nb + 1;  // psym[cursor .. nb+1) holds the symbols in order
+    // TraceBackwards (squeeze.c:317-336) is a pointer chase i -> i - length_array[i].  Per window of
+    // 4096 positions (in shared memory) it is run SPECULATIVELY from 32 starting points at once:
+    // lane s chases from the top of its 128-position segment and numbers the nodes it visits.  The
+    // true path enters a segment within 258 positions of its top; chains from nearby starts merge
+    // after a few hops, so lane 0 then only stitches: follow the true path inside a segment until it
+    // hits a numbered node (or leaves the segment), adopt the speculative chain from there on.  A
+    // third pass re-walks the chains 32 wide and writes the adopted nodes.  Each symbol is emitted
+    // as (start position << 9 | length); psym[cursor .. nb+1) holds the symbols in order.
+    uint32_t cursor = nb + 1;
     {
-      uint32_t idx = nb;
-      const uint32_t win_a = smem_u32(&s.u.win[0]);
+      uint32_t idx = nb;  // current true path node
+      const uint32_t la_a = smem_u32(&s.u.tr.la[0]), mk_a = smem_u32(&s.u.tr.mark[0]);
       const bool la_odd = (((uintptr_t)la) >> 1) & 1;  // make 4-byte loads aligned
+      constexpr uint32_t kSegLen = 128;
       while (idx > 0) {
         // window covers la[wlo .. idx], wlo chosen so that &la[wlo] is 4-byte aligned
-        uint32_t wlo = idx >= 8184u ? idx - 8183u : 0u;
+        uint32_t wlo = idx >= 4088u ? idx - 4087u : 0u;
         if (((wlo & 1u) != 0) != la_odd) wlo = wlo > 0 ? wlo - 1 : 0;  // align (or start at 0)
         const uint32_t cnt = idx - wlo + 1;
         if ((((uintptr_t)(la + wlo)) & 3) == 0) {
           const uint32_t* src = (const uint32_t*)(la + wlo);
-          uint32_t* dst = (uint32_t*)&s.u.win[0];
+          uint32_t* dst = (uint32_t*)&s.u.tr.la[0];
           for (uint32_t t = lane; t < (cnt + 1) / 2; t += 32) dst[t] = src[t];
         } else {
-          for (uint32_t t = lane; t < cnt; t += 32) s.u.win[t] = la[wlo + t];
+          for (uint32_t t = lane; t < cnt; t += 32) s.u.tr.la[t] = la[wlo + t];
+        }
+        for (uint32_t t = lane; t < 2048; t += 32) ((uint32_t*)&s.u.tr.mark[0])[t] = 0;
+        __syncwarp();
+        // one hop: length clamped to [1, i] so a corrupted chain cannot hang
+#define ZB_HOP(i_, l_) { asm volatile("ld.shared.u16 %0, [%1];" : "=r"(l_) : "r"(la_a + ((i_) - wlo) * 2)); l_ = max(l_, 1u); l_ = min(l_, (i_)); }
+        // ---- pass 1: speculative chains.  Segment s = positions (lo, hi], hi = idx - 128 s ----
+        const uint32_t hi = idx >= lane * kSegLen ? idx - lane * kSegLen : 0u;
+        const uint32_t lo = hi >= kSegLen ? hi - kSegLen : 0u;          // exclusive
+        const uint32_t floor_ = lo > wlo ? lo : (wlo > 0 ? wlo - 1 : 0u);  // stop below the window as well
+        uint32_t exit_s = hi, cnt_s = 0;
+        if (hi > 0 && hi >= wlo) {
+          uint32_t i = hi;
+          while (i > floor_) {
+            uint32_t l;
+            cnt_s++;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(mk_a + (i - wlo) * 2), "h"((unsigned short)cnt_s) : "memory");
+            ZB_HOP(i, l)
+            i -= l;
+          }
+          exit_s = i;
         }
         __syncwarp();
-        if (lane == 0) {
-          uint32_t i = idx;
-          // one step of the chase; lengths are clamped to [1, i] so a corrupted chain cannot hang
-#define ZB_TRACE_STEP()                                                                     \
-          {                                                                                 \
-            uint32_t l_;                                                                    \
-            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(l_) : "r"(win_a + (i - wlo) * 2)); \
-            l_ = max(l_, 1u);                                                               \
-            l_ = min(l_, i);                                                                \
-            i -= l_;                                                                        \
-            psym[--cursor] = (i << 9) | l_;                                                 \
+        // ---- pass 2: stitch (segment by segment; the few sequential hops run on every lane alike) ----
+        uint32_t e = idx;         // true node entering the current segment
+        uint32_t my_from = 0xffffffffu, my_base = 0;  // this lane's chain is adopted from node number my_from on
+        for (uint32_t sg = 0; sg < 32; sg++) {
+          const uint32_t shi = idx >= sg * kSegLen ? idx - sg * kSegLen : 0u;
+          if (shi == 0 || shi < wlo || e == 0 || e < wlo) break;
+          const uint32_t slo = shi >= kSegLen ? shi - kSegLen : 0u;
+          const uint32_t sfl = slo > wlo ? slo : (wlo > 0 ? wlo - 1 : 0u);
+          const uint32_t s_exit = __shfl_sync(0xffffffffu, exit_s, sg), s_cnt = __shfl_sync(0xffffffffu, cnt_s, sg);
+          if (e <= sfl) continue;  // the path jumps over this segment
+          uint32_t i = e, from = 0;
+          while (i > sfl) {
+            uint32_t mk;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(mk) : "r"(mk_a + (i - wlo) * 2));
+            if (mk) { from = mk; break; }
+            uint32_t l;
+            ZB_HOP(i, l)
+            i -= l;
+            --cursor;
+            if (lane == 0) psym[cursor] = (i << 9) | l;
           }
-          while (i >= wlo + 4 * 258) {  // four steps cannot leave the window
-            ZB_TRACE_STEP() ZB_TRACE_STEP() ZB_TRACE_STEP() ZB_TRACE_STEP()
+          if (from) {  // merged: nodes from..s_cnt of lane sg's chain are on the path
+            if (lane == sg) { my_from = from; my_base = cursor; }
+            cursor -= s_cnt - from + 1;
+            e = s_exit;
+          } else {
+            e = i;
           }
-          while (i > 0 && i >= wlo) ZB_TRACE_STEP()
-#undef ZB_TRACE_STEP
-          idx = i;
         }
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        cursor = __shfl_sync(0xffffffffu, cursor, 0);
-        flags = __shfl_sync(0xffffffffu, flags, 0);
+        // ---- pass 3: emit the adopted part of every chain ----
+        if (my_from != 0xffffffffu) {
+          uint32_t i = hi, k = 0;
+          while (i > floor_) {
+            uint32_t l;
+            k++;
+            ZB_HOP(i, l)
+            i -= l;
+            if (k >= my_from) psym[my_base - 1 - (k - my_from)] = (i << 9) | l;
+          }
+        }
+#undef ZB_HOP
+        idx = e;
         __syncwarp();
       }
     }
