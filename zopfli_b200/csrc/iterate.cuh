@@ -819,7 +819,14 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         if ((((uintptr_t)(la + wlo)) & 3) == 0) {
           const uint32_t* src = (const uint32_t*)(la + wlo);
           uint32_t* dst = (uint32_t*)&s.u.tr.la[0];
-          for (uint32_t t = lane; t < (cnt + 1) / 2; t += 32) dst[t] = src[t];
+          const uint32_t nw = (cnt + 1) / 2;
+          for (uint32_t tb = 0; tb < nw; tb += 32 * 16) {  // 16 loads in flight per lane
+            uint32_t v[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) { const uint32_t t = tb + u * 32 + lane; v[u] = t < nw ? src[t] : 0u; }
+#pragma unroll
+            for (int u = 0; u < 16; u++) { const uint32_t t = tb + u * 32 + lane; if (t < nw) dst[t] = v[u]; }
+          }
         } else {
           for (uint32_t t = lane; t < cnt; t += 32) s.u.tr.la[t] = la[wlo + t];
         }
