@@ -122,6 +122,18 @@ __device__ __forceinline__ double round_to_f32(double x) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_a) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_a, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(bar_a), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
 __device__ __forceinline__ void cta_sync64() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
   uint32_t v;
@@ -591,8 +603,11 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
       const bool is_l0 = lane == 0;
       double w = kInfD; uint32_t wl = 0;
       double e2c = kInfD; uint32_t e2l = 0;  // pending(j+1)
-      uint32_t xch_r = smem_u32(&s.u.dp.xch[0]);
-      asm volatile("" : "+r"(xch_r));
+      uint32_t xch_r = smem_u32(&s.u.dp.xch[0]), full_r = smem_u32(&s.full[0]), empty_r = smem_u32(&s.empty[0]);
+      uint32_t flag_r = smem_u32(&s.u.dp.flag[0]);
+      asm volatile("" : "+r"(xch_r), "+r"(full_r), "+r"(empty_r), "+r"(flag_r));
+      // magic-rounding state: the constant and the cost interval it is valid for (see below)
+      double Cm = 0.0, mg_lo = 1.0, mg_hi = 0.0;
       double cj = 0.0;
       uint32_t lfin_prev = 0;           // code of length_array[j], stored one step late
       uint32_t dirty_until = 0;         // largest target that has a ring entry
@@ -600,7 +615,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
       bool just_finished = false;
       // operand pipeline, two steps deep so that no shared-memory latency meets the cost chain:
       // tv / tv1 = edge costs for steps j, j+1; ds2 = distance symbol for step j+2; llb / llb1 = literal costs
-      mbar_wait(&s.full[seq_base & 3u], (seq_base >> 2) & 1u);
+      mbar_wait_a(full_r + (seq_base & 3u) * 8, (seq_base >> 2) & 1u);
       double tv, tv1, llb, llb1;
       uint32_t ds2;
       {
@@ -663,8 +678,8 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
 
       for (uint32_t g = 0; g < ngroups; g++) {
         const uint32_t j0 = g * 32, q = seq_base + g, st = q & 3u, stn = (q + 1) & 3u;
-        if (g + 1 < ngroups) mbar_wait(&s.full[stn], ((q + 1) >> 2) & 1u);  // the operand pipeline runs into the next group
-        const uint32_t flag_cur = s.u.dp.flag[st];
+        if (g + 1 < ngroups) mbar_wait_a(full_r + stn * 8, ((q + 1) >> 2) & 1u);  // the operand pipeline runs into the next group
+        const uint32_t flag_cur = lds_u32(flag_r + st * 4);
         const uint32_t dsx_c = dsx_r + st * 1024, gl_c = gl_r + st * 256;
         const uint32_t lac_c = lac_r + st * 64;
         const uint32_t ring_c = ring_r + ((j0 + 32) & 511u) * 16;  // slot of target j0 + 35
@@ -677,23 +692,35 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
           // a literal edge at every position, so within the group they stay above
           // c - 258 maxlit and below c + 32 maxlit (+ the largest edge for relaxed values);
           // positions after a long-run shortcut (no literal edges there) are excluded.
-          double Cm = 0.0;
           bool magic = false;
           if (j0 + 35 > dirty_until && j0 >= guard_until) {
-            const long long lowb = __double_as_longlong(cj) & 0x7ff0000000000000LL;
-            const double lowd = __longlong_as_double(lowb), highd = __longlong_as_double(lowb + 0x0010000000000000LL);
-            if (lowb > 0 && cj - margin_dn >= lowd && cj + margin_up < highd) {
-              magic = true;
+            if (!(cj >= mg_lo && cj < mg_hi)) {  // left the interval the constant was made for: look at the binade again
+              const long long lowb = __double_as_longlong(cj) & 0x7ff0000000000000LL;
+              mg_lo = __longlong_as_double(lowb) + margin_dn;
+              mg_hi = __longlong_as_double(lowb + 0x0010000000000000LL) - margin_up;
               Cm = __longlong_as_double(lowb + (29LL << 52) + (1LL << 51));
+              if (lowb <= 0) { mg_lo = 1.0; mg_hi = 0.0; }
             }
+            magic = cj >= mg_lo && cj < mg_hi;
           }
           if (magic) ZB_DP_FAST_GROUP(false, true)
           else if (j0 + 35 > dirty_until) ZB_DP_FAST_GROUP(false, false)
           else ZB_DP_FAST_GROUP(true, false)
         } else {
-          // ---- general group: per-step checks ----
-          const uint32_t jend = j0 + 32 < nb ? j0 + 32 : nb;
-          for (uint32_t j = j0; j < jend; j++) {
+          // ---- general group, in blocks of eight steps: a block without a flagged position still
+          // runs the straight-line code (ring-joining variant); only the others check per step ----
+          for (uint32_t sb = 0; sb < 4; sb++) {
+          const uint32_t jb = j0 + sb * 8;
+          if (jb >= nb) break;
+          if (skip_noop && ((flag_cur >> (sb * 8)) & 0xffu) == 0 && skip_left == 0 && !just_finished && jb + 8 <= nb) {
+            uint32_t t0_s = t0_l - sb * 64, dsx_s = dsx_c + sb * 256, gl_s = gl_c + sb * 64, lac_s = lac_c + sb * 16;
+            uint32_t ring_s = ring_c + sb * 128, lane_rot = (lane - 3u - sb * 8u) & 31u, sidx = 3u + sb * 8u;
+            ZB_DP_FAST_8(true, false)
+            (void)lane_rot;
+            continue;
+          }
+          const uint32_t jend = jb + 8 < nb ? jb + 8 : nb;
+          for (uint32_t j = jb; j < jend; j++) {
             const uint32_t jl = j & 31u;
             const double tv2 = lds_f64(t0_l + ds2 * 512 - (jl + 2) * 8);
             const uint32_t ds3 = lds_u8(dsx_c + (jl + 3) * 32);   // rows 32.. are the next stage (or its mirror)
@@ -783,9 +810,10 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
             cj = cnext;
             tv = tv1; tv1 = tv2; ds2 = ds3; llb = llb1; llb1 = llb2;
           }
+          }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s.empty[st]);  // the feeder may write back lac[st] and refill the stage
+        if (lane == 0) mbar_arrive_a(empty_r + st * 8);  // the feeder may write back lac[st] and refill the stage
       }
 #undef ZB_DP_FAST_GROUP
 #undef ZB_DP_FAST_8
