@@ -123,6 +123,7 @@ def run_reference(args, rank):
 
 
 def run_product(args, rank, world):
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
     import torch
     import torch.distributed as dist
     import zopfli_b200 as zb
@@ -169,9 +170,13 @@ def run_product(args, rank, world):
         if world == 1:
             return lib.compress_ptr(hptr, n, zb.ZOPFLI_FORMAT_GZIP, dev_ptr=dptr if resident else None,
                                     numiterations=NUMITER)
+        crc_box = []
+        crc_thread = threading.Thread(target=lambda: crc_box.append(lib.crc32(hptr + halo, n)))  # ctypes drops the GIL
+        crc_thread.start()
         span = lib.deflate_span_ptr(hptr, total, halo, total, final=int(rank == world - 1),
                                     dev_ptr=dptr if resident else None, numiterations=NUMITER)
-        crc = lib.crc32(hptr + halo, n)
+        crc_thread.join()
+        crc = crc_box[0]
         # gather spans + crc to rank 0 over NCCL
         meta = torch.tensor([len(span), crc, n], dtype=torch.int64, device=dev)
         metas = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(world)]
