@@ -75,6 +75,26 @@ void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vecto
     g_split_stores[i].finalize();
   }
 }
+void Engine::greedy_to_split(const std::vector<ParseRange>& r, std::vector<uint32_t>& sizes, int lane) {
+  std::vector<zb::Lz77Store>& g_split_stores = g_split_stores_lane[(unsigned)lane % kLanes];
+  g_split_stores.clear();
+  g_split_stores.resize(r.size());
+  sizes.assign(r.size(), 0);
+  for (size_t i = 0; i < r.size(); i++) {
+    ZoStore st;
+    zo_store_init(&st);
+    zo_lz77_greedy(p_->in.data(), r[i].instart, r[i].inend, &st);
+    g_split_stores[i].append(st.litlens, st.dists, st.size, 0);
+    g_split_stores[i].finalize();
+    sizes[i] = (uint32_t)st.size;
+    zo_store_free(&st);
+  }
+}
+void Engine::split_positions(const std::vector<SplitPos>& q, std::vector<uint32_t>& bytepos, int lane) {
+  std::vector<zb::Lz77Store>& g_split_stores = g_split_stores_lane[(unsigned)lane % kLanes];
+  bytepos.assign(q.size(), 0);
+  for (size_t i = 0; i < q.size(); i++) bytepos[i] = (uint32_t)g_split_stores[q[i].store].pos[q[i].idx];
+}
 void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lane) {
   std::vector<zb::Lz77Store>& g_split_stores = g_split_stores_lane[(unsigned)lane % kLanes];
   static thread_local DynScratch s;

@@ -174,31 +174,55 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
   debug_mark(cid, "start");
   // ---- stage A: greedy parses (only needed when splitting) ----
   const size_t maxblocks = (size_t)opt->blocksplittingmax;
-  if (opt->blocksplitting) {
+  if (opt->blocksplitting && !host_split_forced()) {
+    // the greedy stores never leave the device: they become the stores of the split service, and
+    // only the byte positions of the chosen split points come back (blocksplitter.c:303-313)
+    std::vector<ParseRange> pr;
+    for (size_t m : cm) pr.push_back({M[m].ms - in_base, M[m].me - in_base, 0, 0});
+    std::vector<uint32_t> gsize;
+    eng.greedy_to_split(pr, gsize, lane_r);
+    double t1 = now_ms();
+    debug_mark(cid, "A greedy done");
+    add_time(g_host_times.other, t1 - t0);
+    // ---- stage B: split search (costs on the device, decisions on the host) ----
+    std::vector<size_t> sizes(gsize.begin(), gsize.end());
+    std::vector<std::vector<size_t>> lps =
+        batched_block_split(sizes, maxblocks, [&](const std::vector<EvalReq>& r, std::vector<uint64_t>& c) {
+          eng.split_eval(reinterpret_cast<const Engine::SplitReq*>(r.data()), r.size(), c.data(), lane_r);
+        });
+    std::vector<Engine::SplitPos> want;
+    for (size_t q = 0; q < nc; q++)
+      for (size_t p : lps[q]) want.push_back({(uint32_t)q, (uint32_t)p});
+    std::vector<uint32_t> bytepos;
+    eng.split_positions(want, bytepos, lane_r);
+    size_t w = 0;
+    for (size_t q = 0; q < nc; q++) {
+      Master& mb = M[cm[q]];
+      mb.cuts.push_back(mb.ms);
+      for (size_t k = 0; k < lps[q].size(); k++) mb.cuts.push_back(mb.ms + bytepos[w++]);
+      mb.cuts.push_back(mb.me);
+      if (opt->verbose) {
+        fprintf(stderr, "block split points: ");
+        for (size_t c = 1; c + 1 < mb.cuts.size(); c++) fprintf(stderr, "%d ", (int)mb.cuts[c]);
+        fprintf(stderr, "\n");
+      }
+    }
+    double t2 = now_ms();
+    debug_mark(cid, "B split done");
+    add_time(g_host_times.split, t2 - t1);
+    t0 = t2;
+  } else if (opt->blocksplitting) {  // ZOPFLI_B200_HOST_SPLIT=1: the reference's search on the host estimators
     std::vector<ParseRange> pr;
     for (size_t m : cm) pr.push_back({M[m].ms - in_base, M[m].me - in_base, 0, 0});
     ParseResult res;
     eng.parse(pr, res, lane_r);
     double t1 = now_ms();
-    debug_mark(cid, "A greedy done");
     add_time(g_host_times.other, t1 - t0);
-    // ---- stage B: split search (costs on the device, decisions on the host) ----
-    std::vector<std::vector<size_t>> lps;
-    if (!host_split_forced()) {
-      std::vector<uint64_t> off(nc);
-      for (size_t q = 0; q < nc; q++) off[q] = res.off[q];
-      lps = device_block_split(eng, res.ll.data(), res.d.data(), off, res.size, maxblocks, lane_r);
-    }
     parallel_for(nc, [&](size_t q) {
       Master& mb = M[cm[q]];
-      std::vector<size_t> lp;
-      if (host_split_forced()) {
-        mb.greedy.append(res.ll.data() + res.off[q], res.d.data() + res.off[q], res.size[q], mb.ms);
-        mb.greedy.finalize();
-        lp = block_split_lz77(make_cost(mb.greedy), mb.greedy.size(), maxblocks);
-      } else {
-        lp = lps[q];
-      }
+      mb.greedy.append(res.ll.data() + res.off[q], res.d.data() + res.off[q], res.size[q], mb.ms);
+      mb.greedy.finalize();
+      std::vector<size_t> lp = block_split_lz77(make_cost(mb.greedy), mb.greedy.size(), maxblocks);
       // LZ77 indices -> byte positions (blocksplitter.c:303-313)
       const uint16_t* ll = res.ll.data() + res.off[q];
       const uint16_t* dd = res.d.data() + res.off[q];
@@ -209,15 +233,9 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
         pos += dd[i] == 0 ? 1 : ll[i];
       }
       mb.cuts.push_back(mb.me);
-      if (opt->verbose) {
-        fprintf(stderr, "block split points: ");
-        for (size_t c = 1; c + 1 < mb.cuts.size(); c++) fprintf(stderr, "%d ", (int)mb.cuts[c]);
-        fprintf(stderr, "\n");
-      }
       mb.greedy.clear();
     });
     double t2 = now_ms();
-    debug_mark(cid, "B split done");
     add_time(g_host_times.split, t2 - t1);
     t0 = t2;
   } else {

@@ -553,12 +553,9 @@ void Engine::match_table(uint64_t instart, uint64_t inend, std::vector<uint16_t>
   }
 }
 
-void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vector<uint64_t>& off,
-                         const std::vector<uint32_t>& size, int lane_id) {
-  Impl& m = *p_;
-  Lane& l = m.lane[(unsigned)lane_id % Engine::kLanes];
-  std::lock_guard<std::mutex> g(l.mu);
-  CK(cudaSetDevice(m.dev));
+// builds the split service of lane `l` over stores that already sit on the device
+static void split_setup(Lane& l, const uint16_t* dev_ll, const uint16_t* dev_d, const std::vector<uint64_t>& off,
+                        const std::vector<uint32_t>& size) {
   const size_t ns = off.size();
   uint64_t total = 0, nsnap_total = 0, pos_total = 0;
   for (size_t i = 0; i < ns; i++) total = std::max<uint64_t>(total, off[i] + size[i]);
@@ -575,22 +572,15 @@ void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vecto
     pos_total += (uint64_t)size[i] + 1;
     for (uint32_t c = 0; c * kSnap < size[i]; c++) work.push_back({(uint32_t)i, c});
   }
-  l.sp_ll.ensure(total * 2 + 64);
-  l.sp_d.ensure(total * 2 + 64);
   l.sp_llsym.ensure(total * 2 + 64);
   l.sp_dsym.ensure(total + 64);
   l.sp_snaps.ensure(nsnap_total * 320 * 4 + 64);
   l.sp_pos.ensure(pos_total * 4 + 64);
-  l.tic();
-  if (total) {
-    CK(cudaMemcpyAsync(l.sp_ll.p, ll, total * 2, cudaMemcpyHostToDevice, l.stream));
-    CK(cudaMemcpyAsync(l.sp_d.p, d, total * 2, cudaMemcpyHostToDevice, l.stream));
-  }
   l.upload(l.sp_stores, l.sp_desc);
   l.upload(l.sp_work, work);
   SplitBatch& b = l.sp_batch;
-  b.ll = l.sp_ll.as<uint16_t>();
-  b.d = l.sp_d.as<uint16_t>();
+  b.ll = dev_ll;
+  b.d = dev_d;
   b.llsym = l.sp_llsym.as<uint16_t>();
   b.dsym = l.sp_dsym.as<uint8_t>();
   b.pos = l.sp_pos.as<uint32_t>();
@@ -603,9 +593,81 @@ void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vecto
     k_split_prep_snap<<<(unsigned)((work.size() + 7) / 8), 256, 0, l.stream>>>(b, l.sp_work.as<SnapWork>(), (uint32_t)work.size());
   if (ns) k_split_prep_prefix<<<(unsigned)ns, 320, 0, l.stream>>>(b);
   CK(cudaGetLastError());
-  l.toc(l.acc.ms_split);
   l.acc.launches += ns + 3;
+}
+
+void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vector<uint64_t>& off,
+                         const std::vector<uint32_t>& size, int lane_id) {
+  Impl& m = *p_;
+  Lane& l = m.lane[(unsigned)lane_id % Engine::kLanes];
+  std::lock_guard<std::mutex> g(l.mu);
+  CK(cudaSetDevice(m.dev));
+  uint64_t total = 0;
+  for (size_t i = 0; i < off.size(); i++) total = std::max<uint64_t>(total, off[i] + size[i]);
+  l.sp_ll.ensure(total * 2 + 64);
+  l.sp_d.ensure(total * 2 + 64);
+  l.tic();
+  if (total) {
+    CK(cudaMemcpyAsync(l.sp_ll.p, ll, total * 2, cudaMemcpyHostToDevice, l.stream));
+    CK(cudaMemcpyAsync(l.sp_d.p, d, total * 2, cudaMemcpyHostToDevice, l.stream));
+  }
+  split_setup(l, l.sp_ll.as<uint16_t>(), l.sp_d.as<uint16_t>(), off, size);
+  l.toc(l.acc.ms_split);
   l.acc.h2d_bytes += total * 4;
+}
+
+void Engine::greedy_to_split(const std::vector<ParseRange>& ranges, std::vector<uint32_t>& sizes, int lane_id) {
+  Impl& m = *p_;
+  Lane& l = m.lane[(unsigned)lane_id % Engine::kLanes];
+  std::lock_guard<std::mutex> g(l.mu);
+  CK(cudaSetDevice(m.dev));
+  const size_t ns = ranges.size();
+  sizes.assign(ns, 0);
+  if (ns == 0) return;
+  for (const ParseRange& r : ranges)
+    if (r.mode != 0) { fprintf(stderr, "zopfli-b200: greedy_to_split takes greedy ranges only\n"); abort(); }
+  Impl::Layout L;
+  m.build_layout(ranges, L);
+  Batch b = m.prepare(L, l);
+  l.tic();
+  k_greedy<<<(unsigned)ns, 32, 0, l.stream>>>(b, 0);
+  CK(cudaGetLastError());
+  l.toc(l.acc.ms_greedy);
+  l.acc.launches++;
+  std::vector<JobState> js(ns);
+  l.tic();
+  CK(cudaMemcpyAsync(js.data(), l.jobs.p, ns * sizeof(JobState), cudaMemcpyDeviceToHost, l.stream));
+  CK(cudaStreamSynchronize(l.stream));
+  l.toc(l.acc.ms_d2h);
+  l.acc.d2h_bytes += ns * sizeof(JobState);
+  std::vector<uint64_t> off(ns);
+  for (size_t i = 0; i < ns; i++) { sizes[i] = js[i].greedy_size; off[i] = L.segs[i].pos_off; }
+  l.tic();
+  split_setup(l, b.st_ll[0], b.st_d[0], off, sizes);  // k_greedy wrote range i's store at its pos_off
+  l.toc(l.acc.ms_split);
+}
+
+__global__ void k_split_gather_pos(SplitBatch b, const Engine::SplitPos* __restrict__ q, uint32_t n, uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = b.pos[b.stores[q[i].store].pos_off + q[i].idx];
+}
+
+void Engine::split_positions(const std::vector<SplitPos>& q, std::vector<uint32_t>& bytepos, int lane_id) {
+  Impl& m = *p_;
+  Lane& l = m.lane[(unsigned)lane_id % Engine::kLanes];
+  std::lock_guard<std::mutex> g(l.mu);
+  CK(cudaSetDevice(m.dev));
+  bytepos.assign(q.size(), 0);
+  if (q.empty()) return;
+  l.sp_evals.ensure(q.size() * sizeof(SplitPos) + 64);
+  l.sp_out.ensure(q.size() * 4 + 64);
+  CK(cudaMemcpyAsync(l.sp_evals.p, q.data(), q.size() * sizeof(SplitPos), cudaMemcpyHostToDevice, l.stream));
+  k_split_gather_pos<<<(unsigned)((q.size() + 255) / 256), 256, 0, l.stream>>>(l.sp_batch, l.sp_evals.as<SplitPos>(), (uint32_t)q.size(),
+                                                                              l.sp_out.as<uint32_t>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(bytepos.data(), l.sp_out.p, q.size() * 4, cudaMemcpyDeviceToHost, l.stream));
+  CK(cudaStreamSynchronize(l.stream));
+  l.acc.launches++;
 }
 
 void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lane_id) {

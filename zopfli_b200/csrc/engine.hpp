@@ -59,6 +59,12 @@ class Engine {
   // split_eval prices a batch of (store, lstart, lend) ranges on the device.
   void split_begin(const uint16_t* ll, const uint16_t* d, const std::vector<uint64_t>& off,
                    const std::vector<uint32_t>& size, int lane = 1);
+  // Stage A + B without a symbol round trip: greedy parse of `ranges` whose stores stay on the device
+  // and become the stores of the split service of the same lane.  sizes[i] = symbols of range i.
+  void greedy_to_split(const std::vector<ParseRange>& ranges, std::vector<uint32_t>& sizes, int lane = 1);
+  // byte offset (from the start of its range) of symbol idx of store `store`, for many (store, idx)
+  struct SplitPos { uint32_t store, idx; };
+  void split_positions(const std::vector<SplitPos>& q, std::vector<uint32_t>& bytepos, int lane = 1);
   struct SplitReq { uint32_t store, lstart, lend; };
   void split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lane = 1);
 
