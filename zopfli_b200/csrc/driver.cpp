@@ -180,7 +180,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
     std::vector<ParseRange> pr;
     for (size_t m : cm) pr.push_back({M[m].ms - in_base, M[m].me - in_base, 0, 0});
     std::vector<uint32_t> gsize;
-    eng.greedy_to_split(pr, gsize, lane_r);
+    eng.greedy_to_split(pr, gsize, lane_g);  // stages A and B sit on the critical path: high-priority lane
     double t1 = now_ms();
     debug_mark(cid, "A greedy done");
     add_time(g_host_times.other, t1 - t0);
@@ -188,13 +188,13 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
     std::vector<size_t> sizes(gsize.begin(), gsize.end());
     std::vector<std::vector<size_t>> lps =
         batched_block_split(sizes, maxblocks, [&](const std::vector<EvalReq>& r, std::vector<uint64_t>& c) {
-          eng.split_eval(reinterpret_cast<const Engine::SplitReq*>(r.data()), r.size(), c.data(), lane_r);
+          eng.split_eval(reinterpret_cast<const Engine::SplitReq*>(r.data()), r.size(), c.data(), lane_g);
         });
     std::vector<Engine::SplitPos> want;
     for (size_t q = 0; q < nc; q++)
       for (size_t p : lps[q]) want.push_back({(uint32_t)q, (uint32_t)p});
     std::vector<uint32_t> bytepos;
-    eng.split_positions(want, bytepos, lane_r);
+    eng.split_positions(want, bytepos, lane_g);
     size_t w = 0;
     for (size_t q = 0; q < nc; q++) {
       Master& mb = M[cm[q]];
@@ -441,7 +441,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
       debug_mark(cid, "C giants parsed");
       adopt(0);
       add_time(g_host_times.other, now_ms() - tw);
-      finish(dirty, lane_r);
+      finish(dirty, lane_g);  // the giants' lane is idle now and has stream priority
       debug_mark(cid, "D-F dirty done");
     }
   }

@@ -484,10 +484,18 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
     const uint32_t gs = js->greedy_size;
     const uint16_t* gl = b.st_ll[0] + sd.pos_off;
     const uint16_t* gd = b.st_d[0] + sd.pos_off;
-    for (uint32_t t = lane; t < gs; t += 32) {
-      uint32_t l = gl[t], d = gd[t];
-      if (d == 0) atomicAdd(&s.stats[l], 1u);
-      else { atomicAdd(&s.stats[length_symbol((int)l)], 1u); atomicAdd(&s.stats[288 + dist_symbol((int)d)], 1u); }
+    for (uint32_t tb = 0; tb < gs; tb += 32 * 8) {  // loads batched: the loop is latency-bound otherwise
+      uint32_t lv[8], dv[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const uint32_t t = tb + u * 32 + lane; lv[u] = t < gs ? gl[t] : 0u; dv[u] = t < gs ? gd[t] : 0u; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const uint32_t t = tb + u * 32 + lane;
+        if (t >= gs) continue;
+        const uint32_t l = lv[u], d = dv[u];
+        if (d == 0) atomicAdd(&s.stats[l], 1u);
+        else { atomicAdd(&s.stats[length_symbol((int)l)], 1u); atomicAdd(&s.stats[288 + dist_symbol((int)d)], 1u); }
+      }
     }
     __syncwarp();
     if (lane == 0) s.stats[256] = 1;  // squeeze.c:409
@@ -932,14 +940,21 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
     uint16_t* cd = b.st_d[curbuf] + sd.pos_off;
     for (int i = lane; i < 320; i += 32) s.hist[i] = 0;
     __syncwarp();
+    uint32_t en[4];  // symbols of the next trip, fetched one trip ahead
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t t = u * 32 + lane;
+      en[u] = t < nsym ? psym[cursor + t] : 1u;  // dummy literal at position 0 for the tail
+    }
     for (uint32_t base = 0; base < nsym; base += 128) {
       uint32_t e[4];
       uint4 ra[4], rc[4];
       uint32_t by[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const uint32_t t = base + u * 32 + lane;
-        e[u] = t < nsym ? psym[cursor + t] : 1u;  // dummy literal at position 0 for the tail
+        e[u] = en[u];
+        const uint32_t t = base + 128 + u * 32 + lane;
+        en[u] = t < nsym ? psym[cursor + t] : 1u;
       }
 #pragma unroll
       for (int u = 0; u < 4; u++) {

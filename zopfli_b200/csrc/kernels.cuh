@@ -578,7 +578,13 @@ __global__ void __launch_bounds__(32) k_greedy(Batch b, int buf) {
     const uint32_t wb = i;
     const uint32_t wn = (n - wb) < (uint32_t)(kGreedyWin + kGreedyLook) ? (n - wb) : (uint32_t)(kGreedyWin + kGreedyLook);
     const uint32_t nchain = wn < (uint32_t)kGreedyWin ? wn : (uint32_t)kGreedyWin;
-    for (uint32_t t = lane; t < wn; t += 32) { wld[t] = ld[wb + t]; wby[t] = in[wb + t]; }
+    for (uint32_t tb = 0; tb < wn; tb += 32 * 8) {  // 16 loads in flight per lane: the refill is pure latency
+      uint32_t v[8], c[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const uint32_t t = tb + u * 32 + lane; v[u] = t < wn ? ld[wb + t] : 0u; c[u] = t < wn ? (uint32_t)in[wb + t] : 0u; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const uint32_t t = tb + u * 32 + lane; if (t < wn) { wld[t] = v[u]; wby[t] = (uint8_t)c[u]; } }
+    }
     __syncwarp();
     for (uint32_t r = lane; r < nchain; r += 32) {  // 1: every position as a B state
       uint32_t cnt;
