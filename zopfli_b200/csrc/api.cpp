@@ -134,6 +134,11 @@ size_t num_master_blocks(size_t insize) {  // deflate.c:912-924 do/while
   return insize == 0 ? 1 : (insize + kMasterBlock - 1) / kMasterBlock;
 }
 
+bool api_debug() {
+  static int v = [] { const char* e = getenv("ZOPFLI_B200_DEBUG"); return e && atoi(e) ? 1 : 0; }();
+  return v != 0;
+}
+
 void deflate_impl(const ZopfliOptions* options, int btype, int final, const unsigned char* in,
                   size_t insize, const unsigned char* dev_in, unsigned char* bp, unsigned char** out,
                   size_t* outsize) {
@@ -144,8 +149,12 @@ void deflate_impl(const ZopfliOptions* options, int btype, int final, const unsi
     if (dev_in) Engine::get().set_input_device(dev_in, insize);
     else Engine::get().set_input_host(in, insize);
   }
+  const double t1 = now_ms();
   deflate_units(options, btype, final != 0, in, master_units(insize, 0, num_master_blocks(insize)), 0, pieces);
+  const double t2 = now_ms();
   splice_pieces(pieces, in, bp, out, outsize);
+  if (api_debug())
+    fprintf(stderr, "[zb] api: set_input %.1f ms, deflate_units %.1f ms, splice %.1f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
   if (options->verbose) {
     fprintf(stderr, "Original Size: %lu, Deflate: %lu, Compression: %f%% Removed\n", (unsigned long)insize,
             (unsigned long)(*outsize - offset), 100.0 * (double)(insize - (*outsize - offset)) / (double)insize);
@@ -162,7 +171,9 @@ void compress_impl(const ZopfliOptions* options, ZopfliFormat fmt, const unsigne
     static const unsigned char hdr[10] = {31, 139, 8, 0, 0, 0, 0, 0, 2, 3};
     append_bytes(hdr, 10, out, outsize);
     deflate_impl(options, 2, 1, in, insize, dev_in, &bp, out, outsize);
+    const double tj = now_ms();
     crc_thread.join();
+    if (api_debug()) fprintf(stderr, "[zb] api: crc join waited %.1f ms\n", now_ms() - tj);
     unsigned char tr[8] = {(unsigned char)(crc & 255), (unsigned char)((crc >> 8) & 255),
                            (unsigned char)((crc >> 16) & 255), (unsigned char)((crc >> 24) & 255),
                            (unsigned char)(insize & 255), (unsigned char)((insize >> 8) & 255),
