@@ -5,8 +5,10 @@
 // the symbol range, so here (a) every probe of a FindMinimum round is priced in one batch,
 // (b) FindMinimum is started for EVERY current block of every store as soon as the block exists
 // (whichever the "largest first" rule picks next, its answer is already there), and (c) all stores
-// advance in lockstep rounds.  One round = one call of the batch evaluator (a kernel launch on the
-// device, k_split_eval).  The sequential decision logic (largest splittable block first, `done`
+// advance in lockstep rounds, and (d) while few searches are active a round prices two or three
+// levels of the nine-point recursion at once (every interval the next level could narrow to),
+// which divides the number of rounds -- the latency that is left -- by the depth.  One round =
+// one call of the batch evaluator (a kernel launch on the device, k_split_eval).  The sequential decision logic (largest splittable block first, `done`
 // marks, maxblocks, the `lz77size - 1` end quirk of :203) is replayed unchanged on the cached
 // answers, so the split points are identical to the reference's.
 #pragma once
@@ -35,13 +37,21 @@ struct FmTask {  // one FindMinimum(SplitCost) over the block [cstart, cend)
   bool exhaustive;
   size_t pos;
   uint64_t lastbest = kLarge;
-  size_t p[9];
   bool have_orig = false;
   uint64_t origcost = 0;
   bool finished = false;
   size_t llpos = 0;
   uint64_t splitcost = 0;
-  size_t req_base = 0, req_count = 0;  // slice of the current batch
+  size_t req_base = 0;   // the orig-cost request of the current batch, if any
+  int root = -1;         // node of the current interval in this round's speculation tree
+};
+
+struct SpecNode {        // one (start, end) interval of the nine-point recursion and its probes
+  size_t start, end;
+  size_t p[9];
+  size_t req_base;       // 18 requests: (cstart, p[i]), (p[i], cend)
+  bool has;              // end - start > 9
+  int child[9];
 };
 
 struct StoreState {
@@ -120,11 +130,19 @@ inline std::vector<std::vector<size_t>> batched_block_split(const std::vector<si
   }
   std::vector<EvalReq> reqs;
   std::vector<uint64_t> costs;
+  std::vector<SpecNode> nodes;
+  const size_t kBudget = 6000;  // probes per round up to which deeper speculation is worth its kernel time
   for (;;) {
     reqs.clear();
+    nodes.clear();
     bool any = false;
+    size_t narrowing = 0;
+    for (FmTask& t : T)
+      if (!t.finished && !S[t.store].finished && !t.exhaustive && t.end - t.start > 9) narrowing++;
+    const int depth = narrowing * 18 * 91 <= kBudget ? 3 : (narrowing * 18 * 10 <= kBudget ? 2 : 1);
     for (FmTask& t : T) {
-      if (t.finished || S[t.store].finished) { t.req_count = 0; continue; }
+      t.root = -1;
+      if (t.finished || S[t.store].finished) continue;
       any = true;
       t.req_base = reqs.size();
       if (!t.have_orig) reqs.push_back({t.store, (uint32_t)t.cstart, (uint32_t)t.cend});
@@ -133,14 +151,33 @@ inline std::vector<std::vector<size_t>> batched_block_split(const std::vector<si
           reqs.push_back({t.store, (uint32_t)t.cstart, (uint32_t)i});
           reqs.push_back({t.store, (uint32_t)i, (uint32_t)t.cend});
         }
-      } else if (t.end - t.start > 9) {  // blocksplitter.c:73
-        for (int i = 0; i < 9; i++) {
-          t.p[i] = t.start + (size_t)(i + 1) * ((t.end - t.start) / 10);
-          reqs.push_back({t.store, (uint32_t)t.cstart, (uint32_t)t.p[i]});
-          reqs.push_back({t.store, (uint32_t)t.p[i], (uint32_t)t.cend});
-        }
+      } else {
+        // speculation tree over the intervals the recursion can reach within `depth` levels
+        struct Builder {
+          std::vector<SpecNode>& nodes; std::vector<EvalReq>& reqs; const FmTask& t;
+          int build(size_t start, size_t end, int d) {
+            const int id = (int)nodes.size();
+            nodes.push_back(SpecNode());
+            SpecNode n;
+            n.start = start; n.end = end; n.has = end - start > 9;  // blocksplitter.c:73
+            n.req_base = reqs.size();
+            for (int i = 0; i < 9; i++) n.child[i] = -1;
+            if (n.has) {
+              for (int i = 0; i < 9; i++) {
+                n.p[i] = start + (size_t)(i + 1) * ((end - start) / 10);
+                reqs.push_back({t.store, (uint32_t)t.cstart, (uint32_t)n.p[i]});
+                reqs.push_back({t.store, (uint32_t)n.p[i], (uint32_t)t.cend});
+              }
+              if (d > 1)
+                for (int i = 0; i < 9; i++)
+                  n.child[i] = build(i == 0 ? start : n.p[i - 1], i == 8 ? end : n.p[i + 1], d - 1);
+            }
+            nodes[id] = n;
+            return id;
+          }
+        } bld{nodes, reqs, t};
+        t.root = bld.build(t.start, t.end, depth);
       }
-      t.req_count = reqs.size() - t.req_base;
     }
     if (!any) break;
     costs.assign(reqs.size(), 0);
@@ -158,26 +195,26 @@ inline std::vector<std::vector<size_t>> batched_block_split(const std::vector<si
           if (v < best) { best = v; result = i; }
         }
         t.llpos = result; t.splitcost = best; t.finished = true;
-      } else if (t.end - t.start <= 9) {
-        t.llpos = t.pos; t.splitcost = t.lastbest; t.finished = true;
-      } else {  // blocksplitter.c:74-91
+        continue;
+      }
+      for (int cur = t.root; cur >= 0;) {  // blocksplitter.c:71-91, one loop iteration per tree level
+        const SpecNode& n = nodes[cur];
+        if (!n.has) { t.llpos = t.pos; t.splitcost = t.lastbest; t.finished = true; break; }
+        const size_t kb = n.req_base;
         int besti = 0;
-        uint64_t best = costs[k] + costs[k + 1];
+        uint64_t best = costs[kb] + costs[kb + 1];
         for (int i = 1; i < 9; i++) {
-          uint64_t v = costs[k + 2 * i] + costs[k + 2 * i + 1];
+          uint64_t v = costs[kb + 2 * i] + costs[kb + 2 * i + 1];
           if (v < best) { best = v; besti = i; }
         }
-        if (best > t.lastbest) {
-          t.llpos = t.pos; t.splitcost = t.lastbest; t.finished = true;
-        } else {
-          size_t ns_ = besti == 0 ? t.start : t.p[besti - 1];
-          size_t ne_ = besti == 8 ? t.end : t.p[besti + 1];
-          t.start = ns_; t.end = ne_;
-          t.pos = t.p[besti];
-          t.lastbest = best;
-          if (t.end - t.start <= 9) { t.llpos = t.pos; t.splitcost = t.lastbest; t.finished = true; }
-        }
+        if (best > t.lastbest) { t.llpos = t.pos; t.splitcost = t.lastbest; t.finished = true; break; }
+        t.start = besti == 0 ? n.start : n.p[besti - 1];
+        t.end = besti == 8 ? n.end : n.p[besti + 1];
+        t.pos = n.p[besti];
+        t.lastbest = best;
+        cur = n.child[besti];
       }
+      if (!t.finished && t.end - t.start <= 9) { t.llpos = t.pos; t.splitcost = t.lastbest; t.finished = true; }
     }
     for (size_t st = 0; st < ns; st++) advance((uint32_t)st);
   }
