@@ -208,3 +208,14 @@ def test_splice_many_small_parts_all_bit_phases(ref, mock):
         outs.append((C.string_at(out, n.value), bp.value))
     assert outs[0] == outs[1]
     assert zlib.decompress(outs[1][0], -15) == base
+
+
+def test_nocopy_result_wrapper(mock):
+    """compress_ptr_nocopy hands out the library's malloc()ed buffer itself; same bytes, explicit free."""
+    data = TXT[:60000]
+    a = np.frombuffer(data + b"\0" * 16, np.uint8)
+    want = mock.compress(data, zb.ZOPFLI_FORMAT_ZLIB, numiterations=1)
+    ob = mock.compress_ptr_nocopy(a.ctypes.data, len(data), zb.ZOPFLI_FORMAT_ZLIB, numiterations=1)
+    assert len(ob) == len(want) and ob.tobytes() == want and bytes(ob.view[:16]) == want[:16]
+    ob.close()
+    ob.close()  # idempotent

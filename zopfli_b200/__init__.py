@@ -59,6 +59,30 @@ def _pad(data):
     return p
 
 
+class OutBuffer:
+    """The library's own malloc()ed result (zopfli.h:86-88: the caller frees), exposed without a copy.
+    Supports len(), the buffer protocol via .view (a ctypes array over the allocation), tobytes();
+    freed on close() / garbage collection."""
+
+    def __init__(self, libc, ptr, size):
+        self._libc, self._ptr, self.size = libc, ptr, size
+        self.view = (C.c_ubyte * size).from_address(ptr.value) if size else (C.c_ubyte * 0)()
+
+    def __len__(self):
+        return self.size
+
+    def tobytes(self) -> bytes:
+        return C.string_at(self._ptr, self.size) if self.size else b""
+
+    def close(self):
+        if self._ptr is not None and self._ptr.value:
+            self.view = None
+            self._libc.free(self._ptr)
+        self._ptr = None
+
+    __del__ = close
+
+
 class Library:
     """ctypes view of one build of the C ABI (the product library by default)."""
 
@@ -142,6 +166,16 @@ class Library:
         else:
             self.lib.ZopfliB200CompressDevice(C.byref(o), fmt, host_ptr, nbytes, dev_ptr, C.byref(out), C.byref(n))
         return self._take(out, n)
+
+    def compress_ptr_nocopy(self, host_ptr, nbytes, fmt=ZOPFLI_FORMAT_GZIP, dev_ptr=None, **kw) -> OutBuffer:
+        """compress_ptr without the copy into a Python bytes object: what a C caller gets back."""
+        o = self.options(**kw)
+        out, n = C.c_void_p(None), C.c_size_t(0)
+        if dev_ptr is None:
+            self.lib.ZopfliCompress(C.byref(o), fmt, host_ptr, nbytes, C.byref(out), C.byref(n))
+        else:
+            self.lib.ZopfliB200CompressDevice(C.byref(o), fmt, host_ptr, nbytes, dev_ptr, C.byref(out), C.byref(n))
+        return OutBuffer(self.libc, out, n.value)
 
     def deflate(self, data, btype=2, final=1, **kw):
         """ZopfliDeflate (deflate.h:58-60) -> (bytes, bp)."""
