@@ -58,6 +58,13 @@ int ZopfliB200DeviceAutoTypeBits(const unsigned short* litlens, const unsigned s
 size_t ZopfliB200HostBlockSplitLZ77(const unsigned char* in, const unsigned short* litlens,
                                     const unsigned short* dists, size_t n, size_t maxblocks,
                                     size_t* points, size_t cap);
+/* The same search as the product runs it (batched_split.hpp: every FindMinimum of every current
+ * block in lockstep rounds, `budget` probes per round bound the speculation depth), costs from the
+ * host estimators, for several stores at once: store s = symbols [off[s], off[s]+size[s]).
+ * points[s*cap ..] receives store s's split points, npoints[s] their number. */
+void ZopfliB200HostBatchedSplit(const unsigned short* litlens, const unsigned short* dists, size_t nstores,
+                                const size_t* off, const size_t* size, size_t maxblocks, size_t budget,
+                                size_t* points, size_t cap, size_t* npoints);
 double ZopfliB200HostBlockSize(const unsigned char* in, const unsigned short* litlens,
                                const unsigned short* dists, size_t n, size_t lstart, size_t lend,
                                int btype /* 0,1,2 or -1 for AutoType */);

@@ -143,3 +143,38 @@ def test_full_size_properties(lib):
     assert zlib.decompress(z, -15) == data
     spans = [lib.deflate_span(data, m, min(m + 3, 8), final=int(m + 3 >= 8)) for m in range(0, 8, 3)]
     assert lib.splice_spans(spans)[0] == z
+
+
+def test_nocopy_result_and_device_input(ref, lib):
+    """compress_ptr_nocopy (the malloc()ed result itself) with a device-resident input copy."""
+    import torch
+    data = TXT[:1200000]
+    host = torch.zeros(len(data) + 64, dtype=torch.uint8).pin_memory()
+    host[: len(data)] = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+    dev = host.cuda()
+    want = ref.compress(data, 0, numiterations=2)
+    for dptr in (None, dev.data_ptr()):
+        ob = lib.compress_ptr_nocopy(host.data_ptr(), len(data), zb.ZOPFLI_FORMAT_GZIP, dev_ptr=dptr, numiterations=2)
+        assert len(ob) == len(want) and ob.tobytes() == want
+        ob.close()
+
+
+def test_pipeline_shapes_give_one_stream(ref):
+    """Chunk pipelines, the giant-block lane split and the host/device split service are scheduling
+    choices: every combination must produce the reference's bytes.  The switches are read once per
+    process, hence subprocesses."""
+    import os, subprocess, sys, tempfile
+    data = TXT  # three master blocks
+    want = ref.compress(data, 2, numiterations=2)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "in.bin")
+        open(src, "wb").write(data)
+        code = ("import sys; sys.path.insert(0, %r); import zopfli_b200 as zb; d = open(%r, 'rb').read(); "
+                "open(sys.argv[1], 'wb').write(zb.compress(d, zb.ZOPFLI_FORMAT_DEFLATE, numiterations=2))" % (root, src))
+        for i, env in enumerate([{"ZOPFLI_B200_FORCE_CHUNKS": "3", "ZOPFLI_B200_GIANT": "50000"},
+                                 {"ZOPFLI_B200_FORCE_CHUNKS": "2", "ZOPFLI_B200_GIANT": "100000000"},
+                                 {"ZOPFLI_B200_HOST_SPLIT": "1"}]):
+            out = os.path.join(td, "out%d.bin" % i)
+            subprocess.check_call([sys.executable, "-c", code, out], env=dict(os.environ, **env))
+            assert open(out, "rb").read() == want, env

@@ -219,3 +219,22 @@ def test_nocopy_result_wrapper(mock):
     assert len(ob) == len(want) and ob.tobytes() == want and bytes(ob.view[:16]) == want[:16]
     ob.close()
     ob.close()  # idempotent
+
+
+@pytest.mark.parametrize("budget", [0, 200, 3000, 100000])
+def test_batched_split_scheduler_matches_reference(ref, host, budget):
+    """batched_split.hpp (speculative FindMinimum for every block, lockstep rounds, one to three
+    levels of the nine-point recursion per round depending on `budget`) returns the reference's
+    ZopfliBlockSplitLZ77 points (blocksplitter.c:215-273) for several stores at once."""
+    rng = np.random.default_rng(5)
+    stores = []
+    datas = [TXT[:400000], corpus.synth_binary(300000, 7), corpus.mixed_small(90000), TXT[900000:960000],
+             corpus.adv_runs()[:120000], TXT[1000000:1000500]]
+    for d in datas:
+        ll, dd = ref.lz77(d, 0, len(d), 0, 1)   # greedy store
+        stores.append((d, ll, dd))
+    for maxblocks in (15, 4, 0):
+        got = host.host_batched_split([(ll, dd) for _, ll, dd in stores], maxblocks=maxblocks, budget=budget)
+        for (d, ll, dd), g in zip(stores, got):
+            want = ref.block_split_lz77(d, ll, dd, maxblocks=maxblocks)
+            assert np.array_equal(g, want), (len(d), maxblocks, budget)

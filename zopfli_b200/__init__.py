@@ -46,7 +46,7 @@ class Stats(C.Structure):
 EXPORTS = ["ZopfliInitOptions", "ZopfliCompress", "ZopfliDeflate", "ZopfliDeflatePart",
            "ZopfliGzipCompress", "ZopfliZlibCompress", "ZopfliB200LZ77", "ZopfliB200LZ77Batch",
            "ZopfliB200MatchTable", "ZopfliB200DynamicBlockBits", "ZopfliB200DeviceAutoTypeBits", "ZopfliB200HostBlockSplitLZ77",
-           "ZopfliB200HostBlockSize", "ZopfliB200HostEmitBlock", "ZopfliB200HostLengthLimited",
+           "ZopfliB200HostBatchedSplit", "ZopfliB200HostBlockSize", "ZopfliB200HostEmitBlock", "ZopfliB200HostLengthLimited",
            "ZopfliB200DeflateSpan", "ZopfliB200AppendSpan", "ZopfliB200Crc32", "ZopfliB200Crc32Combine", "ZopfliB200CompressDevice",
            "ZopfliB200GetStats", "ZopfliB200ResetStats", "ZopfliB200SetStream", "ZopfliB200Device",
            "ZopfliB200Version"]
@@ -115,6 +115,8 @@ class Library:
         L.ZopfliB200DynamicBlockBits.restype = C.c_uint64
         L.ZopfliB200HostBlockSplitLZ77.argtypes = [vp, vp, vp, sz, sz, vp, sz]
         L.ZopfliB200HostBlockSplitLZ77.restype = sz
+        L.ZopfliB200HostBatchedSplit.argtypes = [vp, vp, sz, vp, vp, sz, sz, vp, sz, vp]
+        L.ZopfliB200HostBatchedSplit.restype = None
         L.ZopfliB200HostBlockSize.argtypes = [vp, vp, vp, sz, sz, sz, C.c_int]
         L.ZopfliB200HostBlockSize.restype = C.c_double
         L.ZopfliB200HostEmitBlock.argtypes = [vp, vp, vp, sz, sz, sz, C.c_int, C.c_int, vp, sz]
@@ -166,6 +168,19 @@ class Library:
         else:
             self.lib.ZopfliB200CompressDevice(C.byref(o), fmt, host_ptr, nbytes, dev_ptr, C.byref(out), C.byref(n))
         return self._take(out, n)
+
+    def host_batched_split(self, stores, maxblocks=15, budget=6000):
+        """stores: list of (litlens, dists) arrays -> list of split-point arrays (batched_split.hpp on host costs)"""
+        ll = np.concatenate([np.asarray(a, np.uint16) for a, _ in stores]) if stores else np.zeros(0, np.uint16)
+        dd = np.concatenate([np.asarray(b, np.uint16) for _, b in stores]) if stores else np.zeros(0, np.uint16)
+        size = np.array([len(a) for a, _ in stores], np.uint64)
+        off = np.concatenate([[0], np.cumsum(size)[:-1]]).astype(np.uint64)
+        cap = 64 + maxblocks
+        pts = np.zeros(len(stores) * cap, np.uint64)
+        npts = np.zeros(len(stores), np.uint64)
+        self.lib.ZopfliB200HostBatchedSplit(ll.ctypes.data, dd.ctypes.data, len(stores), off.ctypes.data, size.ctypes.data,
+                                            maxblocks, budget, pts.ctypes.data, cap, npts.ctypes.data)
+        return [pts[i * cap: i * cap + int(npts[i])].astype(np.int64) for i in range(len(stores))]
 
     def compress_ptr_nocopy(self, host_ptr, nbytes, fmt=ZOPFLI_FORMAT_GZIP, dev_ptr=None, **kw) -> OutBuffer:
         """compress_ptr without the copy into a Python bytes object: what a C caller gets back."""

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/zopfli_b200.h"
+#include "batched_split.hpp"
 #include "driver.hpp"
 #include "engine.hpp"
 #include "host_split.hpp"
@@ -399,6 +400,22 @@ size_t ZopfliB200HostBlockSplitLZ77(const unsigned char* in, const unsigned shor
   std::vector<size_t> p = block_split_lz77(cost, st.size(), maxblocks);
   for (size_t i = 0; i < p.size() && i < cap; i++) points[i] = p[i];
   return p.size();
+}
+
+void ZopfliB200HostBatchedSplit(const unsigned short* litlens, const unsigned short* dists, size_t nstores,
+                                const size_t* off, const size_t* size, size_t maxblocks, size_t budget,
+                                size_t* points, size_t cap, size_t* npoints) {
+  std::vector<Lz77Store> st(nstores);
+  std::vector<size_t> sizes(nstores);
+  for (size_t s = 0; s < nstores; s++) { make_store(litlens + off[s], dists + off[s], size[s], st[s]); sizes[s] = size[s]; }
+  std::vector<std::vector<size_t>> r = batched_block_split(sizes, maxblocks, [&](const std::vector<EvalReq>& q, std::vector<uint64_t>& c) {
+    DynScratch sc;
+    for (size_t i = 0; i < q.size(); i++) c[i] = auto_type_bits(st[q[i].store], q[i].lstart, q[i].lend, sc);
+  }, budget);
+  for (size_t s = 0; s < nstores; s++) {
+    npoints[s] = r[s].size();
+    for (size_t i = 0; i < r[s].size() && i < cap; i++) points[s * cap + i] = r[s][i];
+  }
 }
 
 double ZopfliB200HostBlockSize(const unsigned char* in, const unsigned short* litlens,

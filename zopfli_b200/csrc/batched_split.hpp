@@ -66,8 +66,9 @@ struct StoreState {
 
 }  // namespace bsplit
 
+// budget: probes per round up to which deeper speculation is worth its kernel time
 inline std::vector<std::vector<size_t>> batched_block_split(const std::vector<size_t>& sizes, size_t maxblocks,
-                                                             const BatchEvalFn& eval) {
+                                                             const BatchEvalFn& eval, size_t budget = 6000) {
   using namespace bsplit;
   const size_t ns = sizes.size();
   std::vector<StoreState> S(ns);
@@ -131,7 +132,7 @@ inline std::vector<std::vector<size_t>> batched_block_split(const std::vector<si
   std::vector<EvalReq> reqs;
   std::vector<uint64_t> costs;
   std::vector<SpecNode> nodes;
-  const size_t kBudget = 6000;  // probes per round up to which deeper speculation is worth its kernel time
+  const size_t kBudget = budget;
   for (;;) {
     reqs.clear();
     nodes.clear();
