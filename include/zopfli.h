@@ -58,6 +58,30 @@ void ZopfliDeflatePart(const ZopfliOptions* options, int btype, int final,
                        const unsigned char* in, size_t instart, size_t inend,
                        unsigned char* bp, unsigned char** out, size_t* outsize);
 
+/* lz77.h:44-62 -- the output type of the hot path, as callers of deflate.h see it: symbol i is a
+ * literal litlens[i] when dists[i] == 0, else a match of length litlens[i] at distance dists[i].
+ * Only litlens, dists and size are read by the two functions below; the remaining members keep
+ * the reference's layout (pointers it maintains for its own bookkeeping). */
+typedef struct ZopfliLZ77Store {
+  unsigned short* litlens;
+  unsigned short* dists;
+  size_t size;
+  const unsigned char* data;
+  size_t* pos;
+  unsigned short* ll_symbol;
+  unsigned short* d_symbol;
+  size_t* ll_counts;
+  size_t* d_counts;
+} ZopfliLZ77Store;
+
+/* deflate.h:79-80, deflate.c:584-608.  Exact size in bits of symbols [lstart, lend) as one block of
+ * type btype (0 stored, 1 fixed, 2 dynamic).  Host arithmetic (integers); no GPU involved. */
+double ZopfliCalculateBlockSize(const ZopfliLZ77Store* lz77, size_t lstart, size_t lend, int btype);
+
+/* deflate.h:85-86, deflate.c:610-621.  Minimum over the three block types (fixed only considered
+ * for stores of at most 1000 symbols, as in the reference). */
+double ZopfliCalculateBlockSizeAutoType(const ZopfliLZ77Store* lz77, size_t lstart, size_t lend);
+
 /* gzip_container.h:42-44, gzip_container.c:84-124 */
 void ZopfliGzipCompress(const ZopfliOptions* options,
                         const unsigned char* in, size_t insize,

@@ -238,3 +238,48 @@ def test_batched_split_scheduler_matches_reference(ref, host, budget):
         for (d, ll, dd), g in zip(stores, got):
             want = ref.block_split_lz77(d, ll, dd, maxblocks=maxblocks)
             assert np.array_equal(g, want), (len(d), maxblocks, budget)
+
+
+def test_deflate_h_block_size_entry_points(ref, host):
+    """ZopfliCalculateBlockSize / ...AutoType (deflate.h:79-86) take the reference's own
+    ZopfliLZ77Store: a store BUILT BY THE REFERENCE is priced by both libraries."""
+    import ctypes as C
+
+    class Store(C.Structure):  # lz77.h:44-62
+        _fields_ = [("litlens", C.POINTER(C.c_ushort)), ("dists", C.POINTER(C.c_ushort)), ("size", C.c_size_t),
+                    ("data", C.c_void_p), ("pos", C.c_void_p), ("ll_symbol", C.c_void_p), ("d_symbol", C.c_void_p),
+                    ("ll_counts", C.c_void_p), ("d_counts", C.c_void_p)]
+
+    class BlockState(C.Structure):  # lz77.h:86-97
+        _fields_ = [("options", C.c_void_p), ("lmc", C.c_void_p), ("blockstart", C.c_size_t), ("blockend", C.c_size_t)]
+
+    for lib in (ref.lib, host.lib):
+        for f in (lib.ZopfliCalculateBlockSize, lib.ZopfliCalculateBlockSizeAutoType):
+            f.restype = C.c_double
+        lib.ZopfliCalculateBlockSize.argtypes = [C.POINTER(Store), C.c_size_t, C.c_size_t, C.c_int]
+        lib.ZopfliCalculateBlockSizeAutoType.argtypes = [C.POINTER(Store), C.c_size_t, C.c_size_t]
+    for data in (TXT[:90000], corpus.random_bytes(5000), TXT[:700], corpus.adv_runs()[:50000]):
+        arr = np.frombuffer(data + b"\0" * 16, np.uint8)
+        o = zb.ZopfliOptions(0, 0, 1, 1, 0, 15)
+        st, bs = Store(), BlockState()
+        ref.lib.ZopfliInitLZ77Store(C.c_void_p(arr.ctypes.data), C.byref(st))
+        ref.lib.ZopfliInitBlockState(C.byref(o), C.c_size_t(0), C.c_size_t(len(data)), 0, C.byref(bs))
+        ref.lib.ZopfliAllocHash.restype = None
+        hbuf = C.create_string_buffer(256)  # ZopfliHash (hash.h:29-47): a few pointers and ints
+        ref.lib.ZopfliAllocHash(C.c_size_t(32768), hbuf)
+        ref.lib.ZopfliLZ77Greedy(C.byref(bs), C.c_void_p(arr.ctypes.data), C.c_size_t(0), C.c_size_t(len(data)), C.byref(st), hbuf)
+        n = st.size
+        assert n > 0
+        rng = np.random.default_rng(n)
+        ranges = [(0, n), (0, 0), (n // 3, n // 3 + 1), (n // 4, 3 * n // 4)] + \
+                 [tuple(sorted(rng.integers(0, n + 1, 2))) for _ in range(12)]
+        for a, b in ranges:
+            a, b = int(a), int(b)
+            for btype in (0, 1, 2):
+                assert ref.lib.ZopfliCalculateBlockSize(C.byref(st), a, b, btype) == \
+                    host.lib.ZopfliCalculateBlockSize(C.byref(st), a, b, btype), (len(data), a, b, btype)
+            assert ref.lib.ZopfliCalculateBlockSizeAutoType(C.byref(st), a, b) == \
+                host.lib.ZopfliCalculateBlockSizeAutoType(C.byref(st), a, b), (len(data), a, b)
+        ref.lib.ZopfliCleanHash(hbuf)
+        ref.lib.ZopfliCleanBlockState(C.byref(bs))
+        ref.lib.ZopfliCleanLZ77Store(C.byref(st))

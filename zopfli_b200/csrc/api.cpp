@@ -432,6 +432,14 @@ double ZopfliB200HostBlockSize(const unsigned char* in, const unsigned short* li
   return (double)dynamic_block_bits(h, nullptr, nullptr, s);
 }
 
+double ZopfliCalculateBlockSize(const ZopfliLZ77Store* lz77, size_t lstart, size_t lend, int btype) {
+  return ZopfliB200HostBlockSize(lz77->data, lz77->litlens, lz77->dists, lz77->size, lstart, lend, btype);
+}
+
+double ZopfliCalculateBlockSizeAutoType(const ZopfliLZ77Store* lz77, size_t lstart, size_t lend) {
+  return ZopfliB200HostBlockSize(lz77->data, lz77->litlens, lz77->dists, lz77->size, lstart, lend, -1);
+}
+
 uint64_t ZopfliB200HostEmitBlock(const unsigned char* in, const unsigned short* litlens,
                                  const unsigned short* dists, size_t n, size_t lstart, size_t lend, int btype,
                                  int final, unsigned char* out, size_t cap) {
