@@ -184,6 +184,10 @@ def test_chunk_pipelines(ref, mock, monkeypatch):
         monkeypatch.setenv("ZOPFLI_B200_FORCE_CHUNKS", str(chunks))
         monkeypatch.setenv("ZOPFLI_B200_GIANT", "60000")
         assert mock.compress(data, 2, numiterations=1) == want, chunks
+    # a pipeline takes its master blocks in batches (bounded device memory on GiB inputs)
+    monkeypatch.setenv("ZOPFLI_B200_FORCE_CHUNKS", "2")
+    monkeypatch.setenv("ZOPFLI_B200_BATCH", "1")
+    assert mock.compress(data, 2, numiterations=1) == want
 
 
 def test_splice_many_small_parts_all_bit_phases(ref, mock):

@@ -457,10 +457,26 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
     if (nchunks < 1) nchunks = 1;
     std::vector<std::vector<size_t>> chunks(nchunks);
     for (size_t m = 0; m < nm; m++) chunks[m * nchunks / nm].push_back(m);
+    // A pipeline takes its master blocks in batches: device memory is ~100 B per position of a
+    // batch per lane pair, so 32 master blocks per batch keep a 1 GiB input (C3) at ~13 GB of arenas
+    // where one batch per pipeline would need ~110 GB.  The 100 MB bench runs one batch per pipeline.
+    size_t batch = 32;
+    if (const char* e = getenv("ZOPFLI_B200_BATCH")) batch = std::max<size_t>(1, (size_t)atoi(e));
+    auto run_pipeline = [&](size_t c) {
+      const std::vector<size_t>& all = chunks[c];
+      for (size_t a = 0; a < all.size(); a += batch) {
+        std::vector<size_t> part(all.begin() + a, all.begin() + std::min(all.size(), a + batch));
+        run_chunk(part, (int)(2 * c), (int)(2 * c + 1));
+        for (size_t m : part) {  // the stores of finished master blocks are no longer needed
+          M[m].lz77 = Lz77Store();
+          std::vector<Lz77Store>().swap(M[m].fixedstores);
+          std::vector<Lz77Store>().swap(M[m].blockstores);
+        }
+      }
+    };
     std::vector<std::thread> th;
-    for (size_t c = 1; c < nchunks; c++)
-      th.emplace_back([&, c] { run_chunk(chunks[c], (int)(2 * c), (int)(2 * c + 1)); });
-    run_chunk(chunks[0], 0, 1);
+    for (size_t c = 1; c < nchunks; c++) th.emplace_back([&, c] { run_pipeline(c); });
+    run_pipeline(0);
     for (auto& t : th) t.join();
   }
   for (size_t m = 0; m < nm; m++)
