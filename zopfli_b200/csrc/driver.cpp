@@ -12,6 +12,7 @@
 //   stage F  host  bit emission per block (threaded) + bit-offset splice
 #include "driver.hpp"
 
+#include <sched.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -52,11 +53,32 @@ void debug_mark(int chunk, const char* what) {
   if (debug_on()) fprintf(stderr, "[zb] %8.1f ms  chunk %d  %s\n", now_ms() - g_debug_t0, chunk, what);
 }
 
+// CPUs this process may actually use: affinity mask, capped by the cgroup CPU quota (v2 cpu.max or
+// v1 cfs_quota_us / cfs_period_us) -- a container on a 128-thread host is often limited to a few cores
+int usable_cpus() {
+  int n = (int)std::thread::hardware_concurrency();
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min(n > 0 ? n : 1 << 20, CPU_COUNT(&set));
+  double quota = -1, period = -1;
+  if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+    char q[64];
+    if (fscanf(f, "%63s %lf", q, &period) == 2 && strcmp(q, "max") != 0) quota = atof(q);
+    fclose(f);
+  } else {
+    if (FILE* g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) { if (fscanf(g, "%lf", &quota) != 1) quota = -1; fclose(g); }
+    if (FILE* g = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) { if (fscanf(g, "%lf", &period) != 1) period = -1; fclose(g); }
+  }
+  if (quota > 0 && period > 0) n = std::min(n, (int)(quota / period + 0.999));
+  return n < 1 ? 1 : n;
+}
+
 int host_threads() {
   static int n = [] {
-    const char* e = getenv("ZOPFLI_B200_THREADS");
-    int v = e ? atoi(e) : (int)std::thread::hardware_concurrency();
-    return v < 1 ? 1 : (v > 256 ? 256 : v);
+    if (const char* e = getenv("ZOPFLI_B200_THREADS")) { int v = atoi(e); return v < 1 ? 1 : (v > 256 ? 256 : v); }
+    int v = std::min(usable_cpus(), 32);
+    // one process per GPU (torchrun): the ranks of a box share its cores
+    if (const char* w = getenv("LOCAL_WORLD_SIZE")) { int k = atoi(w); if (k > 1) v = std::max(2, v / k); }
+    return v < 1 ? 1 : v;
   }();
   return n;
 }

@@ -67,7 +67,7 @@ constexpr uint32_t kLogTabN = 1u << 21;
 
 }  // namespace
 
-struct Lane {  // an independent stream + arena set; two lanes let a batch of giant blocks run beside the rest
+struct Lane {  // an independent stream + arena set; chunk pipelines use a pair each (giant blocks beside the rest)
   std::mutex mu;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[2];

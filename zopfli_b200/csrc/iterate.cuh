@@ -1,10 +1,13 @@
-// k_iterate: the whole ZopfliLZ77Optimal loop for one deflate block in one persistent warp
+// k_iterate: the whole ZopfliLZ77Optimal loop for one deflate block in one persistent CTA of two
+// warps -- warp 0 runs the algorithm, warp 1 feeds the forward DP
 // (/root/reference/src/zopfli/squeeze.c:446-526; fixed-tree variant :528-560).
 //
 //   per iteration:  cost model constants (GetCostModelMinCost squeeze.c:163-198)
-//                   forward DP          (GetBestLengths squeeze.c:217-309)   push form, costs in a
-//                                        512-entry shared-memory ring, fp64 add / fp32 store
-//                   trace-back          (TraceBackwards squeeze.c:317-336)   shared-memory windows
+//                   forward DP          (GetBestLengths squeeze.c:217-309)   push form, pending costs
+//                                        of the next 32 targets in a register window, longer edges
+//                                        in a 512-entry shared-memory ring, fp64 add / fp32 store
+//                   trace-back          (TraceBackwards squeeze.c:317-336)   speculative multi-start
+//                                        chase in shared-memory windows
 //                   follow + histogram  (FollowPath squeeze.c:338-389)       table lookups, 32 wide
 //                   exact block size    (ZopfliCalculateBlockSize deflate.c:584-608)
 //                   statistics          (squeeze.c:496-518, tree.c:71-94, RNG squeeze.c:80-107)

@@ -13,7 +13,7 @@
 //                 at a time, replay the sequential best/sublen/switch/hop-cap
 //                 semantics with warp scans; emits (len,dist) and the run list
 //   k_greedy      lazy-matching greedy parse over the (len,dist) table      lz77.c:544-630
-//   k_iterate     persistent warp per block: forward DP, trace-back, follow-path, histogram,
+//   k_iterate     persistent CTA per block (DP warp + feeder warp): forward DP, trace-back, follow-path, histogram,
 //                 exact dynamic-block size, statistics / entropy / randomisation -- the whole
 //                 ZopfliLZ77Optimal loop with no host round trip            squeeze.c:217-526
 //
