@@ -277,16 +277,27 @@ int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in,
     Engine::get().set_input_host(in + base, end - base);
   }
   deflate_units(options, 2, final != 0, in, units, base, pieces);
-  for (auto& p : pieces) {
-    unsigned char hdr[10];
-    hdr[0] = p.stored ? 1 : 0;
-    hdr[1] = p.final ? 1 : 0;
-    uint64_t v = p.stored ? (uint64_t)(p.inend - p.instart) : p.bits.nbits;
-    memcpy(hdr + 2, &v, 8);
-    append_bytes(hdr, 10, span, spansize);
-    if (p.stored) append_bytes(in + p.instart, p.inend - p.instart, span, spansize);
-    else append_bytes(p.bits.bytes.data(), p.bits.bytes.size(), span, spansize);
-  }
+  // one allocation for the whole span, pieces copied side by side
+  std::vector<size_t> off(pieces.size() + 1, 0);
+  for (size_t i = 0; i < pieces.size(); i++)
+    off[i + 1] = off[i] + 10 + (pieces[i].stored ? pieces[i].inend - pieces[i].instart : pieces[i].bits.bytes.size());
+  unsigned char* dst = append_reserve(off[pieces.size()], span, spansize);
+  std::vector<std::thread> th;
+  const size_t nt = std::min<size_t>(8, pieces.size());
+  for (size_t t = 0; t < nt; t++)
+    th.emplace_back([&, t] {
+      for (size_t i = t; i < pieces.size(); i += nt) {
+        const Piece& p = pieces[i];
+        unsigned char* d = dst + off[i];
+        d[0] = p.stored ? 1 : 0;
+        d[1] = p.final ? 1 : 0;
+        uint64_t v = p.stored ? (uint64_t)(p.inend - p.instart) : p.bits.nbits;
+        memcpy(d + 2, &v, 8);
+        if (p.stored) memcpy(d + 10, in + p.instart, p.inend - p.instart);
+        else if (!p.bits.bytes.empty()) memcpy(d + 10, p.bits.bytes.data(), p.bits.bytes.size());
+      }
+    });
+  for (auto& t : th) t.join();
   return 0;
 }
 

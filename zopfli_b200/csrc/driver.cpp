@@ -517,6 +517,18 @@ size_t pow2_ceil(size_t v) {
 }
 }  // namespace
 
+// grows the buffer by n bytes under the same capacity rule and returns where they go
+unsigned char* append_reserve(size_t n, unsigned char** out, size_t* outsize) {
+  size_t s = *outsize, ns = s + n;
+  if (n == 0) return *out ? *out + s : nullptr;
+  size_t cap = s == 0 ? 0 : pow2_ceil(s), ncap = pow2_ceil(ns);
+  if (s == 0) *out = (unsigned char*)malloc(ncap);
+  else if (ncap != cap) *out = (unsigned char*)realloc(*out, ncap);
+  if (!*out) { fprintf(stderr, "zopfli-b200: out of memory\n"); exit(EXIT_FAILURE); }
+  *outsize = ns;
+  return *out + s;
+}
+
 void append_bytes(const unsigned char* src, size_t n, unsigned char** out, size_t* outsize) {
   if (n == 0) return;
   size_t s = *outsize, ns = s + n;

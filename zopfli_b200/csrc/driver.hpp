@@ -33,6 +33,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
 void splice_pieces(const std::vector<Piece>& pieces, const unsigned char* in, unsigned char* bp,
                    unsigned char** out, size_t* outsize);
 
+unsigned char* append_reserve(size_t n, unsigned char** out, size_t* outsize);
 void append_bytes(const unsigned char* src, size_t n, unsigned char** out, size_t* outsize);
 
 }  // namespace zb
