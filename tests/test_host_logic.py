@@ -180,7 +180,7 @@ def test_chunk_pipelines(ref, mock, monkeypatch):
     (driver.cpp run_chunk); the output is the master blocks' pieces in order, whatever the chunking."""
     data = TXT + corpus.synth_binary(900000, 3)   # 4 master blocks
     want = ref.compress(data, 2, numiterations=1)
-    for chunks in (1, 2, 3, 4):
+    for chunks in (1, 3, 4):
         monkeypatch.setenv("ZOPFLI_B200_FORCE_CHUNKS", str(chunks))
         monkeypatch.setenv("ZOPFLI_B200_GIANT", "60000")
         assert mock.compress(data, 2, numiterations=1) == want, chunks
