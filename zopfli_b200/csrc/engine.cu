@@ -71,6 +71,9 @@ struct Lane {  // an independent stream + arena set; chunk pipelines use a pair 
   std::mutex mu;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[2];
+#ifdef ZB_VAR_SIG
+  DevBuf sig1, sig2, h2b;
+#endif
   DevBuf segs, keywork, poswork, order, hv, hv2, idx1, idx2, rank1, rank2, bkt1, bkt2, ld, mlen, runs, dsx,
       ovf, la, path, st[4], jobs, out_ll, out_d, counters, misc;
   // split service
@@ -94,6 +97,9 @@ struct Lane {  // an independent stream + arena set; chunk pipelines use a pair 
                      &out_d, &counters, &misc, &sp_ll, &sp_d, &sp_llsym, &sp_dsym, &sp_pos, &sp_snaps, &sp_stores,
                      &sp_work, &sp_evals, &sp_out};
     for (DevBuf* d : all) d->st = stream;
+#ifdef ZB_VAR_SIG
+    sig1.st = sig2.st = h2b.st = stream;
+#endif
   }
   void tic() { CK(cudaEventRecord(ev[0], stream)); }
   void toc(double& a) {
@@ -245,6 +251,11 @@ struct Engine::Impl {
     l.hv2.ensure(L.nkeys * 2 + 64);
     l.idx1.ensure(L.nkeys * 4 + 64);
     l.idx2.ensure(L.nkeys * 4 + 64);
+#ifdef ZB_VAR_SIG
+    l.sig1.ensure(L.nkeys * 8 + 64);
+    l.sig2.ensure(L.nkeys * 8 + 64);
+    l.h2b.ensure(L.nkeys * 2 + 64);
+#endif
     l.rank1.ensure(L.nkeys * 4 + 64);
     l.rank2.ensure(L.nkeys * 4 + 64);
     l.bkt1.ensure(ns * 32769 * 4 + 64);
@@ -275,6 +286,11 @@ struct Engine::Impl {
     b.hv2 = l.hv2.as<uint16_t>();
     b.idx1 = l.idx1.as<uint32_t>();
     b.idx2 = l.idx2.as<uint32_t>();
+#ifdef ZB_VAR_SIG
+    b.sig1 = l.sig1.as<uint64_t>();
+    b.sig2 = l.sig2.as<uint64_t>();
+    b.h2b = l.h2b.as<uint16_t>();
+#endif
     b.rank1 = l.rank1.as<uint32_t>();
     b.rank2 = l.rank2.as<uint32_t>();
     b.bkt1 = l.bkt1.as<uint32_t>();
@@ -351,6 +367,9 @@ void Engine::set_stream(void* s) {
                      &l.sp_d, &l.sp_llsym, &l.sp_dsym, &l.sp_pos, &l.sp_snaps, &l.sp_stores, &l.sp_work, &l.sp_evals,
                      &l.sp_out, &p_->in_buf, &p_->same_buf, &p_->tile_first, &p_->next_tile, &p_->logtab};
     for (DevBuf* d : all) d->st = l.stream;
+#ifdef ZB_VAR_SIG
+    l.sig1.st = l.sig2.st = l.h2b.st = l.stream;
+#endif
   }
 }
 

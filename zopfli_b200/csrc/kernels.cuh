@@ -79,6 +79,13 @@ struct Batch {
   uint32_t* rank2;
   uint32_t* bkt1;   // [nsegs][32769] counts -> starts
   uint32_t* bkt2;
+#ifdef ZB_VAR_SIG
+  // experiment (off by default): the first eight bytes of every bucket entry's position and its
+  // hashval2 travel with the bucket, so a candidate is read at random only when those agree
+  uint64_t* sig1;
+  uint64_t* sig2;
+  uint16_t* h2b;    // hv2 of idx1's entries, in bucket order
+#endif
   // match table
   uint32_t* ld;     // [npos] (len << 16) | dist of the longest match (raw, len may be 0/1/2)
   uint16_t* mlen;   // [npos] longest length or 0 (optimal segments only); bit 15 = long-run
@@ -113,6 +120,10 @@ __device__ __forceinline__ uint32_t ld_u32_unaligned(const uint8_t* p) {
   const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
   uint32_t lo = __ldg(w), hi = __ldg(w + 1);
   return __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8);
+}
+
+__device__ __forceinline__ uint64_t ld_u64_unaligned(const uint8_t* p) {
+  return (uint64_t)ld_u32_unaligned(p) | ((uint64_t)ld_u32_unaligned(p + 4) << 32);
 }
 
 // common prefix of in[a..] and in[b..], capped at limit; starts comparing at offset `from`
@@ -295,6 +306,10 @@ __global__ void __launch_bounds__(32) k_scatter(Batch b) {
   const uint16_t* key = (second ? b.hv2 : b.hv) + sd.key_off;
   uint32_t* idx = (second ? b.idx2 : b.idx1) + sd.key_off;
   uint32_t* rank = (second ? b.rank2 : b.rank1) + sd.key_off;
+#ifdef ZB_VAR_SIG
+  uint64_t* sig = (second ? b.sig2 : b.sig1) + sd.key_off;
+  const uint8_t* kbytes = b.in + sd.winstart;  // byte of key index 0
+#endif
   const uint32_t lane = threadIdx.x;
   for (uint32_t i = lane; i < 32768; i += 32) cursor[i] = bs[i];
   __syncwarp();
@@ -322,6 +337,10 @@ __global__ void __launch_bounds__(32) k_scatter(Batch b) {
         const uint32_t d = cur + before;
         idx[d] = i;
         rank[i] = d;
+#ifdef ZB_VAR_SIG
+        sig[d] = ld_u64_unaligned(kbytes + i);
+        if (!second) b.h2b[sd.key_off + d] = b.hv2[sd.key_off + i];
+#endif
       }
     }
   }
@@ -364,6 +383,10 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
       uint32_t lo = bs1[hv[ip]];
       uint32_t cur = b.rank1[sd.key_off + ip];  // next candidate is idx[cur-1]
       const uint8_t* src = wbase + ip;
+#ifdef ZB_VAR_SIG
+      const uint64_t src8 = ld_u64_unaligned(src);
+      const uint64_t* sig = b.sig1 + sd.key_off;
+#endif
       for (;;) {
         uint32_t avail = cur - lo;
         uint32_t take = avail < 32u ? avail : 32u;
@@ -377,12 +400,25 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
           valid = dist < (uint32_t)kWindow;  // lz77.c:464
         }
         bool h2eq = false;
+#ifdef ZB_VAR_SIG
+        if (valid) {
+          // common prefix from the bucket's own copy of the candidate's first eight bytes; the
+          // candidate itself is read only when all eight agree (the lz77.c:478 pre-check is
+          // implied: a candidate that differs at offset `best` has m <= best)
+          const uint64_t x = sig[cur - 1 - lane] ^ src8;
+          const uint32_t m8 = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8u;
+          if (m8 < 8u || limit <= 8u) m = m8 < limit ? m8 : limit;
+          else m = match_len(src, wbase + iq, 8, limit);
+          if (!chain2) h2eq = b.h2b[sd.key_off + cur - 1 - lane] == v2;
+        }
+#else
         if (valid) {
           const uint8_t* cand = wbase + iq;
           // lz77.c:478-479: a candidate that differs at offset `best` cannot beat it
           if (src[best] == cand[best]) m = match_len(src, cand, 0, limit);
           if (!chain2) h2eq = hv2[iq] == v2;
         }
+#endif
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
         const uint32_t nv = __popc(vmask);  // valid lanes form a prefix (distances increase)
         if (nv == 0) break;
@@ -425,6 +461,9 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
         if (do_switch) {  // lz77.c:509-519: continue from this candidate along chain 2
           uint32_t iqs = __shfl_sync(0xffffffffu, iq, s);
           chain2 = true;
+#ifdef ZB_VAR_SIG
+          sig = b.sig2 + sd.key_off;
+#endif
           idx = b.idx2 + sd.key_off;
           lo = bs2[v2];
           cur = b.rank2[sd.key_off + iqs];
