@@ -125,6 +125,13 @@ __device__ __forceinline__ double round_to_f32(double x) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifdef ZB_VAR_XCH_SPLIT
+#define ZB_XCH_LOAD(a, c, code) { (c) = lds_f64(a); (code) = lds_u32((a) + 8); }
+#define ZB_XCH_STORE(a, c, code, p) { sts_f64_if((a), (c), (p)); sts_u32_if((a) + 8, (code), (p)); }
+#else
+#define ZB_XCH_LOAD(a, c, code) lds_ring((a), (c), (code))
+#define ZB_XCH_STORE(a, c, code, p) sts_ring_if((a), (c), (code), (p))
+#endif
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar_a) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_a) : "memory");
 }
@@ -148,6 +155,12 @@ __device__ __forceinline__ void sts_u16_if(uint32_t a, uint32_t v, bool p) {
 }
 __device__ __forceinline__ void sts_f64(uint32_t a, double c) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(c) : "memory");
+}
+// The hand-off slot {cost, code} of the DP window.  Default: one 16-byte entry, LDS.128 / STS.128.
+// -DZB_VAR_XCH_SPLIT (experiment, off by default): 8 + 4 byte accesses at a + 0 / a + 8, which need no
+// aligned register quad (the 128-bit form costs a few register moves per step).
+__device__ __forceinline__ void sts_u32_if(uint32_t a, uint32_t v, bool p) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.u32 [%0], %1; }" ::"r"(a), "r"(v), "r"((uint32_t)p) : "memory");
 }
 // ring entry {cost, code}
 __device__ __forceinline__ void lds_ring(uint32_t a, double& c, uint32_t& code) {
@@ -649,7 +662,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         const uint32_t ds3_ = lds_u8(dsx_s + (((U) + 3) * 32));                                             \
         const double llb2_ = lds_f64(gl_s + (((U) + 2) * 8));                                               \
         double en_c_; uint32_t en_l_;                                                                       \
-        lds_ring(xch_r + ((((U) + 3) & 3) * 16), en_c_, en_l_);   /* pending(j+2), made at step j-1 */       \
+        ZB_XCH_LOAD(xch_r + ((((U) + 3) & 3) * 16), en_c_, en_l_);   /* pending(j+2), made at step j-1 */    \
         double inc_ = kInfD; uint32_t inl_ = 0;                                                             \
         if (RING) { lds_ring(ring_s + (U) * 16, inc_, inl_); sts_f64_if(ring_s + (U) * 16, kInfD, is_l0); } \
         sts_u16_if(lac_s + (U) * 2, lfin_prev, is_l0);                                                      \
@@ -666,7 +679,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         w = ok_ ? rn_ : w;                                                                                  \
         wl = ok_ ? sidx : wl;                                                                               \
         const bool mine_ = lane_rot == (uint32_t)(U);   /* this lane's target is j+3: complete now */       \
-        sts_ring_if(xch_r + (((U) & 3) * 16), w, wl, mine_);                                                \
+        ZB_XCH_STORE(xch_r + (((U) & 3) * 16), w, wl, mine_);                                               \
         if (mine_) { w = inc_; wl = inl_; }                                                                 \
         sidx++;                                                                                             \
         e2c = en_c_; e2l = en_l_;                                                                           \
@@ -737,7 +750,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
             const uint32_t ds3 = lds_u8(dsx_c + (jl + 3) * 32);   // rows 32.. are the next stage (or its mirror)
             const double llb2 = lds_f64(gl_c + (jl + 2) * 8);
             double en_c; uint32_t en_l;
-            lds_ring(xch_r + ((j + 3) & 3) * 16, en_c, en_l);  // pending(j+2), made at step j-1
+            ZB_XCH_LOAD(xch_r + ((j + 3) & 3) * 16, en_c, en_l);  // pending(j+2), made at step j-1
             sts_u16_if(lac_c + jl * 2, lfin_prev, is_l0);
             const uint32_t m16 = lds_u16(mk_r + st * 64 + jl * 2);
             const uint32_t ml = m16 & 0x7fffu;
@@ -807,7 +820,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
             // target j+3 is complete for every length edge: hand it to the chain; its lane takes
             // on target j+35, whose ring entry (edges longer than 34) is complete as well
             const uint32_t src = (j + 3) & 31;
-            sts_ring_if(xch_r + (j & 3) * 16, w, wl, lane == src);
+            ZB_XCH_STORE(xch_r + (j & 3) * 16, w, wl, lane == src);
             double inc = kInfD; uint32_t inl = 0;
             __syncwarp();
             if (j + 35 <= dirty_until) {
