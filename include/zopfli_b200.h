@@ -87,9 +87,16 @@ int ZopfliB200HostLengthLimited(const uint32_t* freq, int n, int maxbits, unsign
 int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in, size_t insize,
                           const unsigned char* dev_in, size_t start, size_t end, int final,
                           unsigned char** span, size_t* spansize);
-/* Splices a span onto a stream whose last byte has *bp bits in use (bit-offset scan). */
-void ZopfliB200AppendSpan(const unsigned char* span, size_t spansize, unsigned char* bp,
-                          unsigned char** out, size_t* outsize);
+/* Splices a span onto a stream whose last byte has *bp bits in use (bit-offset scan).  The span is
+ * validated first (record sizes against spansize); returns 1 and leaves the output untouched if
+ * it is truncated or malformed. */
+int ZopfliB200AppendSpan(const unsigned char* span, size_t spansize, unsigned char* bp,
+                         unsigned char** out, size_t* outsize);
+/* Bit offset, relative to the first bit the call wrote, at which each master block (deflate.c:
+ * 908-931) of the most recent ZopfliDeflate / ZopfliCompress call starts, plus the end offset as last
+ * entry.  Returns the number of entries (master blocks + 1).  Lets a checker compare sampled master
+ * blocks of one big stream with the reference's ZopfliDeflatePart of the same range. */
+size_t ZopfliB200LastMasterBitOffsets(uint64_t* offsets, size_t cap);
 /* ZopfliCompress with the input already resident on the device (bench `value` leg). */
 void ZopfliB200CompressDevice(const ZopfliOptions* options, ZopfliFormat output_type,
                               const unsigned char* in, size_t insize, const unsigned char* dev_in,

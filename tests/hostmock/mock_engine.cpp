@@ -18,13 +18,18 @@ namespace zb {
 
 struct Engine::Impl {
   std::vector<uint8_t> in;
+  std::vector<zb::Lz77Store> split_stores[Engine::kLanes];  // one set per lane, as in the engine
 };
 
 Engine::Engine() : p_(new Impl) {}
-Engine& Engine::get() {
-  static Engine* e = new Engine;
-  return *e;
+Engine* Engine::acquire() { return new Engine; }  // one fresh mock context per call
+void Engine::release(Engine* e) { delete e->p_; e->p_ = nullptr; }
+EngineStats Engine::stats_all() {
+  EngineStats s;
+  memset(&s, 0, sizeof(s));
+  return s;
 }
+void Engine::reset_stats_all() {}
 int Engine::device() const { return -1; }
 void Engine::set_stream(void*) {}
 EngineStats Engine::stats() {
@@ -64,10 +69,9 @@ uint64_t Engine::device_block_bits(const uint32_t*) { return 0; }
 
 // split service of the mock: the product's own HOST estimators (lz77_store.hpp), so the batched
 // scheduler (batched_split.hpp) is exercised on CPU exactly as the driver uses it
-static std::vector<zb::Lz77Store> g_split_stores_lane[Engine::kLanes];  // one set per lane, as in the engine
 void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vector<uint64_t>& off,
                          const std::vector<uint32_t>& size, int lane) {
-  std::vector<zb::Lz77Store>& g_split_stores = g_split_stores_lane[(unsigned)lane % kLanes];
+  std::vector<zb::Lz77Store>& g_split_stores = p_->split_stores[(unsigned)lane % kLanes];
   g_split_stores.clear();
   g_split_stores.resize(off.size());
   for (size_t i = 0; i < off.size(); i++) {
@@ -76,7 +80,7 @@ void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vecto
   }
 }
 void Engine::greedy_to_split(const std::vector<ParseRange>& r, std::vector<uint32_t>& sizes, int lane) {
-  std::vector<zb::Lz77Store>& g_split_stores = g_split_stores_lane[(unsigned)lane % kLanes];
+  std::vector<zb::Lz77Store>& g_split_stores = p_->split_stores[(unsigned)lane % kLanes];
   g_split_stores.clear();
   g_split_stores.resize(r.size());
   sizes.assign(r.size(), 0);
@@ -91,12 +95,12 @@ void Engine::greedy_to_split(const std::vector<ParseRange>& r, std::vector<uint3
   }
 }
 void Engine::split_positions(const std::vector<SplitPos>& q, std::vector<uint32_t>& bytepos, int lane) {
-  std::vector<zb::Lz77Store>& g_split_stores = g_split_stores_lane[(unsigned)lane % kLanes];
+  std::vector<zb::Lz77Store>& g_split_stores = p_->split_stores[(unsigned)lane % kLanes];
   bytepos.assign(q.size(), 0);
   for (size_t i = 0; i < q.size(); i++) bytepos[i] = (uint32_t)g_split_stores[q[i].store].pos[q[i].idx];
 }
 void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lane) {
-  std::vector<zb::Lz77Store>& g_split_stores = g_split_stores_lane[(unsigned)lane % kLanes];
+  std::vector<zb::Lz77Store>& g_split_stores = p_->split_stores[(unsigned)lane % kLanes];
   static thread_local DynScratch s;
   for (size_t i = 0; i < n; i++) costs[i] = auto_type_bits(g_split_stores[reqs[i].store], reqs[i].lstart, reqs[i].lend, s);
 }

@@ -160,7 +160,7 @@ def test_nocopy_result_and_device_input(ref, lib):
 
 
 def test_pipeline_shapes_give_one_stream(ref):
-    """Chunk pipelines, the giant-block lane split and the host/device split service are scheduling
+    """Chunk pipelines, the giant-block lane split and the host thread count are scheduling
     choices: every combination must produce the reference's bytes.  The switches are read once per
     process, hence subprocesses."""
     import os, subprocess, sys, tempfile
@@ -174,7 +174,37 @@ def test_pipeline_shapes_give_one_stream(ref):
                 "open(sys.argv[1], 'wb').write(zb.compress(d, zb.ZOPFLI_FORMAT_DEFLATE, numiterations=2))" % (root, src))
         for i, env in enumerate([{"ZOPFLI_B200_FORCE_CHUNKS": "3", "ZOPFLI_B200_GIANT": "50000"},
                                  {"ZOPFLI_B200_FORCE_CHUNKS": "2", "ZOPFLI_B200_GIANT": "100000000"},
-                                 {"ZOPFLI_B200_HOST_SPLIT": "1"}]):
+                                 {"ZOPFLI_B200_CONTEXTS": "1", "ZOPFLI_B200_THREADS": "3"}]):
             out = os.path.join(td, "out%d.bin" % i)
             subprocess.check_call([sys.executable, "-c", code, out], env=dict(os.environ, **env))
             assert open(out, "rb").read() == want, env
+
+
+def test_reentrant_concurrent_calls(ref, lib):
+    """The reference keeps no mutable globals (zopfli.h:82-88): concurrent calls on different inputs
+    must not disturb each other.  Eight threads x different inputs x mixed formats / entry points,
+    twice as many callers as engine contexts, all compared with the reference."""
+    import threading
+    inputs = [TXT[:300000], corpus.synth_binary(250000), corpus.adv_runs(), TXT[1000000:1250000],
+              corpus.mixed_small(120000), TXT[500000:1700000], corpus.adv_collide(), b"", ]
+    want, got, errs = {}, {}, []
+    for i, d in enumerate(inputs):
+        want[i] = (ref.compress(d, i % 3, numiterations=3), ref.deflate_part(d, 0, len(d) // 2, final=0, numiterations=2))
+
+    def work(i):
+        try:
+            d = inputs[i]
+            for _ in range(2):
+                got[i] = (lib.compress(d, i % 3, numiterations=3), lib.deflate_part(d, 0, len(d) // 2, final=0, numiterations=2))
+                if got[i] != want[i]:
+                    errs.append(i)
+        except Exception as e:  # pragma: no cover
+            errs.append((i, repr(e)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(inputs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    assert got == want

@@ -287,3 +287,30 @@ def test_deflate_h_block_size_entry_points(ref, host):
         ref.lib.ZopfliCleanHash(hbuf)
         ref.lib.ZopfliCleanBlockState(C.byref(bs))
         ref.lib.ZopfliCleanLZ77Store(C.byref(st))
+
+
+def test_concurrent_calls_and_span_validation(ref, mock):
+    """API-level state (engine lease, layout / timing globals, lazy CRC table) under concurrent callers,
+    and ZopfliB200AppendSpan's rejection of truncated spans."""
+    import threading
+    inputs = [corpus.synth_text(60000, 21), corpus.synth_binary(50000), corpus.adv_runs()[:40000], b"", b"abc" * 3000,
+              corpus.mixed_small(30000)]
+    want = [ref.compress(d, i % 3, numiterations=2) for i, d in enumerate(inputs)]
+    got = [None] * len(inputs)
+
+    def work(i):
+        got[i] = mock.compress(inputs[i], i % 3, numiterations=2)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(inputs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert got == want
+    span = mock.deflate_span(inputs[0], 0, 1, final=1, numiterations=1)
+    assert mock.splice_spans([span])[0] == ref.compress(inputs[0], 2, numiterations=1)
+    for cut in (1, 9, len(span) - 1):
+        with pytest.raises(ValueError):
+            mock.splice_spans([span[:cut]])
+    offs = mock.last_master_bit_offsets()
+    assert len(offs) >= 2 and offs[0] == 0

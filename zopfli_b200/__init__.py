@@ -48,7 +48,7 @@ EXPORTS = ["ZopfliInitOptions", "ZopfliCompress", "ZopfliDeflate", "ZopfliDeflat
            "ZopfliGzipCompress", "ZopfliZlibCompress", "ZopfliB200LZ77", "ZopfliB200LZ77Batch",
            "ZopfliB200MatchTable", "ZopfliB200DynamicBlockBits", "ZopfliB200DeviceAutoTypeBits", "ZopfliB200HostBlockSplitLZ77",
            "ZopfliB200HostBatchedSplit", "ZopfliB200HostBlockSize", "ZopfliB200HostEmitBlock", "ZopfliB200HostLengthLimited",
-           "ZopfliB200DeflateSpan", "ZopfliB200AppendSpan", "ZopfliB200Crc32", "ZopfliB200Crc32Combine", "ZopfliB200CompressDevice",
+           "ZopfliB200DeflateSpan", "ZopfliB200AppendSpan", "ZopfliB200LastMasterBitOffsets", "ZopfliB200Crc32", "ZopfliB200Crc32Combine", "ZopfliB200CompressDevice",
            "ZopfliB200GetStats", "ZopfliB200ResetStats", "ZopfliB200SetStream", "ZopfliB200Device",
            "ZopfliB200Version"]
 
@@ -126,7 +126,9 @@ class Library:
         L.ZopfliB200DeflateSpan.argtypes = [C.POINTER(ZopfliOptions), vp, sz, vp, sz, sz, C.c_int,
                                             C.POINTER(vp), C.POINTER(sz)]
         L.ZopfliB200AppendSpan.argtypes = [vp, sz, C.POINTER(C.c_ubyte), C.POINTER(vp), C.POINTER(sz)]
-        L.ZopfliB200AppendSpan.restype = None
+        L.ZopfliB200AppendSpan.restype = C.c_int
+        L.ZopfliB200LastMasterBitOffsets.argtypes = [vp, sz]
+        L.ZopfliB200LastMasterBitOffsets.restype = sz
         L.ZopfliB200Crc32.argtypes = [vp, sz]
         L.ZopfliB200Crc32.restype = C.c_uint32
         L.ZopfliB200Crc32Combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
@@ -329,8 +331,15 @@ class Library:
             n = C.c_size_t(len(hdr))
         for s in spans:
             b = np.frombuffer(s, np.uint8)
-            self.lib.ZopfliB200AppendSpan(b.ctypes.data, len(b), C.byref(bp), C.byref(out), C.byref(n))
+            if self.lib.ZopfliB200AppendSpan(b.ctypes.data, len(b), C.byref(bp), C.byref(out), C.byref(n)) != 0:
+                raise ValueError("malformed span")
         return self._take(out, n), bp.value
+
+    def last_master_bit_offsets(self):
+        n = int(self.lib.ZopfliB200LastMasterBitOffsets(None, 0))
+        a = np.zeros(max(n, 1), np.uint64)
+        self.lib.ZopfliB200LastMasterBitOffsets(a.ctypes.data, n)
+        return a[:n].astype(np.int64)
 
     # ---- introspection ----
     def stats(self) -> dict:

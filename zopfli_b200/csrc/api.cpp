@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <chrono>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -13,7 +14,6 @@
 #include "batched_split.hpp"
 #include "driver.hpp"
 #include "engine.hpp"
-#include "host_split.hpp"
 #include "lz77_store.hpp"
 
 using namespace zb;
@@ -24,13 +24,14 @@ double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
+std::mutex g_api_mu;   // guards g_total_ms and g_last_layout
 double g_total_ms = 0;
+std::vector<uint64_t> g_last_layout;  // bit offset of every unit (master block) of the most recent deflate call
 
 // ---- CRC-32 (gzip_container.c:27-81 computes the same polynomial bytewise): slicing-by-8 ----
 uint32_t g_crc_tab[8][256];
-bool g_crc_init = false;
-void crc_init() {
-  if (g_crc_init) return;
+std::once_flag g_crc_once;
+void crc_fill() {
   for (uint32_t i = 0; i < 256; i++) {
     uint32_t c = i;
     for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
@@ -38,8 +39,8 @@ void crc_init() {
   }
   for (uint32_t i = 0; i < 256; i++)
     for (int t = 1; t < 8; t++) g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 255];
-  g_crc_init = true;
 }
+void crc_init() { std::call_once(g_crc_once, crc_fill); }
 uint32_t crc32_range(const unsigned char* p, size_t n, uint32_t crc) {  // crc is the running (inverted) state
   while (n && ((uintptr_t)p & 7)) { crc = g_crc_tab[0][(crc ^ *p++) & 255] ^ (crc >> 8); n--; }
   while (n >= 8) {
@@ -146,21 +147,24 @@ void deflate_impl(const ZopfliOptions* options, int btype, int final, const unsi
   double t0 = now_ms();
   size_t offset = *outsize;
   std::vector<Piece> pieces;
+  Engine::Lease eng;  // this call's private engine context
   if (btype != 0) {
-    if (dev_in) Engine::get().set_input_device(dev_in, insize);
-    else Engine::get().set_input_host(in, insize);
+    if (dev_in) eng->set_input_device(dev_in, insize);
+    else eng->set_input_host(in, insize);
   }
   const double t1 = now_ms();
-  deflate_units(options, btype, final != 0, in, master_units(insize, 0, num_master_blocks(insize)), 0, pieces);
+  deflate_units(*eng, options, btype, final != 0, in, master_units(insize, 0, num_master_blocks(insize)), 0, pieces);
   const double t2 = now_ms();
-  splice_pieces(pieces, in, bp, out, outsize);
+  std::vector<uint64_t> layout;
+  splice_pieces(pieces, in, bp, out, outsize, &layout);
+  { std::lock_guard<std::mutex> g(g_api_mu); g_last_layout.swap(layout); }
   if (api_debug())
     fprintf(stderr, "[zb] api: set_input %.1f ms, deflate_units %.1f ms, splice %.1f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
   if (options->verbose) {
     fprintf(stderr, "Original Size: %lu, Deflate: %lu, Compression: %f%% Removed\n", (unsigned long)insize,
             (unsigned long)(*outsize - offset), 100.0 * (double)(insize - (*outsize - offset)) / (double)insize);
   }
-  g_total_ms += now_ms() - t0;
+  { std::lock_guard<std::mutex> g(g_api_mu); g_total_ms += now_ms() - t0; }
 }
 
 void compress_impl(const ZopfliOptions* options, ZopfliFormat fmt, const unsigned char* in, size_t insize,
@@ -184,7 +188,7 @@ void compress_impl(const ZopfliOptions* options, ZopfliFormat fmt, const unsigne
       fprintf(stderr, "Original Size: %d, Gzip: %d, Compression: %f%% Removed\n", (int)insize, (int)*outsize,
               100.0 * (double)(insize - *outsize) / (double)insize);
   } else if (fmt == ZOPFLI_FORMAT_ZLIB) {  // zlib_container.c:50-79
-    uint32_t checksum = adler32(in, (unsigned)insize);
+    uint32_t checksum = adler32(in, insize);
     unsigned cmfflg = 256 * 120 + 3 * 64;
     cmfflg += 31 - cmfflg % 31;
     put_byte((unsigned char)(cmfflg / 256), out, outsize);
@@ -254,8 +258,9 @@ void ZopfliDeflatePart(const ZopfliOptions* options, int btype, int final, const
   size_t base = instart > (size_t)kWindow ? instart - kWindow : 0;
   base &= ~(size_t)15;
   std::vector<Piece> pieces;
-  if (btype != 0) Engine::get().set_input_host(in + base, inend - base);
-  deflate_units(options, btype, final != 0, in, {{instart, inend}}, base, pieces);
+  Engine::Lease eng;
+  if (btype != 0) eng->set_input_host(in + base, inend - base);
+  deflate_units(*eng, options, btype, final != 0, in, {{instart, inend}}, base, pieces);
   splice_pieces(pieces, in, bp, out, outsize);
 }
 
@@ -269,14 +274,15 @@ int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in,
   if (units.empty() && insize == 0) units.push_back({0, 0});
   if (units.empty()) return 0;
   size_t base = 0;
+  Engine::Lease eng;
   if (dev_in) {
-    Engine::get().set_input_device(dev_in, insize);
+    eng->set_input_device(dev_in, insize);
   } else {
     base = start > (size_t)kWindow ? start - kWindow : 0;
     base &= ~(size_t)15;
-    Engine::get().set_input_host(in + base, end - base);
+    eng->set_input_host(in + base, end - base);
   }
-  deflate_units(options, 2, final != 0, in, units, base, pieces);
+  deflate_units(*eng, options, 2, final != 0, in, units, base, pieces);
   // one allocation for the whole span, pieces copied side by side
   std::vector<size_t> off(pieces.size() + 1, 0);
   for (size_t i = 0; i < pieces.size(); i++)
@@ -304,11 +310,21 @@ int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in,
 uint32_t ZopfliB200Crc32(const unsigned char* data, size_t size) { return crc32_parallel(data, size); }
 uint32_t ZopfliB200Crc32Combine(uint32_t crc1, uint32_t crc2, uint64_t len2) { return crc32_combine(crc1, crc2, len2); }
 
-void ZopfliB200AppendSpan(const unsigned char* span, size_t spansize, unsigned char* bp, unsigned char** out,
-                          size_t* outsize) {
+int ZopfliB200AppendSpan(const unsigned char* span, size_t spansize, unsigned char* bp, unsigned char** out,
+                         size_t* outsize) {
   std::vector<Piece> pieces;
   std::vector<unsigned char> rawbytes;  // stored payloads, addressed through instart/inend
   size_t o = 0;
+  // validate the whole span before touching the output: spans arrive over a transport
+  while (o < spansize) {
+    if (spansize - o < 10 || span[o] > 1 || span[o + 1] > 1) return 1;
+    uint64_t v;
+    memcpy(&v, span + o + 2, 8);
+    const uint64_t nbytes = span[o] == 1 ? v : (v + 7) / 8;
+    if (nbytes > spansize - o - 10) return 1;
+    o += 10 + (size_t)nbytes;
+  }
+  o = 0;
   // first pass: collect stored payloads contiguously so Piece offsets can index one buffer
   while (o + 10 <= spansize) {
     uint64_t v;
@@ -330,12 +346,20 @@ void ZopfliB200AppendSpan(const unsigned char* span, size_t spansize, unsigned c
     o += 10 + nbytes;
   }
   splice_pieces(pieces, rawbytes.data(), bp, out, outsize);
+  return 0;
+}
+
+size_t ZopfliB200LastMasterBitOffsets(uint64_t* offsets, size_t cap) {
+  std::lock_guard<std::mutex> g(g_api_mu);
+  for (size_t i = 0; i < g_last_layout.size() && i < cap; i++) offsets[i] = g_last_layout[i];
+  return g_last_layout.size();
 }
 
 int ZopfliB200LZ77Batch(const unsigned char* in, size_t insize, size_t n, const size_t* instart,
                         const size_t* inend, int mode, int numiterations, unsigned short* litlens,
                         unsigned short* dists, size_t cap, size_t* off, size_t* cnt, uint64_t* cost) {
-  Engine& e = Engine::get();
+  Engine::Lease lease;
+  Engine& e = *lease;
   e.set_input_host(in, insize);
   std::vector<ParseRange> pr(n);
   for (size_t i = 0; i < n; i++) pr[i] = {instart[i], inend[i], mode == 0 ? 1 : (mode == 1 ? 2 : 0), numiterations};
@@ -366,7 +390,8 @@ int ZopfliB200LZ77(const unsigned char* in, size_t insize, size_t instart, size_
 int ZopfliB200MatchTable(const unsigned char* in, size_t insize, size_t instart, size_t inend,
                          unsigned short* length, unsigned short* distance, unsigned short* sublen,
                          unsigned short* same, unsigned short* hashval, unsigned short* hashval2) {
-  Engine& e = Engine::get();
+  Engine::Lease lease;
+  Engine& e = *lease;
   e.set_input_host(in, insize);
   std::vector<uint16_t> l, d, s, sm, h1, h2;
   e.match_table(instart, inend, l, d, s, sm, h1, h2);
@@ -381,14 +406,15 @@ int ZopfliB200MatchTable(const unsigned char* in, size_t insize, size_t instart,
 }
 
 uint64_t ZopfliB200DynamicBlockBits(const uint32_t* hist320, int where) {
-  if (where == 1) return Engine::get().device_block_bits(hist320);
+  if (where == 1) { Engine::Lease e; return e->device_block_bits(hist320); }
   DynScratch s;
   return dynamic_block_bits(hist320, nullptr, nullptr, s);
 }
 
 int ZopfliB200DeviceAutoTypeBits(const unsigned short* litlens, const unsigned short* dists, size_t n, size_t nreq,
                                  const size_t* lstart, const size_t* lend, uint64_t* out) {
-  Engine& e = Engine::get();
+  Engine::Lease lease;
+  Engine& e = *lease;
   std::vector<uint64_t> off{0};
   std::vector<uint32_t> size{(uint32_t)n};
   e.split_begin(litlens, dists, off, size);
@@ -404,11 +430,12 @@ size_t ZopfliB200HostBlockSplitLZ77(const unsigned char* in, const unsigned shor
   (void)in;
   Lz77Store st;
   make_store(litlens, dists, n, st);
-  auto cost = [&st](size_t a, size_t b) {
-    thread_local DynScratch s;
-    return auto_type_bits(st, a, b, s);
-  };
-  std::vector<size_t> p = block_split_lz77(cost, st.size(), maxblocks);
+  // the product's own search (batched_split.hpp) with one store and a serial round: every probe is
+  // priced as the reference would, by the host estimators
+  std::vector<size_t> p = batched_block_split({st.size()}, maxblocks, [&](const std::vector<EvalReq>& q, std::vector<uint64_t>& c) {
+    DynScratch sc;
+    for (size_t i = 0; i < q.size(); i++) c[i] = auto_type_bits(st, q[i].lstart, q[i].lend, sc);
+  }, 0)[0];
   for (size_t i = 0; i < p.size() && i < cap; i++) points[i] = p[i];
   return p.size();
 }
@@ -473,12 +500,12 @@ int ZopfliB200HostLengthLimited(const uint32_t* freq, int n, int maxbits, unsign
 }
 
 void ZopfliB200GetStats(ZopfliB200Stats* o) {
-  EngineStats e = Engine::get().stats();
+  EngineStats e = Engine::stats_all();
   o->ms_same = e.ms_same; o->ms_keys = e.ms_keys; o->ms_scan = e.ms_scan; o->ms_scatter = e.ms_scatter;
   o->ms_match = e.ms_match; o->ms_greedy = e.ms_greedy; o->ms_iterate = e.ms_iterate; o->ms_pack = e.ms_pack;
   o->ms_h2d = e.ms_h2d; o->ms_d2h = e.ms_d2h;
   o->ms_host_split = g_host_times.split; o->ms_host_emit = g_host_times.emit; o->ms_host_other = g_host_times.other;
-  o->ms_total = g_total_ms;
+  { std::lock_guard<std::mutex> g(g_api_mu); o->ms_total = g_total_ms; }
   o->launches = e.launches; o->match_positions = e.match_positions; o->iterate_positions = e.iterate_positions;
   o->iterate_steps = e.iterate_steps; o->h2d_bytes = e.h2d_bytes; o->d2h_bytes = e.d2h_bytes;
   for (int k = 0; k < 6; k++) { o->cyc_sum[k] = e.cyc_sum[k]; o->cyc_max[k] = e.cyc_max[k]; }
@@ -488,13 +515,13 @@ void ZopfliB200GetStats(ZopfliB200Stats* o) {
 }
 
 void ZopfliB200ResetStats(void) {
-  Engine::get().reset_stats();
+  Engine::reset_stats_all();
   g_host_times = HostTimes();
-  g_total_ms = 0;
+  { std::lock_guard<std::mutex> g(g_api_mu); g_total_ms = 0; }
 }
 
-void ZopfliB200SetStream(void* s) { Engine::get().set_stream(s); }
-int ZopfliB200Device(void) { return Engine::get().device(); }
+void ZopfliB200SetStream(void* s) { Engine::Lease e; e->set_stream(s); }
+int ZopfliB200Device(void) { Engine::Lease e; return e->device(); }
 const char* ZopfliB200Version(void) { return "zopfli-b200 0.1 (ABI libzopfli.so.1, reference 1.0.3)"; }
 
 }  // extern "C"

@@ -24,7 +24,6 @@
 #include "batched_split.hpp"
 #include "emit.hpp"
 #include "engine.hpp"
-#include "host_split.hpp"
 #include "lz77_store.hpp"
 
 namespace zb {
@@ -122,18 +121,6 @@ struct Master {
   std::vector<Piece> pieces;
 };
 
-RangeCostFn make_cost(const Lz77Store& st) {
-  return [&st](size_t a, size_t b) {
-    thread_local DynScratch s;
-    return auto_type_bits(st, a, b, s);
-  };
-}
-
-bool host_split_forced() {
-  static int v = [] { const char* e = getenv("ZOPFLI_B200_HOST_SPLIT"); return e && atoi(e) ? 1 : 0; }();
-  return v != 0;
-}
-
 // ZopfliBlockSplitLZ77 for many stores at once, split costs priced by the device (k_split_eval)
 std::vector<std::vector<size_t>> device_block_split(Engine& eng, const uint16_t* ll, const uint16_t* d,
                                                     const std::vector<uint64_t>& off, const std::vector<uint32_t>& size,
@@ -158,16 +145,15 @@ void stored_pieces(size_t a, size_t b, bool final, std::vector<Piece>& out) {
 }  // namespace
 
 // in_base: absolute position of device/engine byte 0 (the engine holds bytes [in_base, ...)).
-void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const unsigned char* in,
+void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_last, const unsigned char* in,
                    const std::vector<std::pair<size_t, size_t>>& units, size_t in_base,
                    std::vector<Piece>& pieces) {
-  Engine& eng = Engine::get();
   const size_t nm = units.size();
   std::vector<Master> M(nm);
   for (size_t m = 0; m < nm; m++) { M[m].ms = units[m].first; M[m].me = units[m].second; }
 
   if (btype == 0) {  // deflate.c:826-828
-    for (size_t m = 0; m < nm; m++) stored_pieces(M[m].ms, M[m].me, final_last && m + 1 == nm, pieces);
+    for (size_t m = 0; m < nm; m++) { stored_pieces(M[m].ms, M[m].me, final_last && m + 1 == nm, pieces); pieces.back().unit = (uint32_t)m; }
     return;
   }
   if (btype == 1) {  // deflate.c:829-841: one fixed-tree optimal parse per unit
@@ -181,6 +167,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
       st.finalize();
       Piece p;
       emit_compressed_block(1, final_last && m + 1 == nm, st, 0, st.size(), p.bits);
+      p.unit = (uint32_t)m;
       pieces.push_back(std::move(p));
     }
     return;
@@ -196,7 +183,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
   debug_mark(cid, "start");
   // ---- stage A: greedy parses (only needed when splitting) ----
   const size_t maxblocks = (size_t)opt->blocksplittingmax;
-  if (opt->blocksplitting && !host_split_forced()) {
+  if (opt->blocksplitting) {
     // the greedy stores never leave the device: they become the stores of the split service, and
     // only the byte positions of the chosen split points come back (blocksplitter.c:303-313)
     std::vector<ParseRange> pr;
@@ -231,33 +218,6 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
     }
     double t2 = now_ms();
     debug_mark(cid, "B split done");
-    add_time(g_host_times.split, t2 - t1);
-    t0 = t2;
-  } else if (opt->blocksplitting) {  // ZOPFLI_B200_HOST_SPLIT=1: the reference's search on the host estimators
-    std::vector<ParseRange> pr;
-    for (size_t m : cm) pr.push_back({M[m].ms - in_base, M[m].me - in_base, 0, 0});
-    ParseResult res;
-    eng.parse(pr, res, lane_r);
-    double t1 = now_ms();
-    add_time(g_host_times.other, t1 - t0);
-    parallel_for(nc, [&](size_t q) {
-      Master& mb = M[cm[q]];
-      mb.greedy.append(res.ll.data() + res.off[q], res.d.data() + res.off[q], res.size[q], mb.ms);
-      mb.greedy.finalize();
-      std::vector<size_t> lp = block_split_lz77(make_cost(mb.greedy), mb.greedy.size(), maxblocks);
-      // LZ77 indices -> byte positions (blocksplitter.c:303-313)
-      const uint16_t* ll = res.ll.data() + res.off[q];
-      const uint16_t* dd = res.d.data() + res.off[q];
-      mb.cuts.push_back(mb.ms);
-      size_t pos = mb.ms, k = 0;
-      for (size_t i = 0; i < res.size[q] && k < lp.size(); i++) {
-        if (lp[k] == i) { mb.cuts.push_back(pos); k++; }
-        pos += dd[i] == 0 ? 1 : ll[i];
-      }
-      mb.cuts.push_back(mb.me);
-      mb.greedy.clear();
-    });
-    double t2 = now_ms();
     add_time(g_host_times.split, t2 - t1);
     t0 = t2;
   } else {
@@ -322,7 +282,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
       std::vector<std::vector<size_t>> second(nq);
       std::vector<char> want2(nq, 0);
       for (size_t q = 0; q < nq; q++) want2[q] = opt->blocksplitting && first_points[q].size() > 1;  // deflate.c:872
-      if (!host_split_forced()) {
+      {
         std::vector<uint64_t> off;
         std::vector<uint32_t> size;
         std::vector<size_t> who;
@@ -345,7 +305,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
         DynScratch sc;
         std::vector<size_t> points = first_points[q];
         if (want2[q]) {  // deflate.c:872-893
-          std::vector<size_t> p2 = host_split_forced() ? block_split_lz77(make_cost(mb.lz77), mb.lz77.size(), maxblocks) : second[q];
+          std::vector<size_t> p2 = second[q];
           uint64_t totalcost2 = 0;
           for (size_t i = 0; i <= p2.size(); i++) {
             size_t a = i == 0 ? 0 : p2[i - 1], b = i == p2.size() ? mb.lz77.size() : p2[i];
@@ -502,7 +462,7 @@ void deflate_units(const ZopfliOptions* opt, int btype, bool final_last, const u
     for (auto& t : th) t.join();
   }
   for (size_t m = 0; m < nm; m++)
-    for (auto& p : M[m].pieces) pieces.push_back(std::move(p));
+    for (auto& p : M[m].pieces) { p.unit = (uint32_t)m; pieces.push_back(std::move(p)); }
   (void)in;
 }
 
@@ -547,7 +507,7 @@ void append_bytes(const unsigned char* src, size_t n, unsigned char** out, size_
 // (shifted by their bit phase) in parallel straight into the output buffer; only the bytes shared
 // between neighbouring pieces are merged serially.
 void splice_pieces(const std::vector<Piece>& pieces, const unsigned char* in, unsigned char* bp,
-                   unsigned char** out, size_t* outsize) {
+                   unsigned char** out, size_t* outsize, std::vector<uint64_t>* unit_bits) {
   const size_t np = pieces.size();
   uint64_t bit0 = (uint64_t)*outsize * 8;
   if (*bp != 0 && *outsize > 0) bit0 = (uint64_t)(*outsize - 1) * 8 + *bp;
@@ -572,6 +532,12 @@ void splice_pieces(const std::vector<Piece>& pieces, const unsigned char* in, un
     }
   }
   start[np] = pos;
+  if (unit_bits) {
+    unit_bits->clear();
+    for (size_t i = 0; i < np; i++)
+      if (i == 0 || pieces[i].unit != pieces[i - 1].unit) unit_bits->push_back(start[i] - bit0);
+    unit_bits->push_back(pos - bit0);
+  }
   const size_t oldsize = *outsize, newsize = (size_t)((pos + 7) / 8);
   if (newsize > oldsize) {  // one append of everything (util.h:134-155 capacity rule)
     size_t cap = oldsize == 0 ? 0 : pow2_ceil(oldsize), ncap = pow2_ceil(newsize);

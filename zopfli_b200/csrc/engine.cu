@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 
@@ -64,6 +65,43 @@ struct Timer {
 };
 
 constexpr uint32_t kLogTabN = 1u << 21;
+
+// L[n] = log(n) * kInvLog2 with the HOST libm, exactly the two operations of tree.c:79,85.  Filled once
+// per process by a background thread, uploaded once per device; read-only afterwards, shared by all
+// engine contexts.
+struct LogService {
+  std::mutex mu;
+  std::thread filler;
+  std::vector<double> host;
+  bool started = false, joined = false;
+  double* dev[64] = {nullptr};
+  void start() {
+    std::lock_guard<std::mutex> g(mu);
+    if (started) return;
+    started = true;
+    filler = std::thread([this]() {
+      host.resize(kLogTabN);
+      static const double kInvLog2 = 1.4426950408889;
+      host[0] = 0.0;
+      for (uint32_t i = 1; i < kLogTabN; i++) {
+        volatile double l = log((double)i);
+        host[i] = l * kInvLog2;
+      }
+    });
+  }
+  const double* get(int device, cudaStream_t st) {
+    std::lock_guard<std::mutex> g(mu);
+    if (!joined) { filler.join(); joined = true; }
+    double*& d = dev[device & 63];
+    if (!d) {
+      CK(cudaMalloc(&d, kLogTabN * sizeof(double)));
+      CK(cudaMemcpyAsync(d, host.data(), kLogTabN * sizeof(double), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    return d;
+  }
+};
+LogService g_log;
 
 }  // namespace
 
@@ -121,12 +159,10 @@ struct Engine::Impl {
   int dev = 0;
   Lane lane[Engine::kLanes];
   // input (shared, read-only while parses run)
-  DevBuf in_buf, same_buf, tile_first, next_tile, logtab;
+  DevBuf in_buf, same_buf, tile_first, next_tile;
+  const double* logtab = nullptr;  // shared per-device table (LogService)
   const uint8_t* d_in = nullptr;
   uint64_t insize = 0;
-  std::thread log_thread;
-  std::vector<double> log_host;
-  bool log_ready = false;
   EngineStats st_acc;  // input-side counters; lane counters are merged in stats()
 
   Impl() {
@@ -150,7 +186,7 @@ struct Engine::Impl {
     uint64_t keep = ~0ull;  // keep freed arena memory cached in the pool
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     for (int k = 0; k < Engine::kLanes; k++) lane[k].init((k & 1) == 0);
-    DevBuf* shared[] = {&in_buf, &same_buf, &tile_first, &next_tile, &logtab};
+    DevBuf* shared[] = {&in_buf, &same_buf, &tile_first, &next_tile};
     for (DevBuf* d : shared) d->st = lane[0].stream;
     CK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
     {
@@ -158,26 +194,11 @@ struct Engine::Impl {
       CK(cudaFuncGetAttributes(&fa, k_iterate));
       CK(cudaFuncSetAttribute(k_iterate, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
     }
-    // L[n] = log(n) * kInvLog2 with the HOST libm, exactly the two operations of tree.c:79,85
-    log_thread = std::thread([this]() {
-      log_host.resize(kLogTabN);
-      static const double kInvLog2 = 1.4426950408889;
-      log_host[0] = 0.0;
-      for (uint32_t i = 1; i < kLogTabN; i++) {
-        volatile double l = log((double)i);
-        log_host[i] = l * kInvLog2;
-      }
-    });
+    g_log.start();
   }
 
   void ensure_log() {  // caller holds mu
-    if (log_ready) return;
-    log_thread.join();
-    Lane& l = lane[0];
-    logtab.ensure(kLogTabN * sizeof(double));
-    CK(cudaMemcpyAsync(logtab.p, log_host.data(), kLogTabN * sizeof(double), cudaMemcpyHostToDevice, l.stream));
-    CK(cudaStreamSynchronize(l.stream));
-    log_ready = true;
+    if (!logtab) logtab = g_log.get(dev, lane[0].stream);
   }
 
   void compute_same() {  // caller holds mu; runs on lane 0's stream and completes before returning
@@ -311,7 +332,7 @@ struct Engine::Impl {
     b.st_ll[2] = nullptr;
     b.st_d[2] = nullptr;
     b.jobs = l.jobs.as<JobState>();
-    b.logtab = logtab.as<double>();
+    b.logtab = logtab;
     b.logtab_n = kLogTabN;
     b.out_ll = l.out_ll.as<uint16_t>();
     b.out_d = l.out_d.as<uint16_t>();
@@ -347,9 +368,35 @@ struct Engine::Impl {
 
 Engine::Engine() : p_(new Impl) {}
 
-Engine& Engine::get() {
-  static Engine* e = new Engine;  // intentionally leaked: CUDA teardown order at exit is undefined
-  return *e;
+// ---- context pool: every API call leases one engine context (input buffers + lanes) for its whole
+// duration, so concurrent callers never share mutable device state (the reference is re-entrant,
+// zopfli.h:82-88).  Contexts are created on demand up to ZOPFLI_B200_CONTEXTS (default 4) and are
+// intentionally leaked at exit: CUDA teardown order is undefined.
+namespace {
+std::mutex g_pool_mu;
+std::condition_variable g_pool_cv;
+std::vector<Engine*> g_all, g_free;
+size_t max_contexts() {
+  static size_t n = [] { const char* e = getenv("ZOPFLI_B200_CONTEXTS"); int v = e ? atoi(e) : 4; return (size_t)(v < 1 ? 1 : (v > 16 ? 16 : v)); }();
+  return n;
+}
+}  // namespace
+
+Engine* Engine::acquire() {
+  std::unique_lock<std::mutex> lk(g_pool_mu);
+  for (;;) {
+    if (!g_free.empty()) { Engine* e = g_free.back(); g_free.pop_back(); return e; }
+    if (g_all.size() < max_contexts()) {
+      Engine* e = new Engine;
+      g_all.push_back(e);
+      return e;
+    }
+    g_pool_cv.wait(lk);
+  }
+}
+void Engine::release(Engine* e) {
+  { std::lock_guard<std::mutex> g(g_pool_mu); g_free.push_back(e); }
+  g_pool_cv.notify_one();
 }
 
 int Engine::device() const { return p_->dev; }
@@ -365,12 +412,38 @@ void Engine::set_stream(void* s) {
                      &l.bkt1, &l.bkt2, &l.ld, &l.mlen, &l.runs, &l.dsx, &l.ovf, &l.la, &l.path, &l.st[0], &l.st[1],
                      &l.st[2], &l.st[3], &l.jobs, &l.out_ll, &l.out_d, &l.counters, &l.misc, &l.sp_ll,
                      &l.sp_d, &l.sp_llsym, &l.sp_dsym, &l.sp_pos, &l.sp_snaps, &l.sp_stores, &l.sp_work, &l.sp_evals,
-                     &l.sp_out, &p_->in_buf, &p_->same_buf, &p_->tile_first, &p_->next_tile, &p_->logtab};
+                     &l.sp_out, &p_->in_buf, &p_->same_buf, &p_->tile_first, &p_->next_tile};
     for (DevBuf* d : all) d->st = l.stream;
 #ifdef ZB_VAR_SIG
     l.sig1.st = l.sig2.st = l.h2b.st = l.stream;
 #endif
   }
+}
+
+EngineStats Engine::stats_all() {
+  std::vector<Engine*> all;
+  { std::lock_guard<std::mutex> g(g_pool_mu); all = g_all; }
+  EngineStats r;
+  memset(&r, 0, sizeof(r));
+  for (Engine* e : all) {
+    const EngineStats a = e->stats();
+    r.ms_same += a.ms_same; r.ms_h2d += a.ms_h2d;
+    r.ms_keys += a.ms_keys; r.ms_scan += a.ms_scan; r.ms_scatter += a.ms_scatter; r.ms_match += a.ms_match;
+    r.ms_greedy += a.ms_greedy; r.ms_iterate += a.ms_iterate; r.ms_pack += a.ms_pack; r.ms_d2h += a.ms_d2h;
+    r.ms_split += a.ms_split; r.split_evals += a.split_evals; r.split_rounds += a.split_rounds;
+    r.iterate_launches += a.iterate_launches;
+    r.launches += a.launches; r.match_positions += a.match_positions; r.iterate_positions += a.iterate_positions;
+    r.iterate_steps += a.iterate_steps; r.h2d_bytes += a.h2d_bytes; r.d2h_bytes += a.d2h_bytes;
+    uint64_t ta = 0, tr = 0;
+    for (int i = 0; i < 6; i++) { r.cyc_sum[i] += a.cyc_sum[i]; ta += a.cyc_max[i]; tr += r.cyc_max[i]; }
+    if (ta > tr) { for (int i = 0; i < 6; i++) r.cyc_max[i] = a.cyc_max[i]; r.max_block_positions = a.max_block_positions; }
+  }
+  return r;
+}
+void Engine::reset_stats_all() {
+  std::vector<Engine*> all;
+  { std::lock_guard<std::mutex> g(g_pool_mu); all = g_all; }
+  for (Engine* e : all) e->reset_stats();
 }
 
 EngineStats Engine::stats() {

@@ -33,8 +33,21 @@ struct EngineStats {  // accumulated since the last reset; times from CUDA event
 
 class Engine {
  public:
-  // one engine per process and device; thread-safe (calls are serialised)
-  static Engine& get();
+  // Engine contexts are leased for the duration of one API call (Engine::Lease): a context owns its
+  // input buffers, lanes and arenas, so concurrent calls never share mutable device state.
+  static Engine* acquire();
+  static void release(Engine* e);
+  struct Lease {
+    Engine* e;
+    Lease() : e(Engine::acquire()) {}
+    ~Lease() { Engine::release(e); }
+    Lease(const Lease&) = delete;
+    Lease& operator=(const Lease&) = delete;
+    Engine& operator*() { return *e; }
+    Engine* operator->() { return e; }
+  };
+  static EngineStats stats_all();   // summed over every context of the process
+  static void reset_stats_all();
 
   // Input residency. set_input_host copies to the device (inside the caller's timed region);
   // set_input_device adopts an existing device buffer that must stay valid and be readable
