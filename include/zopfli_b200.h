@@ -73,6 +73,8 @@ double ZopfliB200HostBlockSize(const unsigned char* in, const unsigned short* li
 uint64_t ZopfliB200HostEmitBlock(const unsigned char* in, const unsigned short* litlens,
                                  const unsigned short* dists, size_t n, size_t lstart, size_t lend,
                                  int btype, int final, unsigned char* out, size_t cap);
+/* OptimizeHuffmanForRle (deflate.c:434-518) as restated for host and device, in place, n <= 288. */
+void ZopfliB200HostOptimizeRle(uint32_t* counts, int n);
 /* ZopfliLengthLimitedCodeLengths (katajainen.h:35-36) as restated for host and device. */
 int ZopfliB200HostLengthLimited(const uint32_t* freq, int n, int maxbits, unsigned* bitlengths);
 

@@ -314,3 +314,26 @@ def test_concurrent_calls_and_span_validation(ref, mock):
             mock.splice_spans([span[:cut]])
     offs = mock.last_master_bit_offsets()
     assert len(offs) >= 2 and offs[0] == 0
+
+
+def test_optimize_for_rle_restatement(ref, host):
+    """The run-segmentation form of OptimizeHuffmanForRle (deflate_size.hpp) against the reference's
+    scan (deflate.c:434-518) on histograms with plateaus, zero gaps and near-equal neighbours."""
+    rng = np.random.default_rng(5)
+    for t in range(3000):
+        n = int(rng.choice([32, 288, 30, 19, 7, 1]))
+        kind = t % 5
+        if kind == 0:
+            c = rng.integers(0, 6, n)
+        elif kind == 1:
+            c = np.repeat(rng.integers(0, 40, n), rng.integers(1, 9, n))[:n]
+        elif kind == 2:
+            c = (rng.integers(0, 3, n) == 0) * rng.integers(0, 2000, n)
+        elif kind == 3:
+            c = np.cumsum(rng.integers(-2, 3, n)).clip(0)
+        else:
+            c = rng.integers(0, 1 << int(rng.integers(1, 20)), n)
+        c = np.asarray(c, np.uint32)
+        if len(c) < n:
+            c = np.pad(c, (0, n - len(c)))
+        assert np.array_equal(ref.optimize_rle(c), host.host_optimize_rle(c)), (t, c.tolist())

@@ -47,7 +47,7 @@ EXPORTS = ["ZopfliInitOptions", "ZopfliCompress", "ZopfliDeflate", "ZopfliDeflat
            "ZopfliCalculateBlockSize", "ZopfliCalculateBlockSizeAutoType",
            "ZopfliGzipCompress", "ZopfliZlibCompress", "ZopfliB200LZ77", "ZopfliB200LZ77Batch",
            "ZopfliB200MatchTable", "ZopfliB200DynamicBlockBits", "ZopfliB200DeviceAutoTypeBits", "ZopfliB200HostBlockSplitLZ77",
-           "ZopfliB200HostBatchedSplit", "ZopfliB200HostBlockSize", "ZopfliB200HostEmitBlock", "ZopfliB200HostLengthLimited",
+           "ZopfliB200HostBatchedSplit", "ZopfliB200HostBlockSize", "ZopfliB200HostEmitBlock", "ZopfliB200HostLengthLimited", "ZopfliB200HostOptimizeRle",
            "ZopfliB200DeflateSpan", "ZopfliB200AppendSpan", "ZopfliB200LastMasterBitOffsets", "ZopfliB200Crc32", "ZopfliB200Crc32Combine", "ZopfliB200CompressDevice",
            "ZopfliB200GetStats", "ZopfliB200ResetStats", "ZopfliB200SetStream", "ZopfliB200Device",
            "ZopfliB200Version"]
@@ -123,6 +123,8 @@ class Library:
         L.ZopfliB200HostEmitBlock.argtypes = [vp, vp, vp, sz, sz, sz, C.c_int, C.c_int, vp, sz]
         L.ZopfliB200HostEmitBlock.restype = C.c_uint64
         L.ZopfliB200HostLengthLimited.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.ZopfliB200HostOptimizeRle.argtypes = [vp, C.c_int]
+        L.ZopfliB200HostOptimizeRle.restype = None
         L.ZopfliB200DeflateSpan.argtypes = [C.POINTER(ZopfliOptions), vp, sz, vp, sz, sz, C.c_int,
                                             C.POINTER(vp), C.POINTER(sz)]
         L.ZopfliB200AppendSpan.argtypes = [vp, sz, C.POINTER(C.c_ubyte), C.POINTER(vp), C.POINTER(sz)]
@@ -286,6 +288,11 @@ class Library:
         bits = self.lib.ZopfliB200HostEmitBlock(None, ll.ctypes.data, dd.ctypes.data, len(ll), lstart, lend,
                                                 btype, final, out.ctypes.data, cap)
         return out[: (bits + 7) // 8].tobytes(), int(bits)
+
+    def host_optimize_rle(self, counts):
+        c = np.ascontiguousarray(counts, np.uint32).copy()
+        self.lib.ZopfliB200HostOptimizeRle(c.ctypes.data, len(c))
+        return c
 
     def host_length_limited(self, freq, maxbits):
         f = np.ascontiguousarray(freq, np.uint32)

@@ -499,6 +499,12 @@ int ZopfliB200HostLengthLimited(const uint32_t* freq, int n, int maxbits, unsign
   return 0;
 }
 
+void ZopfliB200HostOptimizeRle(uint32_t* counts, int n) {
+  if (n < 0 || n > kNumLL) return;
+  uint8_t good[kNumLL];
+  optimize_for_rle(n, counts, good);
+}
+
 void ZopfliB200GetStats(ZopfliB200Stats* o) {
   EngineStats e = Engine::stats_all();
   o->ms_same = e.ms_same; o->ms_keys = e.ms_keys; o->ms_scan = e.ms_scan; o->ms_scatter = e.ms_scatter;

@@ -121,55 +121,83 @@ ZB_HD void patch_distance_codes(LenT* d_lengths) {  // deflate.c:86-99
   else if (num == 1) d_lengths[d_lengths[0] ? 1 : 0] = 1;
 }
 
-// Run-length statistics of the code-length sequence for one (use_16,use_17,use_18) choice:
-// the 19 code-length-code counts of deflate.c:137-196 without materialising the RLE stream.
+// ---- code-length RLE of the tree header (deflate.c:105-249) ----
+// The transmitted sequence is ll_len[0 .. hlit+257) followed by d_len[0 .. hdist+1).  tok(sym, extra)
+// is called for every token in stream order: sym 0..15 = a literal code length, 16/17/18 = repeat
+// codes with their extra value.  Token counts per run come from closed forms (quotient / remainder
+// by the repeat capacity) -- the same function serves size evaluation (counting functor) and
+// emission (emit_bits.hpp, writing functor), so the two can never disagree.
+struct TreeShape { unsigned hlit, hdist, total; };
+
 template <typename LenT>
-ZB_HD void tree_rle_counts(const LenT* ll_lengths, const LenT* d_lengths, bool use_16, bool use_17,
-                           bool use_18, uint32_t* clcounts, unsigned* hlit_out,
-                           unsigned* hdist_out) {
-  unsigned hlit = 29, hdist = 29;
-  for (int i = 0; i < 19; i++) clcounts[i] = 0;
-  while (hlit > 0 && ll_lengths[257 + hlit - 1] == 0) hlit--;    // deflate.c:133-134
-  while (hdist > 0 && d_lengths[1 + hdist - 1] == 0) hdist--;
-  const unsigned hlit2 = hlit + 257;
-  const unsigned total = hlit2 + hdist + 1;
-  for (unsigned i = 0; i < total; i++) {
-    unsigned symbol = i < hlit2 ? ll_lengths[i] : d_lengths[i - hlit2];
-    unsigned count = 1;
-    if (use_16 || (symbol == 0 && (use_17 || use_18))) {
-      for (unsigned j = i + 1;
-           j < total && symbol == (unsigned)(j < hlit2 ? ll_lengths[j] : d_lengths[j - hlit2]); j++)
-        count++;
-    }
-    i += count - 1;
-    if (symbol == 0 && count >= 3) {
-      if (use_18) while (count >= 11) { unsigned c2 = count > 138 ? 138 : count; clcounts[18]++; count -= c2; }
-      if (use_17) while (count >= 3) { unsigned c2 = count > 10 ? 10 : count; clcounts[17]++; count -= c2; }
-    }
-    if (use_16 && count >= 4) {
-      count--;
-      clcounts[symbol]++;
-      while (count >= 3) { unsigned c2 = count > 6 ? 6 : count; clcounts[16]++; count -= c2; }
-    }
-    clcounts[symbol] += count;
-  }
-  *hlit_out = hlit;
-  *hdist_out = hdist;
+ZB_HD TreeShape tree_shape(const LenT* ll_len, const LenT* d_len) {
+  TreeShape s;
+  s.hlit = 29;
+  s.hdist = 29;
+  while (s.hlit > 0 && ll_len[256 + s.hlit] == 0) s.hlit--;   // trailing zeros are not sent (deflate.c:133-136)
+  while (s.hdist > 0 && d_len[s.hdist] == 0) s.hdist--;
+  s.total = s.hlit + 257 + s.hdist + 1;
+  return s;
 }
 
-// deflate.c:105-249 with out == NULL
+template <typename LenT, typename Tok>
+ZB_HD void tree_tokens(const LenT* ll_len, const LenT* d_len, const TreeShape& sh, unsigned flags, Tok tok) {
+  const bool use_16 = (flags & 1) != 0, use_17 = (flags & 2) != 0, use_18 = (flags & 4) != 0;
+  const unsigned nll = sh.hlit + 257;
+  auto at = [&](unsigned i) -> unsigned { return i < nll ? ll_len[i] : d_len[i - nll]; };
+  unsigned i = 0;
+  while (i < sh.total) {
+    const unsigned v = at(i);
+    unsigned j = i + 1;
+    if (use_16 || (v == 0 && (use_17 || use_18)))   // runs are only looked for where a repeat code could use them
+      while (j < sh.total && at(j) == v) j++;
+    unsigned c = j - i;   // c equal lengths v
+    i = j;
+    if (v == 0) {
+      if (use_18 && c >= 11) {           // 11..138 zeros per token
+        for (unsigned k = c / 138; k; k--) tok(18u, 127u);
+        c %= 138;
+        if (c >= 11) { tok(18u, c - 11); c = 0; }
+      }
+      if (use_17 && c >= 3) {            // 3..10 zeros per token
+        for (unsigned k = c / 10; k; k--) tok(17u, 7u);
+        c %= 10;
+        if (c >= 3) { tok(17u, c - 3); c = 0; }
+      }
+    }
+    if (use_16 && c >= 4) {              // the length itself, then "repeat previous" 3..6 times per token
+      tok(v, 0u);
+      c--;
+      for (unsigned k = c / 6; k; k--) tok(16u, 3u);
+      c %= 6;
+      if (c >= 3) { tok(16u, c - 3); c = 0; }
+    }
+    for (; c; c--) tok(v, 0u);
+  }
+}
+
+ZB_HD unsigned clcl_rank_symbol(unsigned k) {  // RFC1951 3.2.7 transmission order of the code-length alphabet
+  // 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15
+  if (k < 3) return 16 + k;
+  if (k == 3) return 0;
+  const unsigned h = (k - 4) >> 1;
+  return (k & 1) ? 7 - h : 8 + h;
+}
+
+// EncodeTree with out == NULL (deflate.c:105-249): bits of the tree header for one flag choice
 template <typename LenT>
 ZB_HD uint32_t encode_tree_size(const LenT* ll_lengths, const LenT* d_lengths, bool use_16,
                                 bool use_17, bool use_18) {
   uint32_t clcounts[19];
+  for (int i = 0; i < 19; i++) clcounts[i] = 0;
+  const TreeShape sh = tree_shape(ll_lengths, d_lengths);
+  tree_tokens(ll_lengths, d_lengths, sh, (use_16 ? 1u : 0u) | (use_17 ? 2u : 0u) | (use_18 ? 4u : 0u),
+              [&](unsigned sym, unsigned) { clcounts[sym]++; });
   uint8_t clcl[19];
-  unsigned hlit, hdist;
-  tree_rle_counts(ll_lengths, d_lengths, use_16, use_17, use_18, clcounts, &hlit, &hdist);
   PmScratch<19, 7> s;
   length_limited<19, 7>(clcounts, 19, 7, clcl, s);
-  const unsigned char order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
   unsigned hclen = 15;
-  while (hclen > 0 && clcounts[order[hclen + 4 - 1]] == 0) hclen--;
+  while (hclen > 0 && clcounts[clcl_rank_symbol(hclen + 3)] == 0) hclen--;
   uint32_t r = 14 + (hclen + 4) * 3;
   for (int i = 0; i < 19; i++) r += clcl[i] * clcounts[i];
   r += clcounts[16] * 2 + clcounts[17] * 3 + clcounts[18] * 7;
@@ -199,50 +227,46 @@ ZB_HD uint64_t symbol_bits(const CntT* llc, const CntT* dc, const LenT* ll, cons
   return r + ll[256];
 }
 
-// deflate.c:434-518.  `good` is caller scratch of `length` bytes.
+// OptimizeHuffmanForRle (deflate.c:434-518) as three passes over RUNS instead of one flag-driven
+// scan: (1) drop trailing zeros; (2) every maximal run of equal counts that is long enough for an
+// RLE code (>= 5 zeros, >= 7 non-zeros) is pinned; (3) greedy segmentation: a segment grows while the
+// next count is unpinned and within 4 of `limit`, a finished segment of >= 4 counts (>= 3 when all zero)
+// is flattened to its rounded mean, and the next segment's limit is the mean of the four counts ahead.
+// `good` is caller scratch of `length` bytes.
 template <typename CntT>
 ZB_HD void optimize_for_rle(int length, CntT* counts, uint8_t* good) {
-  for (; length >= 0; --length) {
-    if (length == 0) return;
-    if (counts[length - 1] != 0) break;
+  while (length > 0 && counts[length - 1] == 0) length--;
+  if (length == 0) return;
+  for (int a = 0; a < length;) {                       // pass 2: pin long runs
+    int b = a + 1;
+    while (b < length && counts[b] == counts[a]) b++;
+    const uint8_t pin = (b - a) >= (counts[a] == 0 ? 5 : 7) ? 1 : 0;
+    for (int k = a; k < b; k++) good[k] = pin;
+    a = b;
   }
-  for (int i = 0; i < length; ++i) good[i] = 0;
-  CntT symbol = counts[0];
-  int stride = 0;
-  for (int i = 0; i < length + 1; ++i) {
-    if (i == length || counts[i] != symbol) {
-      if ((symbol == 0 && stride >= 5) || (symbol != 0 && stride >= 7))
-        for (int k = 0; k < stride; ++k) good[i - k - 1] = 1;
-      stride = 1;
-      if (i != length) symbol = counts[i];
-    } else {
-      ++stride;
+  auto ahead = [&](int i) -> uint64_t {                  // limit for a segment starting at i
+    if (i < length - 3) return ((uint64_t)counts[i] + counts[i + 1] + counts[i + 2] + counts[i + 3] + 2) / 4;
+    return i < length ? (uint64_t)counts[i] : 0;
+  };
+  uint64_t limit = good[0] ? ahead(0) : (uint64_t)counts[0];
+  for (int a = 0; a < length;) {                       // pass 3: segment, flatten
+    int b = a + 1;
+    uint64_t sum = counts[a];
+    while (b < length && !good[b]) {
+      const uint64_t c = counts[b];
+      if ((c > limit ? c - limit : limit - c) >= 4) break;
+      sum += c;
+      b++;
     }
-  }
-  stride = 0;
-  uint64_t limit = counts[0], sum = 0;
-  for (int i = 0; i < length + 1; ++i) {
-    bool brk = (i == length) || good[i];
-    if (!brk) {
-      uint64_t c = counts[i];
-      brk = (c > limit ? c - limit : limit - c) >= 4;
+    const int stride = b - a;
+    if (stride >= 4 || (stride >= 3 && sum == 0)) {
+      uint64_t mean = (sum + (uint64_t)(stride / 2)) / (uint64_t)stride;
+      if (mean < 1) mean = 1;
+      if (sum == 0) mean = 0;
+      for (int k = a; k < b; k++) counts[k] = (CntT)mean;
     }
-    if (brk) {
-      if (stride >= 4 || (stride >= 3 && sum == 0)) {
-        int count = (int)((sum + (uint64_t)(stride / 2)) / (uint64_t)stride);
-        if (count < 1) count = 1;
-        if (sum == 0) count = 0;
-        for (int k = 0; k < stride; ++k) counts[i - k - 1] = (CntT)count;
-      }
-      stride = 0;
-      sum = 0;
-      if (i < length - 3)
-        limit = ((uint64_t)counts[i] + counts[i + 1] + counts[i + 2] + counts[i + 3] + 2) / 4;
-      else if (i < length) limit = counts[i];
-      else limit = 0;
-    }
-    ++stride;
-    if (i != length) sum += counts[i];
+    limit = ahead(b);
+    a = b;
   }
 }
 
