@@ -6,19 +6,34 @@
 // logic -- block splitting, block-type choice, bit emission, containers, splice -- can be checked
 // against the reference on a box without a GPU.  The shipped library links engine.cu instead and
 // has no such path.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
 
 #include <vector>
 
 #include "../../oracle/zopfli_oracle.h"
 #include "../../zopfli_b200/csrc/engine.hpp"
+#include <memory>
+
+#include "../../zopfli_b200/csrc/host_emit.hpp"
 #include "../../zopfli_b200/csrc/lz77_store.hpp"
 
 namespace zb {
 
 struct Engine::Impl {
   std::vector<uint8_t> in;
+  size_t insize = 0;
   std::vector<zb::Lz77Store> split_stores[Engine::kLanes];  // one set per lane, as in the engine
+  std::vector<uint16_t> sym_ll[3], sym_d[3];                // kPack / kFin / kFix, indexed like the input
+  std::vector<std::unique_ptr<BlockPlan>> plans;
+  std::mutex mu;
+  void ensure_sym() {
+    for (int b = 0; b < 3; b++)
+      if (sym_ll[b].size() < insize + 64) { sym_ll[b].assign(insize + 64, 0); sym_d[b].assign(insize + 64, 0); }
+  }
 };
 
 Engine::Engine() : p_(new Impl) {}
@@ -41,7 +56,10 @@ void Engine::reset_stats() {}
 void Engine::set_input_host(const uint8_t* in, size_t n) {
   p_->in.assign(in, in + n);
   p_->in.resize(n + 64, 0);
+  p_->insize = n;
+  p_->ensure_sym();
 }
+uint64_t Engine::input_size() const { return p_->insize; }
 void Engine::set_input_device(const uint8_t*, size_t) {}
 void Engine::parse(const std::vector<ParseRange>& r, ParseResult& out, int) {
   out.off.assign(r.size(), 0);
@@ -61,6 +79,60 @@ void Engine::parse(const std::vector<ParseRange>& r, ParseResult& out, int) {
     out.d.insert(out.d.end(), st.dists, st.dists + st.size);
     zo_store_free(&st);
   }
+}
+void Engine::parse_keep(const std::vector<ParseRange>& r, int dest, std::vector<uint32_t>& sizes,
+                        std::vector<uint64_t>& costs, int lane) {
+  ParseResult res;
+  parse(r, res, lane);
+  sizes = res.size;
+  costs = res.cost;
+  std::lock_guard<std::mutex> g(p_->mu);
+  for (size_t i = 0; i < r.size(); i++) {
+    memcpy(p_->sym_ll[dest].data() + r[i].instart, res.ll.data() + res.off[i], res.size[i] * 2);
+    memcpy(p_->sym_d[dest].data() + r[i].instart, res.d.data() + res.off[i], res.size[i] * 2);
+  }
+}
+void Engine::concat_stores(const std::vector<SymCopy>& copies, const std::vector<uint64_t>& store_off,
+                           const std::vector<uint32_t>& store_size, int lane) {
+  for (const SymCopy& c : copies) {
+    memcpy(p_->sym_ll[kFin].data() + c.dst_off, p_->sym_ll[kPack].data() + c.src_off, (size_t)c.n * 2);
+    memcpy(p_->sym_d[kFin].data() + c.dst_off, p_->sym_d[kPack].data() + c.src_off, (size_t)c.n * 2);
+  }
+  std::vector<zb::Lz77Store>& st = p_->split_stores[(unsigned)lane % kLanes];
+  st.clear();
+  st.resize(store_off.size());
+  for (size_t i = 0; i < store_off.size(); i++) {
+    st[i].append(p_->sym_ll[kFin].data() + store_off[i], p_->sym_d[kFin].data() + store_off[i], store_size[i], 0);
+    st[i].finalize();
+  }
+}
+void Engine::plan_blocks(const std::vector<PlanReq>& reqs, std::vector<PlanCost>& costs, std::vector<uint64_t>& handles,
+                         int) {
+  costs.resize(reqs.size());
+  handles.resize(reqs.size());
+  for (size_t i = 0; i < reqs.size(); i++) {
+    std::unique_ptr<BlockPlan> p(new BlockPlan);
+    host_block_plan(p_->sym_ll[reqs[i].buf].data() + reqs[i].off, p_->sym_d[reqs[i].buf].data() + reqs[i].off, reqs[i].n, *p);
+    costs[i] = PlanCost{p->unc_bits, p->fixed_bits, p->dyn_bits};
+    handles[i] = (uint64_t)(uintptr_t)p.get();
+    std::lock_guard<std::mutex> g(p_->mu);
+    p_->plans.push_back(std::move(p));
+  }
+}
+void Engine::emit(const std::vector<EmitPiece>& pieces, uint64_t total_bits, uint8_t* host_dst) {
+  const size_t nbytes = (size_t)((total_bits + 7) / 8);
+  std::vector<uint8_t> buf(nbytes + 16, 0);
+  for (const EmitPiece& p : pieces) {
+    HostBitSink sink{buf.data(), p.bit_start};
+    if (p.type == 0) {
+      host_emit_stored(p.final != 0, p_->in.data() + p.in_start, p.in_len, sink);
+    } else {
+      const uint64_t nb = host_emit_block(p.type, p.final != 0, p_->sym_ll[p.buf].data() + p.off, p_->sym_d[p.buf].data() + p.off,
+                                          p.n, (const BlockPlan*)(uintptr_t)p.plan, sink);
+      if (nb != p.nbits) { fprintf(stderr, "mock: emitted %llu bits, predicted %llu\n", (unsigned long long)nb, (unsigned long long)p.nbits); abort(); }
+    }
+  }
+  memcpy(host_dst, buf.data(), nbytes);
 }
 void Engine::match_table(uint64_t, uint64_t, std::vector<uint16_t>&, std::vector<uint16_t>&,
                          std::vector<uint16_t>&, std::vector<uint16_t>&, std::vector<uint16_t>&,

@@ -14,6 +14,7 @@
 #include "batched_split.hpp"
 #include "driver.hpp"
 #include "engine.hpp"
+#include "host_emit.hpp"
 #include "lz77_store.hpp"
 
 using namespace zb;
@@ -148,18 +149,16 @@ void deflate_impl(const ZopfliOptions* options, int btype, int final, const unsi
   size_t offset = *outsize;
   std::vector<Piece> pieces;
   Engine::Lease eng;  // this call's private engine context
-  if (btype != 0) {
-    if (dev_in) eng->set_input_device(dev_in, insize);
-    else eng->set_input_host(in, insize);
-  }
+  if (dev_in) eng->set_input_device(dev_in, insize);
+  else eng->set_input_host(in, insize);
   const double t1 = now_ms();
   deflate_units(*eng, options, btype, final != 0, in, master_units(insize, 0, num_master_blocks(insize)), 0, pieces);
   const double t2 = now_ms();
   std::vector<uint64_t> layout;
-  splice_pieces(pieces, in, bp, out, outsize, &layout);
+  assemble(*eng, pieces, 0, bp, out, outsize, &layout);
   { std::lock_guard<std::mutex> g(g_api_mu); g_last_layout.swap(layout); }
   if (api_debug())
-    fprintf(stderr, "[zb] api: set_input %.1f ms, deflate_units %.1f ms, splice %.1f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
+    fprintf(stderr, "[zb] api: set_input %.1f ms, deflate_units %.1f ms, emit %.1f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
   if (options->verbose) {
     fprintf(stderr, "Original Size: %lu, Deflate: %lu, Compression: %f%% Removed\n", (unsigned long)insize,
             (unsigned long)(*outsize - offset), 100.0 * (double)(insize - (*outsize - offset)) / (double)insize);
@@ -259,9 +258,9 @@ void ZopfliDeflatePart(const ZopfliOptions* options, int btype, int final, const
   base &= ~(size_t)15;
   std::vector<Piece> pieces;
   Engine::Lease eng;
-  if (btype != 0) eng->set_input_host(in + base, inend - base);
+  eng->set_input_host(in + base, inend - base);
   deflate_units(*eng, options, btype, final != 0, in, {{instart, inend}}, base, pieces);
-  splice_pieces(pieces, in, bp, out, outsize);
+  assemble(*eng, pieces, base, bp, out, outsize);
 }
 
 int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in, size_t insize,
@@ -283,27 +282,39 @@ int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in,
     eng->set_input_host(in + base, end - base);
   }
   deflate_units(*eng, options, 2, final != 0, in, units, base, pieces);
-  // one allocation for the whole span, pieces copied side by side
-  std::vector<size_t> off(pieces.size() + 1, 0);
-  for (size_t i = 0; i < pieces.size(); i++)
-    off[i + 1] = off[i] + 10 + (pieces[i].stored ? pieces[i].inend - pieces[i].instart : pieces[i].bits.bytes.size());
-  unsigned char* dst = append_reserve(off[pieces.size()], span, spansize);
-  std::vector<std::thread> th;
-  const size_t nt = std::min<size_t>(8, pieces.size());
-  for (size_t t = 0; t < nt; t++)
-    th.emplace_back([&, t] {
-      for (size_t i = t; i < pieces.size(); i += nt) {
-        const Piece& p = pieces[i];
-        unsigned char* d = dst + off[i];
-        d[0] = p.stored ? 1 : 0;
-        d[1] = p.final ? 1 : 0;
-        uint64_t v = p.stored ? (uint64_t)(p.inend - p.instart) : p.bits.nbits;
-        memcpy(d + 2, &v, 8);
-        if (p.stored) memcpy(d + 10, in + p.instart, p.inend - p.instart);
-        else if (!p.bits.bytes.empty()) memcpy(d + 10, p.bits.bytes.data(), p.bits.bytes.size());
-      }
-    });
-  for (auto& t : th) t.join();
+  // Records: maximal runs of compressed pieces, each emitted on the device from bit offset 0 of a
+  // byte-aligned slot of one download buffer, and stored pieces as raw bytes.
+  struct Rec { bool stored; bool final; size_t first, count; uint64_t bit0, nbits; };
+  std::vector<Rec> recs;
+  std::vector<Engine::EmitPiece> ep_all;
+  uint64_t pos = 0;
+  for (size_t i = 0; i < pieces.size();) {
+    if (pieces[i].type == 0) { recs.push_back({true, pieces[i].final, i, 1, 0, 0}); i++; continue; }
+    size_t j = i;
+    while (j < pieces.size() && pieces[j].type != 0) j++;
+    std::vector<Piece> run(pieces.begin() + i, pieces.begin() + j);
+    std::vector<Engine::EmitPiece> ep;
+    const uint64_t end = layout_pieces(run, base, pos, ep, nullptr);
+    recs.push_back({false, pieces[j - 1].final, i, j - i, pos, end - pos});
+    ep_all.insert(ep_all.end(), ep.begin(), ep.end());
+    pos = (end + 63) & ~(uint64_t)63;  // the next run starts on a fresh word: no shared bytes between records
+    i = j;
+  }
+  std::vector<unsigned char> bits((size_t)(pos / 8) + 8, 0);
+  if (pos) eng->emit(ep_all, pos, bits.data());
+  size_t total = 0;
+  for (const Rec& r : recs) total += 10 + (r.stored ? pieces[r.first].inend - pieces[r.first].instart : (size_t)((r.nbits + 7) / 8));
+  unsigned char* d = append_reserve(total, span, spansize);
+  for (const Rec& r : recs) {
+    d[0] = r.stored ? 1 : 0;
+    d[1] = r.final ? 1 : 0;
+    const uint64_t v = r.stored ? (uint64_t)(pieces[r.first].inend - pieces[r.first].instart) : r.nbits;
+    memcpy(d + 2, &v, 8);
+    const size_t nb = r.stored ? (size_t)v : (size_t)((v + 7) / 8);
+    if (r.stored) memcpy(d + 10, in + pieces[r.first].instart, nb);
+    else memcpy(d + 10, bits.data() + r.bit0 / 8, nb);
+    d += 10 + nb;
+  }
   return 0;
 }
 
@@ -312,7 +323,7 @@ uint32_t ZopfliB200Crc32Combine(uint32_t crc1, uint32_t crc2, uint64_t len2) { r
 
 int ZopfliB200AppendSpan(const unsigned char* span, size_t spansize, unsigned char* bp, unsigned char** out,
                          size_t* outsize) {
-  std::vector<Piece> pieces;
+  std::vector<SpanPiece> pieces;
   std::vector<unsigned char> rawbytes;  // stored payloads, addressed through instart/inend
   size_t o = 0;
   // validate the whole span before touching the output: spans arrive over a transport
@@ -331,7 +342,7 @@ int ZopfliB200AppendSpan(const unsigned char* span, size_t spansize, unsigned ch
     memcpy(&v, span + o + 2, 8);
     bool stored = span[o] == 1;
     size_t nbytes = stored ? (size_t)v : (size_t)((v + 7) / 8);
-    Piece p;
+    SpanPiece p;
     p.stored = stored;
     p.final = span[o + 1] != 0;
     if (stored) {
@@ -482,12 +493,16 @@ uint64_t ZopfliB200HostEmitBlock(const unsigned char* in, const unsigned short* 
                                  const unsigned short* dists, size_t n, size_t lstart, size_t lend, int btype,
                                  int final, unsigned char* out, size_t cap) {
   (void)in;
-  Lz77Store st;
-  make_store(litlens, dists, n, st);
-  BitString bs;
-  emit_compressed_block(btype, final != 0, st, lstart, lend, bs);
-  if (bs.bytes.size() <= cap) memcpy(out, bs.bytes.data(), bs.bytes.size());
-  return bs.nbits;
+  if (lstart > lend || lend > n || (btype != 1 && btype != 2)) return 0;
+  BlockPlan plan;
+  host_block_plan(litlens + lstart, dists + lstart, lend - lstart, plan);
+  const uint64_t want = btype == 2 ? plan.dyn_bits : plan.fixed_bits;
+  std::vector<uint8_t> buf((size_t)(want / 8) + 16, 0);
+  HostBitSink sink{buf.data(), 0};
+  const uint64_t nbits = host_emit_block(btype, final != 0, litlens + lstart, dists + lstart, lend - lstart, &plan, sink);
+  if (nbits != want) { fprintf(stderr, "zopfli-b200: emitted %llu bits, predicted %llu\n", (unsigned long long)nbits, (unsigned long long)want); abort(); }
+  if ((nbits + 7) / 8 <= cap) memcpy(out, buf.data(), (size_t)((nbits + 7) / 8));
+  return nbits;
 }
 
 int ZopfliB200HostLengthLimited(const uint32_t* freq, int n, int maxbits, unsigned* bitlengths) {

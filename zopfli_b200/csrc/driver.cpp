@@ -22,9 +22,8 @@
 #include <thread>
 
 #include "batched_split.hpp"
-#include "emit.hpp"
+#include "emit_bits.hpp"
 #include "engine.hpp"
-#include "lz77_store.hpp"
 
 namespace zb {
 
@@ -104,42 +103,25 @@ void parallel_for(size_t n, F fn) {
 
 struct FinalBlock {
   size_t lstart, lend;       // symbol range in the master block's store
-  uint64_t unc, fixed, dyn;
+  size_t a, b;               // byte range (absolute input positions)
+  Engine::PlanCost c;
+  uint64_t plan;
   bool expensive = false;
   int fixed_req = -1;        // index into the fixed re-parse batch
 };
 
 struct Master {
   size_t ms, me;                       // byte range
-  Lz77Store greedy;
-  std::vector<size_t> cuts;            // block boundaries in bytes (ms, ..., me)
-  std::vector<Lz77Store> blockstores;
-  Lz77Store lz77;
-  std::vector<size_t> points;          // final split points (symbol indices)
-  std::vector<FinalBlock> finals;
-  std::vector<Lz77Store> fixedstores;
+  std::vector<size_t> cuts;            // first-split block boundaries in bytes (ms, ..., me)
+  std::vector<uint32_t> bsize;         // symbols of every first-split block's optimal parse
   std::vector<Piece> pieces;
 };
 
-// ZopfliBlockSplitLZ77 for many stores at once, split costs priced by the device (k_split_eval)
-std::vector<std::vector<size_t>> device_block_split(Engine& eng, const uint16_t* ll, const uint16_t* d,
-                                                    const std::vector<uint64_t>& off, const std::vector<uint32_t>& size,
-                                                    size_t maxblocks, int lane = 1) {
-  eng.split_begin(ll, d, off, size, lane);
-  std::vector<size_t> sizes(size.begin(), size.end());
-  return batched_block_split(sizes, maxblocks, [&](const std::vector<EvalReq>& r, std::vector<uint64_t>& c) {
-    static_assert(sizeof(EvalReq) == sizeof(Engine::SplitReq), "layout");
-    eng.split_eval(reinterpret_cast<const Engine::SplitReq*>(r.data()), r.size(), c.data(), lane);
-  });
-}
-
-void stored_pieces(size_t a, size_t b, bool final, std::vector<Piece>& out) {
-  Piece p;
-  p.stored = true;
-  p.instart = a;
-  p.inend = b;
-  p.final = final;
-  out.push_back(std::move(p));
+// ZopfliCalculateBlockSizeAutoType (deflate.c:610-621) from the three sizes; `store_size` is the symbol
+// count of the store the range belongs to (the reference tests lz77->size)
+uint64_t auto_type(const Engine::PlanCost& c, size_t store_size) {
+  const uint64_t fixed = store_size > 1000 ? c.unc : c.fixed;
+  return (c.unc < fixed && c.unc < c.dyn) ? c.unc : (fixed < c.dyn ? fixed : c.dyn);
 }
 
 }  // namespace
@@ -151,29 +133,46 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
   const size_t nm = units.size();
   std::vector<Master> M(nm);
   for (size_t m = 0; m < nm; m++) { M[m].ms = units[m].first; M[m].me = units[m].second; }
+  (void)in;
 
   if (btype == 0) {  // deflate.c:826-828
-    for (size_t m = 0; m < nm; m++) { stored_pieces(M[m].ms, M[m].me, final_last && m + 1 == nm, pieces); pieces.back().unit = (uint32_t)m; }
+    for (size_t m = 0; m < nm; m++) {
+      Piece p;
+      p.type = 0;
+      p.instart = M[m].ms;
+      p.inend = M[m].me;
+      p.final = final_last && m + 1 == nm;
+      p.unit = (uint32_t)m;
+      pieces.push_back(p);
+    }
     return;
   }
   if (btype == 1) {  // deflate.c:829-841: one fixed-tree optimal parse per unit
     std::vector<ParseRange> pr;
     for (auto& mb : M) pr.push_back({mb.ms - in_base, mb.me - in_base, 2, 0});
-    ParseResult res;
-    eng.parse(pr, res);
+    std::vector<uint32_t> sizes;
+    std::vector<uint64_t> costs;
+    eng.parse_keep(pr, Engine::kFix, sizes, costs, 0);
+    std::vector<Engine::PlanReq> rq;
+    for (size_t m = 0; m < nm; m++) rq.push_back({M[m].ms - in_base, sizes[m], (uint32_t)Engine::kFix});
+    std::vector<Engine::PlanCost> pc;
+    std::vector<uint64_t> ph;
+    eng.plan_blocks(rq, pc, ph, 0);
     for (size_t m = 0; m < nm; m++) {
-      Lz77Store st;
-      st.append(res.ll.data() + res.off[m], res.d.data() + res.off[m], res.size[m], M[m].ms);
-      st.finalize();
       Piece p;
-      emit_compressed_block(1, final_last && m + 1 == nm, st, 0, st.size(), p.bits);
+      p.type = 1;
+      p.buf = Engine::kFix;
+      p.off = M[m].ms - in_base;
+      p.n = sizes[m];
+      p.nbits = pc[m].fixed;
+      p.final = final_last && m + 1 == nm;
       p.unit = (uint32_t)m;
-      pieces.push_back(std::move(p));
+      pieces.push_back(p);
     }
     return;
   }
 
-  // The master blocks are processed as a few independent chunk pipelines (stages A-F each), one
+  // The master blocks are processed as a few independent chunk pipelines (stages A-E each), one
   // host thread and one pair of engine lanes per chunk: while one chunk's split search waits on
   // round trips or its longest DP chain is still running, the others keep the GPU busy.
   auto run_chunk = [&](const std::vector<size_t>& cm, int lane_g, int lane_r) {
@@ -181,11 +180,11 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
   const int cid = lane_g / 2;
   double t0 = now_ms();
   debug_mark(cid, "start");
-  // ---- stage A: greedy parses (only needed when splitting) ----
   const size_t maxblocks = (size_t)opt->blocksplittingmax;
   if (opt->blocksplitting) {
-    // the greedy stores never leave the device: they become the stores of the split service, and
-    // only the byte positions of the chosen split points come back (blocksplitter.c:303-313)
+    // ---- stage A: greedy parse of every master block (blocksplitter.c:288-296).  The greedy stores
+    // never leave the device: they become the stores of the split service, and only the byte positions
+    // of the chosen split points come back (blocksplitter.c:303-313)
     std::vector<ParseRange> pr;
     for (size_t m : cm) pr.push_back({M[m].ms - in_base, M[m].me - in_base, 0, 0});
     std::vector<uint32_t> gsize;
@@ -224,7 +223,7 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
     for (size_t m : cm) { M[m].cuts.push_back(M[m].ms); M[m].cuts.push_back(M[m].me); }
   }
 
-  // ---- stage C: optimal parse of every block ----
+  // ---- stage C: optimal parse of every block (deflate.c:854-869); the stores stay on the device ----
   {
     std::vector<ParseRange> pr;
     std::vector<std::pair<size_t, size_t>> owner;
@@ -234,8 +233,8 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
         owner.push_back({m, i});
       }
     // The critical path of this stage is the DP chain of the largest blocks.  Giant blocks go to
-    // engine lane 0 on their own (their tables are ready within milliseconds, so their iterate
-    // kernel starts at once); everything else is prepared and parsed on lane 1 meanwhile.
+    // the even engine lane on their own (their tables are ready within milliseconds, so their iterate
+    // kernel starts at once); everything else is prepared and parsed on the odd lane meanwhile.
     uint64_t kGiant = 250000;
     if (const char* e = getenv("ZOPFLI_B200_GIANT")) kGiant = strtoull(e, nullptr, 10);  // tests: force the two-lane path
     std::vector<ParseRange> prs[2];
@@ -245,165 +244,183 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
       prs[lane].push_back(pr[k]);
       idx[lane].push_back(k);
     }
-    ParseResult res[2];
-    for (size_t m : cm) M[m].blockstores.resize(M[m].cuts.size() - 1);
-    auto adopt = [&](int lane) {  // parse results of one lane -> per-block stores
-      const ParseResult& r = res[lane];
-      parallel_for(idx[lane].size(), [&](size_t q) {
-        const size_t k = idx[lane][q];
-        Master& mb = M[owner[k].first];
-        Lz77Store& st = mb.blockstores[owner[k].second];
-        st.append(r.ll.data() + r.off[q], r.d.data() + r.off[q], r.size[q], mb.cuts[owner[k].second]);
-        st.finalize();
-      });
+    for (size_t m : cm) M[m].bsize.assign(M[m].cuts.size() - 1, 0);
+    auto parse_lane = [&](int which, int lane) {
+      std::vector<uint32_t> sizes;
+      std::vector<uint64_t> costs;
+      eng.parse_keep(prs[which], Engine::kPack, sizes, costs, lane);
+      for (size_t q = 0; q < idx[which].size(); q++) {
+        const size_t k = idx[which][q];
+        M[owner[k].first].bsize[owner[k].second] = sizes[q];
+      }
     };
 
-    // ---- stages D-F for a set of master blocks whose blocks are all parsed ----
+    // ---- stages D-E for a set of master blocks whose blocks are all parsed: second split attempt,
+    // block types (deflate.c:872-893, 747-800).  Works on sizes only; every store stays on the device.
     auto finish = [&](const std::vector<size_t>& ms, int lane) {
       const size_t nq = ms.size();
       if (nq == 0) return;
       double td0 = now_ms();
-      // stage D: second split attempt and block types
-      std::vector<std::vector<ParseRange>> fixed_req(nq);
-      std::vector<uint64_t> totalcost(nq, 0);
+      // D1: concatenate the block stores of every master block (ZopfliAppendLZ77Store, deflate.c:863)
+      std::vector<Engine::SymCopy> copies;
       std::vector<std::vector<size_t>> first_points(nq);
-      parallel_for(nq, [&](size_t q) {  // D1: concatenate the blocks, cost of the first split
-        Master& mb = M[ms[q]];
-        DynScratch sc;
-        const size_t nblocks = mb.blockstores.size();
-        for (size_t i = 0; i < nblocks; i++) {
-          totalcost[q] += auto_type_bits(mb.blockstores[i], 0, mb.blockstores[i].size(), sc);  // deflate.c:862
-          mb.lz77.append(mb.blockstores[i]);
-          if (i + 1 < nblocks) first_points[q].push_back(mb.lz77.size());
-        }
-        mb.blockstores.clear();
-        mb.lz77.finalize();
-      });
-      std::vector<std::vector<size_t>> second(nq);
+      std::vector<uint64_t> moff(nq), total(nq, 0);
       std::vector<char> want2(nq, 0);
-      for (size_t q = 0; q < nq; q++) want2[q] = opt->blocksplitting && first_points[q].size() > 1;  // deflate.c:872
-      {
-        std::vector<uint64_t> off;
-        std::vector<uint32_t> size;
-        std::vector<size_t> who;
-        uint64_t total = 0;
-        for (size_t q = 0; q < nq; q++)
-          if (want2[q]) { who.push_back(q); off.push_back(total); size.push_back((uint32_t)M[ms[q]].lz77.size()); total += M[ms[q]].lz77.size(); }
-        if (!who.empty()) {
-          std::vector<uint16_t> fll(total), fd(total);
-          parallel_for(who.size(), [&](size_t k) {
-            const Lz77Store& st = M[ms[who[k]]].lz77;
-            memcpy(fll.data() + off[k], st.litlens.data(), st.size() * 2);
-            memcpy(fd.data() + off[k], st.dists.data(), st.size() * 2);
-          });
-          std::vector<std::vector<size_t>> r = device_block_split(eng, fll.data(), fd.data(), off, size, maxblocks, lane);
-          for (size_t k = 0; k < who.size(); k++) second[who[k]] = r[k];
+      std::vector<uint64_t> soff;
+      std::vector<uint32_t> ssize;
+      std::vector<size_t> who;
+      for (size_t q = 0; q < nq; q++) {
+        const Master& mb = M[ms[q]];
+        moff[q] = mb.ms - in_base;
+        for (size_t i = 0; i < mb.bsize.size(); i++) {
+          copies.push_back({mb.cuts[i] - in_base, moff[q] + total[q], mb.bsize[i], 0});
+          total[q] += mb.bsize[i];
+          if (i + 1 < mb.bsize.size()) first_points[q].push_back((size_t)total[q]);
+        }
+        want2[q] = opt->blocksplitting && first_points[q].size() > 1;  // deflate.c:872
+        if (want2[q]) { who.push_back(q); soff.push_back(moff[q]); ssize.push_back((uint32_t)total[q]); }
+      }
+      eng.concat_stores(copies, soff, ssize, lane);
+      // sizes of the first split's blocks (deflate.c:862: AutoType over each block's own store)
+      std::vector<Engine::PlanReq> rq;
+      std::vector<size_t> rq_base(nq);
+      for (size_t q = 0; q < nq; q++) {
+        const Master& mb = M[ms[q]];
+        rq_base[q] = rq.size();
+        uint64_t so = 0;
+        for (size_t i = 0; i < mb.bsize.size(); i++) { rq.push_back({moff[q] + so, mb.bsize[i], (uint32_t)Engine::kFin}); so += mb.bsize[i]; }
+      }
+      std::vector<Engine::PlanCost> c1;
+      std::vector<uint64_t> h1;
+      eng.plan_blocks(rq, c1, h1, lane);
+      std::vector<uint64_t> totalcost(nq, 0);
+      for (size_t q = 0; q < nq; q++)
+        for (size_t i = 0; i < M[ms[q]].bsize.size(); i++) totalcost[q] += auto_type(c1[rq_base[q] + i], M[ms[q]].bsize[i]);
+      // D2: second split attempt on the concatenated stores (deflate.c:872-893)
+      std::vector<std::vector<size_t>> second(nq);
+      std::vector<Engine::PlanCost> c2;
+      std::vector<uint64_t> h2;
+      std::vector<size_t> rq2_base(nq, 0);
+      std::vector<char> use2(nq, 0);
+      if (!who.empty()) {
+        std::vector<size_t> sizes(ssize.begin(), ssize.end());
+        std::vector<std::vector<size_t>> r =
+            batched_block_split(sizes, maxblocks, [&](const std::vector<EvalReq>& rr, std::vector<uint64_t>& c) {
+              eng.split_eval(reinterpret_cast<const Engine::SplitReq*>(rr.data()), rr.size(), c.data(), lane);
+            });
+        std::vector<Engine::PlanReq> rq2;
+        for (size_t k = 0; k < who.size(); k++) {
+          const size_t q = who[k];
+          second[q] = r[k];
+          rq2_base[q] = rq2.size();
+          for (size_t i = 0; i <= r[k].size(); i++) {
+            const size_t a = i == 0 ? 0 : r[k][i - 1], b = i == r[k].size() ? (size_t)total[q] : r[k][i];
+            rq2.push_back({moff[q] + a, (uint32_t)(b - a), (uint32_t)Engine::kFin});
+          }
+        }
+        eng.plan_blocks(rq2, c2, h2, lane);
+        std::vector<Engine::SplitPos> want;
+        std::vector<size_t> want_base(who.size(), 0);
+        for (size_t k = 0; k < who.size(); k++) {
+          const size_t q = who[k];
+          uint64_t totalcost2 = 0;
+          for (size_t i = 0; i <= second[q].size(); i++) totalcost2 += auto_type(c2[rq2_base[q] + i], (size_t)total[q]);
+          use2[q] = totalcost2 < totalcost[q];
+          want_base[k] = want.size();
+          if (use2[q])
+            for (size_t p : second[q]) want.push_back({(uint32_t)k, (uint32_t)p});
+        }
+        // byte positions of the adopted second-pass split points (lz77->pos, deflate.c:769)
+        std::vector<uint32_t> bytepos;
+        eng.split_positions(want, bytepos, lane);
+        for (size_t k = 0; k < who.size(); k++) {
+          const size_t q = who[k];
+          if (!use2[q]) continue;
+          Master& mb = M[ms[q]];
+          mb.cuts.assign(1, mb.ms);
+          for (size_t i = 0; i < second[q].size(); i++) mb.cuts.push_back(mb.ms + bytepos[want_base[k] + i]);
+          mb.cuts.push_back(mb.me);
         }
       }
-      parallel_for(nq, [&](size_t q) {  // D2
-        Master& mb = M[ms[q]];
-        DynScratch sc;
-        std::vector<size_t> points = first_points[q];
-        if (want2[q]) {  // deflate.c:872-893
-          std::vector<size_t> p2 = second[q];
-          uint64_t totalcost2 = 0;
-          for (size_t i = 0; i <= p2.size(); i++) {
-            size_t a = i == 0 ? 0 : p2[i - 1], b = i == p2.size() ? mb.lz77.size() : p2[i];
-            totalcost2 += auto_type_bits(mb.lz77, a, b, sc);
-          }
-          if (totalcost2 < totalcost[q]) points = p2;
-        }
-        mb.points = points;
-        for (size_t i = 0; i <= points.size(); i++) {  // AddLZ77BlockAutoType deflate.c:747-800
+      // final blocks and the fixed-tree re-parses they ask for (AddLZ77BlockAutoType deflate.c:747-800)
+      std::vector<std::vector<FinalBlock>> finals(nq);
+      std::vector<ParseRange> prf;
+      for (size_t q = 0; q < nq; q++) {
+        const Master& mb = M[ms[q]];
+        const std::vector<size_t>& points = use2[q] ? second[q] : first_points[q];
+        const std::vector<Engine::PlanCost>& cc = use2[q] ? c2 : c1;
+        const std::vector<uint64_t>& hh = use2[q] ? h2 : h1;
+        const size_t base = use2[q] ? rq2_base[q] : rq_base[q];
+        for (size_t i = 0; i <= points.size(); i++) {
           FinalBlock fb;
           fb.lstart = i == 0 ? 0 : points[i - 1];
-          fb.lend = i == points.size() ? mb.lz77.size() : points[i];
-          uint32_t h[320];
-          mb.lz77.range_hist(fb.lstart, fb.lend, h);
-          fb.unc = stored_bits(mb.lz77.byte_range(fb.lstart, fb.lend));
-          fb.fixed = fixed_block_bits(h);
-          fb.dyn = dynamic_block_bits(h, nullptr, nullptr, sc);
-          fb.expensive = (mb.lz77.size() < 1000) || ((double)fb.fixed <= (double)fb.dyn * 1.1);  // :760
+          fb.lend = i == points.size() ? (size_t)total[q] : points[i];
+          fb.a = mb.cuts[i];
+          fb.b = mb.cuts[i + 1];
+          fb.c = cc[base + i];
+          fb.plan = hh[base + i];
+          fb.expensive = ((size_t)total[q] < 1000) || ((double)fb.c.fixed <= (double)fb.c.dyn * 1.1);  // :760
           if (fb.lstart == fb.lend) fb.expensive = false;
           if (fb.expensive) {
-            size_t a = mb.lz77.pos[fb.lstart];
-            size_t b = a + mb.lz77.byte_range(fb.lstart, fb.lend);
-            fb.fixed_req = (int)fixed_req[q].size();
-            fixed_req[q].push_back({a - in_base, b - in_base, 2, 0});
+            fb.fixed_req = (int)prf.size();
+            prf.push_back({fb.a - in_base, fb.b - in_base, 2, 0});
           }
-          mb.finals.push_back(fb);
+          finals[q].push_back(fb);
         }
-      });
+      }
       double td1 = now_ms();
       add_time(g_host_times.split, td1 - td0);
-      // stage E: fixed-tree re-parses
-      {
-        std::vector<ParseRange> prf;
-        std::vector<size_t> base(nq, 0);
-        for (size_t q = 0; q < nq; q++) { base[q] = prf.size(); prf.insert(prf.end(), fixed_req[q].begin(), fixed_req[q].end()); }
-        if (!prf.empty()) {
-          ParseResult rf;
-          eng.parse(prf, rf, lane);
-          for (size_t q = 0; q < nq; q++) {
-            Master& mb = M[ms[q]];
-            mb.fixedstores.resize(fixed_req[q].size());
-            for (size_t k = 0; k < fixed_req[q].size(); k++) {
-              size_t g = base[q] + k;
-              mb.fixedstores[k].append(rf.ll.data() + rf.off[g], rf.d.data() + rf.off[g], rf.size[g],
-                                       (size_t)prf[g].instart + in_base);
-              mb.fixedstores[k].finalize();
-            }
-          }
-        }
+      // stage E: fixed-tree re-parses (deflate.c:771-781) and their sizes
+      std::vector<uint32_t> fsize;
+      std::vector<Engine::PlanCost> c3;
+      if (!prf.empty()) {
+        std::vector<uint64_t> fcost, h3;
+        eng.parse_keep(prf, Engine::kFix, fsize, fcost, lane);
+        std::vector<Engine::PlanReq> rq3;
+        for (size_t g = 0; g < prf.size(); g++) rq3.push_back({prf[g].instart, fsize[g], (uint32_t)Engine::kFix});
+        eng.plan_blocks(rq3, c3, h3, lane);
       }
-      double td2 = now_ms();
-      add_time(g_host_times.other, td2 - td1);
-      // stage F: emission, one task per final block
-      std::vector<std::pair<size_t, size_t>> tasks;
       for (size_t q = 0; q < nq; q++) {
-        M[ms[q]].pieces.resize(M[ms[q]].finals.size());
-        for (size_t i = 0; i < M[ms[q]].finals.size(); i++) tasks.push_back({ms[q], i});
+        Master& mb = M[ms[q]];
+        for (size_t i = 0; i < finals[q].size(); i++) {
+          const FinalBlock& fb = finals[q][i];
+          Piece p;
+          p.final = final_last && ms[q] + 1 == nm && i + 1 == finals[q].size();
+          p.unit = (uint32_t)ms[q];
+          if (fb.lstart == fb.lend) {  // deflate.c:763-768: the smallest empty block is a fixed one
+            p.type = 1;
+            p.n = 0;
+            p.nbits = 10;
+            mb.pieces.push_back(p);
+            continue;
+          }
+          const uint64_t fixedcost = fb.expensive ? c3[fb.fixed_req].fixed : fb.c.fixed;  // deflate.c:779
+          if (fb.c.unc < fixedcost && fb.c.unc < fb.c.dyn) {  // deflate.c:783-785
+            p.type = 0;
+            p.instart = fb.a;
+            p.inend = fb.b;
+          } else if (fixedcost < fb.c.dyn) {
+            p.type = 1;
+            p.nbits = fixedcost;
+            if (fb.expensive) { p.buf = Engine::kFix; p.off = fb.a - in_base; p.n = fsize[fb.fixed_req]; }
+            else { p.buf = Engine::kFin; p.off = moff[q] + fb.lstart; p.n = (uint32_t)(fb.lend - fb.lstart); }
+          } else {
+            p.type = 2;
+            p.nbits = fb.c.dyn;
+            p.buf = Engine::kFin;
+            p.off = moff[q] + fb.lstart;
+            p.n = (uint32_t)(fb.lend - fb.lstart);
+            p.plan = fb.plan;
+          }
+          mb.pieces.push_back(p);
+        }
       }
-      parallel_for(tasks.size(), [&](size_t t) {
-        Master& mb = M[tasks[t].first];
-        const size_t i = tasks[t].second;
-        FinalBlock& fb = mb.finals[i];
-        Piece& p = mb.pieces[i];
-        const bool final = final_last && tasks[t].first + 1 == nm && i + 1 == mb.finals.size();
-        if (fb.lstart == fb.lend) {  // deflate.c:763-768
-          p.bits.add_bits(final ? 1 : 0, 1);
-          p.bits.add_bits(1, 2);
-          p.bits.add_bits(0, 7);
-          p.bits.flush();
-          return;
-        }
-        uint64_t fixedcost = fb.fixed;
-        const Lz77Store* fst = nullptr;
-        if (fb.expensive) {
-          fst = &mb.fixedstores[fb.fixed_req];
-          uint32_t h[320];
-          fst->range_hist(0, fst->size(), h);
-          fixedcost = fixed_block_bits(h);  // deflate.c:779
-        }
-        if (fb.unc < fixedcost && fb.unc < fb.dyn) {  // deflate.c:783-785
-          p.stored = true;
-          p.instart = mb.lz77.pos[fb.lstart];
-          p.inend = p.instart + mb.lz77.byte_range(fb.lstart, fb.lend);
-          p.final = final;
-        } else if (fixedcost < fb.dyn) {
-          if (fb.expensive) emit_compressed_block(1, final, *fst, 0, fst->size(), p.bits);
-          else emit_compressed_block(1, final, mb.lz77, fb.lstart, fb.lend, p.bits);
-        } else {
-          emit_compressed_block(2, final, mb.lz77, fb.lstart, fb.lend, p.bits);
-        }
-      });
-      add_time(g_host_times.emit, now_ms() - td2);
+      add_time(g_host_times.other, now_ms() - td1);
     };
 
     if (prs[0].empty() || prs[1].empty()) {
       const int only = prs[0].empty() ? 1 : 0;
-      eng.parse(prs[only], res[only], lane_g);
-      adopt(only);
+      parse_lane(only, lane_g);
       add_time(g_host_times.other, now_ms() - t0);
       finish(cm, lane_r);
     } else {
@@ -411,20 +428,18 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
       for (size_t k : idx[0]) has_giant[owner[k].first] = 1;
       std::vector<size_t> clean, dirty;
       for (size_t m : cm) (has_giant[m] ? dirty : clean).push_back(m);
-      std::thread tg([&] { eng.parse(prs[0], res[0], lane_g); });
-      eng.parse(prs[1], res[1], lane_r);
+      std::thread tg([&] { parse_lane(0, lane_g); });
+      parse_lane(1, lane_r);
       debug_mark(cid, "C rest parsed");
-      adopt(1);
       add_time(g_host_times.other, now_ms() - t0);
       finish(clean, lane_r);   // overlaps the giants' DP chains still running on lane_g
-      debug_mark(cid, "D-F clean done");
+      debug_mark(cid, "D-E clean done");
       double tw = now_ms();
       tg.join();
       debug_mark(cid, "C giants parsed");
-      adopt(0);
       add_time(g_host_times.other, now_ms() - tw);
       finish(dirty, lane_g);  // the giants' lane is idle now and has stream priority
-      debug_mark(cid, "D-F dirty done");
+      debug_mark(cid, "D-E dirty done");
     }
   }
   };  // run_chunk
@@ -449,11 +464,6 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
       for (size_t a = 0; a < all.size(); a += batch) {
         std::vector<size_t> part(all.begin() + a, all.begin() + std::min(all.size(), a + batch));
         run_chunk(part, (int)(2 * c), (int)(2 * c + 1));
-        for (size_t m : part) {  // the stores of finished master blocks are no longer needed
-          M[m].lz77 = Lz77Store();
-          std::vector<Lz77Store>().swap(M[m].fixedstores);
-          std::vector<Lz77Store>().swap(M[m].blockstores);
-        }
       }
     };
     std::vector<std::thread> th;
@@ -462,12 +472,12 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
     for (auto& t : th) t.join();
   }
   for (size_t m = 0; m < nm; m++)
-    for (auto& p : M[m].pieces) { p.unit = (uint32_t)m; pieces.push_back(std::move(p)); }
-  (void)in;
+    for (auto& p : M[m].pieces) pieces.push_back(p);
 }
 
 // ---------------------------------------------------------------------------------------------
-// splice: append pieces to a zopfli-style growing buffer (util.h:134-155 capacity rule)
+// assemble: prefix sum over the exact piece sizes -> one emission launch -> the stream lands in the
+// caller's zopfli-style buffer (util.h:134-155 capacity rule)
 
 namespace {
 size_t pow2_ceil(size_t v) {
@@ -476,6 +486,60 @@ size_t pow2_ceil(size_t v) {
   return p;
 }
 }  // namespace
+
+uint64_t layout_pieces(const std::vector<Piece>& pieces, size_t in_base, uint64_t bit0, std::vector<Engine::EmitPiece>& ep,
+                       std::vector<uint64_t>* unit_bits) {
+  uint64_t pos = bit0;
+  ep.resize(pieces.size());
+  if (unit_bits) unit_bits->clear();
+  for (size_t i = 0; i < pieces.size(); i++) {
+    const Piece& p = pieces[i];
+    Engine::EmitPiece& e = ep[i];
+    memset(&e, 0, sizeof(e));
+    if (unit_bits && (i == 0 || p.unit != pieces[i - 1].unit)) unit_bits->push_back(pos - bit0);
+    e.bit_start = pos;
+    e.type = p.type;
+    e.final = p.final ? 1 : 0;
+    if (p.type == 0) {
+      e.in_start = p.instart - in_base;
+      e.in_len = p.inend - p.instart;
+      pos = stored_end(pos, e.in_len);
+    } else {
+      e.nbits = p.nbits;
+      e.off = p.off;
+      e.n = p.n;
+      e.buf = p.buf;
+      e.plan = p.plan;
+      pos += p.nbits;
+    }
+  }
+  if (unit_bits) unit_bits->push_back(pos - bit0);
+  return pos;
+}
+
+void assemble(Engine& eng, const std::vector<Piece>& pieces, size_t in_base, unsigned char* bp, unsigned char** out,
+              size_t* outsize, std::vector<uint64_t>* unit_bits) {
+  const unsigned phase = (*outsize > 0) ? (*bp & 7u) : 0u;  // bits in use in the last byte (deflate.h:50-53)
+  std::vector<Engine::EmitPiece> ep;
+  const uint64_t total = layout_pieces(pieces, in_base, phase, ep, unit_bits);
+  const size_t nbytes = (size_t)((total + 7) / 8);
+  if (nbytes == 0) return;
+  unsigned char keep = 0;
+  unsigned char* dst;
+  if (phase) {  // the stream's first byte is the caller's last, partially filled one
+    keep = (*out)[*outsize - 1];
+    append_reserve(nbytes - 1, out, outsize);
+    dst = *out + *outsize - nbytes;
+  } else {
+    dst = append_reserve(nbytes, out, outsize);
+  }
+  eng.emit(ep, total, dst);
+  dst[0] |= keep;
+  *bp = (unsigned char)(total & 7);
+}
+
+// ---------------------------------------------------------------------------------------------
+// splice: append position-independent span records (ZopfliB200AppendSpan) to a zopfli-style buffer
 
 // grows the buffer by n bytes under the same capacity rule and returns where they go
 unsigned char* append_reserve(size_t n, unsigned char** out, size_t* outsize) {
@@ -506,15 +570,15 @@ void append_bytes(const unsigned char* src, size_t n, unsigned char** out, size_
 // Every piece's bit offset follows from a prefix sum over the piece sizes, so the pieces are copied
 // (shifted by their bit phase) in parallel straight into the output buffer; only the bytes shared
 // between neighbouring pieces are merged serially.
-void splice_pieces(const std::vector<Piece>& pieces, const unsigned char* in, unsigned char* bp,
-                   unsigned char** out, size_t* outsize, std::vector<uint64_t>* unit_bits) {
+void splice_pieces(const std::vector<SpanPiece>& pieces, const unsigned char* in, unsigned char* bp,
+                   unsigned char** out, size_t* outsize) {
   const size_t np = pieces.size();
   uint64_t bit0 = (uint64_t)*outsize * 8;
   if (*bp != 0 && *outsize > 0) bit0 = (uint64_t)(*outsize - 1) * 8 + *bp;
   std::vector<uint64_t> start(np + 1);
   uint64_t pos = bit0;
   for (size_t i = 0; i < np; i++) {
-    const Piece& p = pieces[i];
+    const SpanPiece& p = pieces[i];
     start[i] = pos;
     if (!p.stored) {
       pos += p.bits.nbits;
@@ -532,12 +596,6 @@ void splice_pieces(const std::vector<Piece>& pieces, const unsigned char* in, un
     }
   }
   start[np] = pos;
-  if (unit_bits) {
-    unit_bits->clear();
-    for (size_t i = 0; i < np; i++)
-      if (i == 0 || pieces[i].unit != pieces[i - 1].unit) unit_bits->push_back(start[i] - bit0);
-    unit_bits->push_back(pos - bit0);
-  }
   const size_t oldsize = *outsize, newsize = (size_t)((pos + 7) / 8);
   if (newsize > oldsize) {  // one append of everything (util.h:134-155 capacity rule)
     size_t cap = oldsize == 0 ? 0 : pow2_ceil(oldsize), ncap = pow2_ceil(newsize);
@@ -555,7 +613,7 @@ void splice_pieces(const std::vector<Piece>& pieces, const unsigned char* in, un
     if (lb >= oldsize && lb < newsize) o[lb] = 0;
   }
   parallel_for(np, [&](size_t i) {
-    const Piece& p = pieces[i];
+    const SpanPiece& p = pieces[i];
     const uint64_t sb = start[i], eb = start[i + 1];
     if (sb == eb) return;
     Edge& e0 = edges[2 * i];

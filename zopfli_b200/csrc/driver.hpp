@@ -7,22 +7,37 @@
 #include <vector>
 
 #include "../../include/zopfli.h"
-#include "emit.hpp"
+#include "engine.hpp"
 
 namespace zb {
 
-// One deflate block of the output: either an already encoded bit string that starts at bit 0,
-// or a stored block that is written at splice time because its padding depends on the absolute
-// bit offset (/root/reference/src/zopfli/deflate.c:643-649).
+// One deflate block of the output stream.  Compressed blocks live on the device as (store buffer,
+// symbol range, plan); their exact bit size is known, so the host can place every block before a bit
+// is written.  Stored blocks name input bytes; their size depends on the bit offset (deflate.c:643-649).
 struct Piece {
+  uint8_t type = 2;          // 0 stored, 1 fixed, 2 dynamic
+  bool final = false;
+  uint8_t buf = 0;           // Engine::StoreBuf
+  uint32_t unit = 0;         // index of the unit (master block) the piece belongs to
+  uint32_t n = 0;            // symbols
+  uint64_t off = 0;          // first symbol in `buf`
+  uint64_t plan = 0;         // Engine::plan_blocks handle (dynamic blocks)
+  uint64_t nbits = 0;        // exact size (compressed blocks)
+  size_t instart = 0, inend = 0;  // stored blocks: absolute input positions
+};
+
+// A record of a position-independent span (ZopfliB200DeflateSpan / AppendSpan): bits that start at bit
+// offset 0, or stored bytes.
+struct BitString {
+  std::vector<uint8_t> bytes;
+  uint64_t nbits = 0;
+};
+struct SpanPiece {
   bool stored = false;
   BitString bits;
   size_t instart = 0, inend = 0;
   bool final = false;
-  uint32_t unit = 0;   // index of the unit (master block) the piece belongs to
 };
-
-class Engine;
 
 struct HostTimes { double split = 0, emit = 0, other = 0; };
 extern HostTimes g_host_times;
@@ -33,10 +48,18 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
                    const std::vector<std::pair<size_t, size_t>>& units, size_t in_base,
                    std::vector<Piece>& pieces);
 
-// unit_bits (optional): receives, relative to the first bit written by this call, the bit offset at
-// which every unit's first piece starts, plus the end offset as last entry
-void splice_pieces(const std::vector<Piece>& pieces, const unsigned char* in, unsigned char* bp,
-                   unsigned char** out, size_t* outsize, std::vector<uint64_t>* unit_bits = nullptr);
+// Places the pieces behind the caller's stream (bit phase *bp), emits them on the device and appends
+// the bytes to *out.  unit_bits (optional) receives the bit offset of every unit's first piece relative
+// to the first bit written, plus the end offset as last entry.
+void assemble(Engine& eng, const std::vector<Piece>& pieces, size_t in_base, unsigned char* bp, unsigned char** out,
+              size_t* outsize, std::vector<uint64_t>* unit_bits = nullptr);
+
+// bit position of every piece when the first one starts at bit0; returns the end position
+uint64_t layout_pieces(const std::vector<Piece>& pieces, size_t in_base, uint64_t bit0, std::vector<Engine::EmitPiece>& ep,
+                       std::vector<uint64_t>* unit_bits);
+
+void splice_pieces(const std::vector<SpanPiece>& pieces, const unsigned char* in, unsigned char* bp,
+                   unsigned char** out, size_t* outsize);
 
 unsigned char* append_reserve(size_t n, unsigned char** out, size_t* outsize);
 void append_bytes(const unsigned char* src, size_t n, unsigned char** out, size_t* outsize);

@@ -17,6 +17,7 @@
 #include "iterate.cuh"
 #include "kernels.cuh"
 #include "split.cuh"
+#include "finish.cuh"
 
 namespace zb {
 
@@ -108,7 +109,12 @@ LogService g_log;
 struct Lane {  // an independent stream + arena set; chunk pipelines use a pair each (giant blocks beside the rest)
   std::mutex mu;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[2];
+  // kernel timing without host synchronisation: event pairs are recorded into a small pool and read
+  // back at the next point where the lane's stream is synchronised anyway (flush_timers)
+  static constexpr int kTimerPairs = 48;
+  cudaEvent_t ev[kTimerPairs][2];
+  double* ev_acc[kTimerPairs];
+  int ev_used = 0;
 #ifdef ZB_VAR_SIG
   DevBuf sig1, sig2, h2b;
 #endif
@@ -128,8 +134,7 @@ struct Lane {  // an independent stream + arena set; chunk pipelines use a pair 
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, high_priority ? hi : lo));
-    CK(cudaEventCreate(&ev[0]));
-    CK(cudaEventCreate(&ev[1]));
+    for (int k = 0; k < kTimerPairs; k++) { CK(cudaEventCreate(&ev[k][0])); CK(cudaEventCreate(&ev[k][1])); }
     DevBuf* all[] = {&segs, &keywork, &poswork, &order, &hv, &hv2, &idx1, &idx2, &rank1, &rank2, &bkt1, &bkt2, &ld,
                      &mlen, &runs, &dsx, &ovf, &la, &path, &st[0], &st[1], &st[2], &st[3], &jobs, &out_ll,
                      &out_d, &counters, &misc, &sp_ll, &sp_d, &sp_llsym, &sp_dsym, &sp_pos, &sp_snaps, &sp_stores,
@@ -139,13 +144,25 @@ struct Lane {  // an independent stream + arena set; chunk pipelines use a pair 
     sig1.st = sig2.st = h2b.st = stream;
 #endif
   }
-  void tic() { CK(cudaEventRecord(ev[0], stream)); }
+  void tic() {
+    if (ev_used == kTimerPairs) { CK(cudaStreamSynchronize(stream)); flush_timers(); }
+    CK(cudaEventRecord(ev[ev_used][0], stream));
+  }
   void toc(double& a) {
-    CK(cudaEventRecord(ev[1], stream));
-    CK(cudaEventSynchronize(ev[1]));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, ev[0], ev[1]));
-    a += ms;
+    CK(cudaEventRecord(ev[ev_used][1], stream));
+    ev_acc[ev_used++] = &a;
+  }
+  void flush_timers() {  // the stream must be idle (caller has synchronised it)
+    for (int k = 0; k < ev_used; k++) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, ev[k][0], ev[k][1]));
+      *ev_acc[k] += ms;
+    }
+    ev_used = 0;
+  }
+  void sync() {
+    CK(cudaStreamSynchronize(stream));
+    flush_timers();
   }
   template <typename T>
   void upload(DevBuf& d, const std::vector<T>& v) {
@@ -164,6 +181,45 @@ struct Engine::Impl {
   const uint8_t* d_in = nullptr;
   uint64_t insize = 0;
   EngineStats st_acc;  // input-side counters; lane counters are merged in stats()
+  // device-resident finish: symbol buffers (Engine::StoreBuf), plan slabs, output stream
+  std::mutex fin_mu;
+  DevBuf sym_ll[3], sym_d[3];
+  struct Slab { BlockPlan* p; size_t cap; };
+  std::vector<Slab> slabs;
+  size_t slab_idx = 0, slab_used = 0;
+  DevBuf outbuf, emit_desc, err_flag;
+
+  void begin_call() {  // a new input: plans of the previous call are dead
+    std::lock_guard<std::mutex> g(fin_mu);
+    slab_idx = 0;
+    slab_used = 0;
+  }
+  // symbol buffer `buf`, sized like the input; allocated on lane 0's stream, which is drained before any
+  // other lane may touch the memory
+  void ensure_sym(int buf) {
+    std::lock_guard<std::mutex> g(fin_mu);
+    const size_t need = (insize + 64) * 2;
+    if (sym_ll[buf].cap >= need && sym_d[buf].cap >= need) return;
+    sym_ll[buf].ensure(need);
+    sym_d[buf].ensure(need);
+    CK(cudaStreamSynchronize(lane[0].stream));
+  }
+  BlockPlan* plan_alloc(size_t n) {  // n contiguous plans; slabs are kept for the context's lifetime
+    std::lock_guard<std::mutex> g(fin_mu);
+    for (;;) {
+      if (slab_idx < slabs.size() && slabs[slab_idx].cap - slab_used >= n) {
+        BlockPlan* r = slabs[slab_idx].p + slab_used;
+        slab_used += n;
+        return r;
+      }
+      if (slab_idx < slabs.size()) { slab_idx++; slab_used = 0; continue; }
+      Slab sl;
+      sl.cap = std::max<size_t>(n, 8192);
+      CK(cudaMalloc((void**)&sl.p, sl.cap * sizeof(BlockPlan)));
+      slabs.push_back(sl);
+      slab_used = 0;
+    }
+  }
 
   Impl() {
     memset(&st_acc, 0, sizeof(st_acc));
@@ -186,7 +242,8 @@ struct Engine::Impl {
     uint64_t keep = ~0ull;  // keep freed arena memory cached in the pool
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     for (int k = 0; k < Engine::kLanes; k++) lane[k].init((k & 1) == 0);
-    DevBuf* shared[] = {&in_buf, &same_buf, &tile_first, &next_tile};
+    DevBuf* shared[] = {&in_buf, &same_buf, &tile_first, &next_tile, &sym_ll[0], &sym_ll[1], &sym_ll[2], &sym_d[0],
+                        &sym_d[1], &sym_d[2], &outbuf, &emit_desc, &err_flag};
     for (DevBuf* d : shared) d->st = lane[0].stream;
     CK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
     {
@@ -412,7 +469,8 @@ void Engine::set_stream(void* s) {
                      &l.bkt1, &l.bkt2, &l.ld, &l.mlen, &l.runs, &l.dsx, &l.ovf, &l.la, &l.path, &l.st[0], &l.st[1],
                      &l.st[2], &l.st[3], &l.jobs, &l.out_ll, &l.out_d, &l.counters, &l.misc, &l.sp_ll,
                      &l.sp_d, &l.sp_llsym, &l.sp_dsym, &l.sp_pos, &l.sp_snaps, &l.sp_stores, &l.sp_work, &l.sp_evals,
-                     &l.sp_out, &p_->in_buf, &p_->same_buf, &p_->tile_first, &p_->next_tile};
+                     &l.sp_out, &p_->in_buf, &p_->same_buf, &p_->tile_first, &p_->next_tile, &p_->sym_ll[0], &p_->sym_ll[1],
+                     &p_->sym_ll[2], &p_->sym_d[0], &p_->sym_d[1], &p_->sym_d[2], &p_->outbuf, &p_->emit_desc, &p_->err_flag};
     for (DevBuf* d : all) d->st = l.stream;
 #ifdef ZB_VAR_SIG
     l.sig1.st = l.sig2.st = l.h2b.st = l.stream;
@@ -483,6 +541,8 @@ void Engine::set_input_host(const uint8_t* in, size_t insize) {
   m.d_in = m.in_buf.as<uint8_t>();
   m.insize = insize;
   m.compute_same();
+  l.sync();  // the other lanes read the input and `same` from their own streams
+  m.begin_call();
 }
 
 void Engine::set_input_device(const uint8_t* dev_in, size_t insize) {
@@ -496,9 +556,28 @@ void Engine::set_input_device(const uint8_t* dev_in, size_t insize) {
   m.d_in = dev_in;
   m.insize = insize;
   m.compute_same();
+  m.lane[0].sync();
+  m.begin_call();
 }
 
 void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out, int lane_id) {
+  parse_common(ranges, out, -1, lane_id);
+}
+
+void Engine::parse_keep(const std::vector<ParseRange>& ranges, int dest, std::vector<uint32_t>& sizes,
+                        std::vector<uint64_t>& costs, int lane_id) {
+  for (const ParseRange& r : ranges)
+    if (r.mode == 0) { fprintf(stderr, "zopfli-b200: parse_keep takes optimal-parse ranges only\n"); abort(); }
+  ParseResult res;
+  parse_common(ranges, res, dest, lane_id);
+  sizes.swap(res.size);
+  costs.swap(res.cost);
+}
+
+uint64_t Engine::input_size() const { return p_->insize; }
+
+// dest < 0: the symbols come back to the host (test seams); otherwise they stay in symbol buffer `dest`
+void Engine::parse_common(const std::vector<ParseRange>& ranges, ParseResult& out, int dest, int lane_id) {
   Impl& m = *p_;
   Lane& l = m.lane[(unsigned)lane_id % Engine::kLanes];
   std::lock_guard<std::mutex> g(l.mu);
@@ -538,20 +617,25 @@ void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out, int 
       l.acc.iterate_launches++;
     }
     l.tic();
-    k_pack<<<(unsigned)ns, 256, 0, l.stream>>>(b, L.any_parse ? 0 : 1);
+    if (dest < 0) {
+      k_pack<<<(unsigned)ns, 256, 0, l.stream>>>(b, L.any_parse ? 0 : 1);
+    } else {
+      m.ensure_sym(dest);
+      k_keep<<<(unsigned)ns, 256, 0, l.stream>>>(b, m.sym_ll[dest].as<uint16_t>(), m.sym_d[dest].as<uint16_t>());
+    }
     CK(cudaGetLastError());
     l.toc(l.acc.ms_pack);
     l.acc.launches++;
     l.tic();
     CK(cudaMemcpyAsync(js.data(), l.jobs.p, ns * sizeof(JobState), cudaMemcpyDeviceToHost, l.stream));
     CK(cudaMemcpyAsync(counters, l.counters.p, sizeof(counters), cudaMemcpyDeviceToHost, l.stream));
-    CK(cudaStreamSynchronize(l.stream));
+    l.sync();
     if (L.any_parse && counters[0] > l.ovf_cap) {  // run-list overflow arena too small: grow, redo
       l.ovf_cap = counters[0] + counters[0] / 4 + 1024;
       if (attempt > 2) { fprintf(stderr, "zopfli-b200: overflow arena did not converge\n"); abort(); }
       continue;
     }
-    const uint32_t total = counters[1];
+    const uint32_t total = dest < 0 ? counters[1] : 0u;
     out.ll.resize(total);
     out.d.resize(total);
     if (total) {
@@ -559,6 +643,7 @@ void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out, int 
       CK(cudaMemcpyAsync(out.d.data(), l.out_d.p, (size_t)total * 2, cudaMemcpyDeviceToHost, l.stream));
     }
     l.toc(l.acc.ms_d2h);
+    l.sync();
     l.acc.d2h_bytes += (uint64_t)total * 4 + ns * sizeof(JobState);
     break;
   }
@@ -604,7 +689,7 @@ void Engine::match_table(uint64_t instart, uint64_t inend, std::vector<uint16_t>
     m.prepare(L, l);
     uint32_t used = 0;
     CK(cudaMemcpyAsync(&used, l.counters.p, 4, cudaMemcpyDeviceToHost, l.stream));
-    CK(cudaStreamSynchronize(l.stream));
+    l.sync();
     if (used > l.ovf_cap) { l.ovf_cap = used + used / 4 + 1024; if (attempt > 2) abort(); continue; }
     h_ld.resize(n); h_runs.resize(n * kRunSlots); h_mlen.resize(n); h_ovf.resize(used + 1);
     h_hv.resize(L.nkeys); h_hv2.resize(L.nkeys); h_same.resize(n);
@@ -705,6 +790,7 @@ void Engine::split_begin(const uint16_t* ll, const uint16_t* d, const std::vecto
   }
   split_setup(l, l.sp_ll.as<uint16_t>(), l.sp_d.as<uint16_t>(), off, size);
   l.toc(l.acc.ms_split);
+  l.sync();
   l.acc.h2d_bytes += total * 4;
 }
 
@@ -729,7 +815,7 @@ void Engine::greedy_to_split(const std::vector<ParseRange>& ranges, std::vector<
   std::vector<JobState> js(ns);
   l.tic();
   CK(cudaMemcpyAsync(js.data(), l.jobs.p, ns * sizeof(JobState), cudaMemcpyDeviceToHost, l.stream));
-  CK(cudaStreamSynchronize(l.stream));
+  l.sync();
   l.toc(l.acc.ms_d2h);
   l.acc.d2h_bytes += ns * sizeof(JobState);
   std::vector<uint64_t> off(ns);
@@ -737,6 +823,7 @@ void Engine::greedy_to_split(const std::vector<ParseRange>& ranges, std::vector<
   l.tic();
   split_setup(l, b.st_ll[0], b.st_d[0], off, sizes);  // k_greedy wrote range i's store at its pos_off
   l.toc(l.acc.ms_split);
+  l.sync();
 }
 
 __global__ void k_split_gather_pos(SplitBatch b, const Engine::SplitPos* __restrict__ q, uint32_t n, uint32_t* __restrict__ out) {
@@ -758,7 +845,7 @@ void Engine::split_positions(const std::vector<SplitPos>& q, std::vector<uint32_
                                                                               l.sp_out.as<uint32_t>());
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(bytepos.data(), l.sp_out.p, q.size() * 4, cudaMemcpyDeviceToHost, l.stream));
-  CK(cudaStreamSynchronize(l.stream));
+  l.sync();
   l.acc.launches++;
 }
 
@@ -785,8 +872,124 @@ void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lan
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(costs, l.sp_out.p, n * 8, cudaMemcpyDeviceToHost, l.stream));
   l.toc(l.acc.ms_split);
+  l.sync();
   l.acc.split_evals += n;
   l.acc.split_rounds++;
+}
+
+void Engine::concat_stores(const std::vector<SymCopy>& copies, const std::vector<uint64_t>& store_off,
+                           const std::vector<uint32_t>& store_size, int lane_id) {
+  Impl& m = *p_;
+  Lane& l = m.lane[(unsigned)lane_id % Engine::kLanes];
+  std::lock_guard<std::mutex> g(l.mu);
+  CK(cudaSetDevice(m.dev));
+  m.ensure_sym(kPack);
+  m.ensure_sym(kFin);
+  static_assert(sizeof(SymCopy) == sizeof(SymCopyDev), "layout");
+  l.tic();
+  if (!copies.empty()) {
+    l.misc.ensure(copies.size() * sizeof(SymCopyDev) + 64);
+    CK(cudaMemcpyAsync(l.misc.p, copies.data(), copies.size() * sizeof(SymCopyDev), cudaMemcpyHostToDevice, l.stream));
+    k_sym_copy<<<(unsigned)copies.size(), 256, 0, l.stream>>>(l.misc.as<SymCopyDev>(), m.sym_ll[kPack].as<uint16_t>(),
+                                                            m.sym_d[kPack].as<uint16_t>(), m.sym_ll[kFin].as<uint16_t>(),
+                                                            m.sym_d[kFin].as<uint16_t>());
+    CK(cudaGetLastError());
+    l.acc.launches++;
+  }
+  if (!store_off.empty()) split_setup(l, m.sym_ll[kFin].as<uint16_t>(), m.sym_d[kFin].as<uint16_t>(), store_off, store_size);
+  l.toc(l.acc.ms_split);
+  l.sync();
+}
+
+void Engine::plan_blocks(const std::vector<PlanReq>& reqs, std::vector<PlanCost>& costs, std::vector<uint64_t>& handles,
+                         int lane_id) {
+  Impl& m = *p_;
+  Lane& l = m.lane[(unsigned)lane_id % Engine::kLanes];
+  std::lock_guard<std::mutex> g(l.mu);
+  CK(cudaSetDevice(m.dev));
+  const size_t n = reqs.size();
+  costs.assign(n, PlanCost{0, 0, 0});
+  handles.assign(n, 0);
+  if (n == 0) return;
+  BlockPlan* plans = m.plan_alloc(n);
+  std::vector<PlanReqDev> rd(n);
+  for (size_t i = 0; i < n; i++) {
+    m.ensure_sym((int)reqs[i].buf);
+    rd[i].ll = m.sym_ll[reqs[i].buf].as<uint16_t>() + reqs[i].off;
+    rd[i].d = m.sym_d[reqs[i].buf].as<uint16_t>() + reqs[i].off;
+    rd[i].out = plans + i;
+    rd[i].n = reqs[i].n;
+    rd[i].pad = 0;
+    handles[i] = (uint64_t)(uintptr_t)(plans + i);
+  }
+  l.sp_evals.ensure(n * sizeof(PlanReqDev) + 64);
+  std::vector<BlockPlan> hp(n);
+  l.tic();
+  CK(cudaMemcpyAsync(l.sp_evals.p, rd.data(), n * sizeof(PlanReqDev), cudaMemcpyHostToDevice, l.stream));
+  k_block_plan<<<(unsigned)n, kPlanThreads, 0, l.stream>>>(l.sp_evals.as<PlanReqDev>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(hp.data(), plans, n * sizeof(BlockPlan), cudaMemcpyDeviceToHost, l.stream));
+  l.toc(l.acc.ms_split);
+  l.sync();
+  l.acc.launches++;
+  l.acc.d2h_bytes += n * sizeof(BlockPlan);
+  for (size_t i = 0; i < n; i++) costs[i] = PlanCost{hp[i].unc_bits, hp[i].fixed_bits, hp[i].dyn_bits};
+}
+
+void Engine::emit(const std::vector<EmitPiece>& pieces, uint64_t total_bits, uint8_t* host_dst) {
+  Impl& m = *p_;
+  Lane& l = m.lane[0];
+  std::lock_guard<std::mutex> g(l.mu);
+  CK(cudaSetDevice(m.dev));
+  const size_t nbytes = (size_t)((total_bits + 7) / 8);
+  if (nbytes == 0) return;
+  const size_t np = pieces.size();
+  std::vector<EmitDesc> ed(np);
+  for (size_t i = 0; i < np; i++) {
+    const EmitPiece& p = pieces[i];
+    EmitDesc& e = ed[i];
+    memset(&e, 0, sizeof(e));
+    e.bit_start = p.bit_start;
+    e.nbits = p.nbits;
+    if (p.type != 0) {
+      m.ensure_sym(p.buf);
+      e.ll = m.sym_ll[p.buf].as<uint16_t>() + p.off;
+      e.d = m.sym_d[p.buf].as<uint16_t>() + p.off;
+      e.plan = (const BlockPlan*)(uintptr_t)p.plan;
+      e.n = p.n;
+    } else {
+      if (p.in_start + p.in_len > m.insize) { fprintf(stderr, "zopfli-b200: stored piece outside the input\n"); abort(); }
+      e.in_start = p.in_start;
+      e.in_len = p.in_len;
+    }
+    e.type_final = (uint32_t)p.type | ((uint32_t)(p.final ? 1 : 0) << 8);
+  }
+  m.outbuf.ensure(nbytes + 64);
+  m.emit_desc.ensure(np * sizeof(EmitDesc) + 64);
+  m.err_flag.ensure(64);
+  l.tic();
+  CK(cudaMemsetAsync(m.outbuf.p, 0, nbytes + 64, l.stream));
+  CK(cudaMemsetAsync(m.err_flag.p, 0, 64, l.stream));
+  uint32_t err = 0;
+  if (np) {
+    CK(cudaMemcpyAsync(m.emit_desc.p, ed.data(), np * sizeof(EmitDesc), cudaMemcpyHostToDevice, l.stream));
+    k_emit<<<(unsigned)np, kEmitThreads, 0, l.stream>>>(m.emit_desc.as<EmitDesc>(), m.d_in, m.outbuf.as<uint32_t>(),
+                                                      m.err_flag.as<uint32_t>());
+    CK(cudaGetLastError());
+    l.acc.launches++;
+  }
+  l.toc(l.acc.ms_pack);
+  l.tic();
+  CK(cudaMemcpyAsync(&err, m.err_flag.p, 4, cudaMemcpyDeviceToHost, l.stream));
+  CK(cudaMemcpyAsync(host_dst, m.outbuf.p, nbytes, cudaMemcpyDeviceToHost, l.stream));
+  l.toc(l.acc.ms_d2h);
+  l.sync();
+  l.acc.d2h_bytes += nbytes;
+  if (err) {
+    fprintf(stderr, "zopfli-b200: emitted block %u does not match its predicted size (%s)\n", err & 0x3fffffffu,
+            (err & 0x80000000u) ? "block" : "tree header");
+    abort();
+  }
 }
 
 uint64_t Engine::device_block_bits(const uint32_t* hist320) {
@@ -803,7 +1006,7 @@ uint64_t Engine::device_block_bits(const uint32_t* hist320) {
   CK(cudaGetLastError());
   uint64_t r = 0;
   CK(cudaMemcpyAsync(&r, dout, 8, cudaMemcpyDeviceToHost, l.stream));
-  CK(cudaStreamSynchronize(l.stream));
+  l.sync();
   return r;
 }
 

@@ -81,12 +81,47 @@ class Engine {
   struct SplitReq { uint32_t store, lstart, lend; };
   void split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lane = 1);
 
+  // ---- device-resident finish (finish.cuh): stores, plans and the output stay on the GPU ----
+  // Three symbol buffers, all indexed like the input (a block never has more symbols than bytes):
+  //   kPack  best parse of every first-split block at [block start ...)
+  //   kFin   the master block's concatenated store at [master start ...)
+  //   kFix   fixed-tree re-parse of a final block at [block start ...)
+  enum StoreBuf { kPack = 0, kFin = 1, kFix = 2 };
+  // parse() whose results stay on the device in buffer `dest`; sizes / costs as in ParseResult
+  void parse_keep(const std::vector<ParseRange>& ranges, int dest, std::vector<uint32_t>& sizes,
+                  std::vector<uint64_t>& costs, int lane = 0);
+  // kPack -> kFin copies (ZopfliAppendLZ77Store), then the split service of `lane` over the kFin stores
+  // [store_off[i], store_off[i] + store_size[i]) (skipped when store_off is empty)
+  struct SymCopy { uint64_t src_off, dst_off; uint32_t n, pad; };
+  void concat_stores(const std::vector<SymCopy>& copies, const std::vector<uint64_t>& store_off,
+                     const std::vector<uint32_t>& store_size, int lane = 1);
+  // stored / fixed / dynamic sizes of symbol ranges + the emission plan of each (kept on the device);
+  // handles[i] identifies range i's plan in emit()
+  struct PlanReq { uint64_t off; uint32_t n; uint32_t buf; };
+  struct PlanCost { uint64_t unc, fixed, dyn; };
+  void plan_blocks(const std::vector<PlanReq>& reqs, std::vector<PlanCost>& costs, std::vector<uint64_t>& handles,
+                   int lane = 1);
+  // Writes every piece at its final bit position and copies bytes [0, ceil(total_bits / 8)) of the
+  // stream to host_dst.  Positions are absolute within the stream of this call (the first piece starts
+  // at the caller's bit phase 0..7); stored pieces name bytes of the engine's input.
+  struct EmitPiece {
+    uint64_t bit_start, nbits;   // nbits: predicted size of a compressed piece (checked by the kernel)
+    uint64_t off;                // symbols [off, off + n) of buffer `buf`
+    uint64_t plan;               // handle from plan_blocks (dynamic pieces)
+    uint64_t in_start, in_len;   // stored pieces: engine-relative input bytes
+    uint32_t n;
+    uint8_t buf, type, final, pad;   // type: 0 stored, 1 fixed, 2 dynamic
+  };
+  void emit(const std::vector<EmitPiece>& pieces, uint64_t total_bits, uint8_t* host_dst);
+  uint64_t input_size() const;
+
   void set_stream(void* cuda_stream);  // optional: run on the caller's stream
   EngineStats stats();
   void reset_stats();
   int device() const;
 
  private:
+  void parse_common(const std::vector<ParseRange>& ranges, ParseResult& out, int dest, int lane);
   Engine();
   struct Impl;
   Impl* p_;

@@ -356,8 +356,11 @@ __device__ __noinline__ void warp_length_limited(const uint32_t* freq, int n, ui
   __syncwarp();
 }
 
-// exact dynamic block size from s.hist (hist[256] already 1): deflate.c:569-608.
-__device__ uint64_t warp_dynamic_bits(const uint32_t* hist, CostStage& cs, uint32_t lane) {
+// exact dynamic block size from s.hist (hist[256] already 1): deflate.c:569-608.  With `choice` the
+// code-length set (cs.len[choice->set]) and the tree flags that realise the size are reported too
+// (what AddDynamicTree / GetDynamicLengths would pick: first minimum of the 8 flag combinations).
+struct DynChoice { uint32_t set, flags, tree_bits; };
+__device__ uint64_t warp_dynamic_bits(const uint32_t* hist, CostStage& cs, uint32_t lane, DynChoice* choice = nullptr) {
   // RLE-smoothed copies of both histograms (TryOptimizeHuffmanForRle deflate.c:525-567): two
   // serial scans side by side, then four warp-wide code constructions
   for (int i = lane; i < 320; i += 32) cs.cnt2[i] = hist[i];
@@ -374,6 +377,7 @@ __device__ uint64_t warp_dynamic_bits(const uint32_t* hist, CostStage& cs, uint3
   if (lane < 16) {
     const uint8_t* l = cs.len[lane >> 3];
     tsz = encode_tree_size(l, l + 288, (lane & 1) != 0, (lane & 2) != 0, (lane & 4) != 0);
+    tsz = (tsz << 3) | (lane & 7u);  // ties go to the lowest flag index (deflate.c:259-267 keeps the first minimum)
   }
   // min over lanes 0..7 and 8..15 (deflate.c:277-290)
 #pragma unroll
@@ -381,7 +385,8 @@ __device__ uint64_t warp_dynamic_bits(const uint32_t* hist, CostStage& cs, uint3
     uint32_t o = __shfl_xor_sync(0xffffffffu, tsz, d);
     tsz = o < tsz ? o : tsz;
   }
-  const uint32_t tree0 = __shfl_sync(0xffffffffu, tsz, 0), tree1 = __shfl_sync(0xffffffffu, tsz, 8);
+  const uint32_t key0 = __shfl_sync(0xffffffffu, tsz, 0), key1 = __shfl_sync(0xffffffffu, tsz, 8);
+  const uint32_t tree0 = key0 >> 3, tree1 = key1 >> 3;
   // symbol bits of both length sets (deflate.c:379-401), all lanes
   uint64_t sb0 = 0, sb1 = 0;
   for (int i = lane; i < 320; i += 32) {
@@ -402,6 +407,12 @@ __device__ uint64_t warp_dynamic_bits(const uint32_t* hist, CostStage& cs, uint3
   }
   const uint64_t size0 = tree0 + sb0 + cs.len[0][256];
   const uint64_t size1 = tree1 + sb1 + cs.len[1][256];
+  if (choice) {
+    const bool second = size1 < size0;  // deflate.c:553-559
+    choice->set = second ? 1u : 0u;
+    choice->flags = (second ? key1 : key0) & 7u;
+    choice->tree_bits = second ? tree1 : tree0;
+  }
   return 3 + (size1 < size0 ? size1 : size0);  // deflate.c:553-559
 }
 
