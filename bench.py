@@ -2,18 +2,19 @@
 """bench.py -- input MiB/s of ZopfliCompress(gzip, numiterations=15, blocksplittingmax=15).
 
 A "step" is one whole compression of the workload: config C2 of BASELINE.json (100,000,000 B of
-enwik8-like text, numiterations=15) per GPU.  With N>1 (torchrun, one rank per GPU) the job is ONE
-gzip stream over N x 100 MB: each rank owns a contiguous shard of master blocks, receives the
-32 KiB halo of its left neighbour and ships its compressed spans to rank 0 over NCCL; rank 0
-splices them by a bit-offset scan.  Weak scaling: per-GPU work is fixed.
+enwik8-like text, numiterations=15) per GPU.  With N>1 (torchrun, one rank per GPU) the job is ONE gzip
+stream over ONE input of N x 100 MB held by rank 0: the library itself (zopfli_b200/csrc/dist.cpp) scatters
+the master-block shards over NCCL, every rank compresses its shard, and the compressed bits are gathered
+straight into their final bit positions on rank 0.  Weak scaling: per-GPU work is fixed.
 
   value   whole-job MiB/s with the input already resident in HBM when the timed region starts
-  e2e     the same through the reference-facing C ABI with HOST buffers (H2D + D2H inside)
+  e2e     the same through the reference-facing C ABI with a PAGEABLE host buffer (H2D + D2H inside)
   --impl reference   the reference's own CPU implementation (oracle/_ref) on a bounded sample
 """
 import argparse
 import gzip
 import json
+import multiprocessing as mp
 import os
 import subprocess
 import sys
@@ -27,10 +28,22 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 MIB = float(1 << 20)
+MB = 1_000_000               # master block (util.h:60)
 SHARD = 100_000_000          # config C2 per GPU
 NUMITER = 15
 ALG_BYTES_PER_STEP = 34.0    # 28 table + 1 input + 2+2 length_array + ~0.6 store, per position-iteration
-REF_SAMPLE = 8_000_000       # bytes of the workload the CPU reference is timed on (K = 8 master blocks)
+REF_MASTERS = 8              # master blocks the CPU reference is timed on (K >= 8)
+GIANT_MASTERS = [85, 84, 78, 42, 40]            # master blocks of the C2 text with the largest deflate blocks
+UNIFORM_MASTERS = [3, 15, 27, 39, 51, 63, 75, 99]  # (tools/find_giant_masters.py)
+
+
+def bench_config(world):
+    return {"workload": "C2 enwik8-like text, %d B per GPU (%d B total, one stream), gzip, numiterations=15, "
+                        "blocksplittingmax=15" % (SHARD, SHARD * world),
+            "l2": "inputs and working set (GBs) far larger than the 126 MB L2; no flush needed",
+            "parallelism": "master-block shards x%d inside the library: NCCL scatter of byte ranges, NCCL gather of "
+                           "compressed bits at their final bit offsets" % world if world > 1
+            else "single GPU, all blocks of all master blocks in flight"}
 
 
 def workload(nbytes, seed):
@@ -88,19 +101,65 @@ def ncu_traffic():
     return None
 
 
-def cpu_reference(data, steps, warmup):
-    """the reference's own single-threaded implementation (it has no threading)"""
+# ---- the reference on the host cores (oracle/_ref: the unmodified reference, -O3 -DNDEBUG, 1 thread) ----
+
+def cpu_reference(data, masters, steps, warmup):
+    """times ZopfliCompress(gzip) of the first `masters` master blocks; the reference has no threading"""
     import zref
     ref = zref.Ref(ndebug=True)
-    sample = data[:REF_SAMPLE]
-    times = []
-    for i in range(warmup + steps):
+    sample = data[:masters * MB]
+    for _ in range(warmup):
+        ref.compress(data[:MB], 0, numiterations=NUMITER)  # warm-up: code and tables paged in
+    times, out = [], None
+    for _ in range(steps):
         t = time.perf_counter()
         out = ref.compress(sample, 0, numiterations=NUMITER)
-        if i >= warmup:
-            times.append(time.perf_counter() - t)
+        times.append(time.perf_counter() - t)
     sec = sum(times) / len(times)
     return len(sample) / MIB / sec, sec, out
+
+
+def _ref_part(args):
+    import zref
+    piece, s, e, final = args
+    return zref.Ref(ndebug=True).deflate_part(piece, s, e, final=final, numiterations=NUMITER)
+
+
+def reference_parts(data, masters, nmasters_total):
+    """ZopfliDeflatePart of sampled master blocks, in a process pool (the children never touch CUDA)"""
+    jobs = []
+    for m in masters:
+        a, b = m * MB, min(len(data), (m + 1) * MB)
+        lo = max(0, a - 32768)
+        jobs.append((data[lo:b], a - lo, b - lo, int(m == nmasters_total - 1)))
+    with mp.get_context("fork").Pool(min(8, max(1, len(jobs)))) as pool:
+        return pool.map(_ref_part, jobs)
+
+
+def bits_of(b):
+    return np.unpackbits(np.frombuffer(b, dtype=np.uint8), bitorder="little")
+
+
+def check_against_reference(stream, offs, data, masters, prefix_out=None, prefix_masters=0):
+    """Sampled master blocks of `stream` (a gzip file) == the reference's ZopfliDeflatePart of the same
+    ranges, located through the per-master-block bit offsets; plus, if given, the reference's gzip of the
+    first `prefix_masters` master blocks as a bit prefix.  Returns (bytes covered, identical)."""
+    body = bits_of(stream[10:-8])
+    nm = len(offs) - 1
+    ok, covered = True, 0
+    if prefix_out is not None and prefix_masters > 1:
+        pb = bits_of(prefix_out[10:-8])
+        n = int(offs[prefix_masters - 1])  # the last block of the sample carries BFINAL there, not here
+        ok &= bool(np.array_equal(body[:n], pb[:n]))
+        covered += (prefix_masters - 1) * MB
+    want = reference_parts(data, masters, nm)
+    for m, (w, wbp) in zip(masters, want):
+        wb = bits_of(w)
+        nb = int(offs[m + 1] - offs[m])
+        same = nb == len(wb) - ((8 - wbp) & 7) and bool(np.array_equal(body[offs[m]:offs[m + 1]], wb[:nb]))
+        ok &= same
+        covered += min(len(data), (m + 1) * MB) - m * MB
+    return covered, ok
 
 
 def run_reference(args, rank):
@@ -108,15 +167,16 @@ def run_reference(args, rank):
         return
     data, kind = workload(SHARD, 2)
     steps, warmup = args.steps, args.warmup
-    v, sec, _ = cpu_reference(data, steps, warmup)
+    # the whole run is bounded to a few minutes: ~1.6 s of CPU per master block
+    masters = min(REF_MASTERS, max(2, int(150 / max(1, steps))))
+    v, sec, _ = cpu_reference(data, masters, steps, warmup)
+    sample = ("first %d bytes (%d master blocks) of the workload per step, oracle/_ref -O3 -DNDEBUG, 1 thread "
+              "(the reference has no threading); warm-up steps use 1 master block" % (masters * MB, masters))
     line = {"impl": "reference", "metric": "input MiB/s at numiterations=15", "value": v, "unit": "MiB/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": kind,
-            "config": {"workload": "C2 enwik8-like text 100,000,000 B, gzip, numiterations=15, blocksplittingmax=15",
-                       "sample": "first %d bytes" % REF_SAMPLE},
-            "cpu_baseline": {"value": v, "unit": "MiB/s", "cores": 1, "kind": "reference",
-                             "sample": "first %d bytes (8 master blocks) of the workload, -O3 -DNDEBUG, 1 thread "
-                                       "(the reference has no threading)" % REF_SAMPLE},
+            "config": bench_config(args.gpus),
+            "cpu_baseline": {"value": v, "unit": "MiB/s", "cores": 1, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "MiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -135,72 +195,51 @@ def run_product(args, rank, world):
         dist.init_process_group("nccl", device_id=dev)
     os.environ["ZOPFLI_B200_DEVICE"] = str(local)
     lib = zb.library()
-    lib.set_stream(torch.cuda.current_stream().cuda_stream)
     steps, warmup = args.steps, args.warmup
 
-    data, kind = workload(SHARD, 2 + rank)
-    n = len(data)
-    halo = 32768 if rank > 0 else 0
-    # pinned host buffer [halo | shard | pad], device copy of the same
-    host = torch.zeros(halo + n + 64, dtype=torch.uint8).pin_memory()
-    host[halo:halo + n] = torch.frombuffer(bytearray(data), dtype=torch.uint8)
-    devbuf = torch.zeros(halo + n + 64, dtype=torch.uint8, device=dev)
-    if world > 1:  # halo exchange over NCCL: last 32 KiB of rank r -> rank r+1
-        devbuf[halo:halo + n].copy_(host[halo:halo + n])
-        tail = devbuf[halo + n - 32768: halo + n].contiguous()
-        recv = torch.empty(32768, dtype=torch.uint8, device=dev)
-        ops = []
-        if rank + 1 < world:
-            ops.append(dist.P2POp(dist.isend, tail, rank + 1))
-        if rank > 0:
-            ops.append(dist.P2POp(dist.irecv, recv, rank - 1))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        if rank > 0:
-            devbuf[:halo].copy_(recv)
-            host[:halo].copy_(recv.cpu())
-    devbuf.copy_(host)
-    torch.cuda.synchronize()
-    hptr, dptr = host.data_ptr(), devbuf.data_ptr()
-    total = halo + n
+    # ---- the workload: rank r generates segment r (seed 2 + r); rank 0 assembles the one input ----
+    seg, kind = workload(SHARD, 2 + rank)
+    n_total = SHARD * world
+    if world > 1:
+        mine = torch.frombuffer(bytearray(seg), dtype=torch.uint8).to(dev)
+        parts = [torch.empty(SHARD, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, parts, dst=0)
+        data = b"".join(p.cpu().numpy().tobytes() for p in parts) if rank == 0 else None
+        del mine, parts
+        # the library's own communicator (csrc/dist.cpp); the id travels through torch.distributed
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(lib.dist_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        lib.dist_init(rank, world, idt.cpu().numpy().tobytes())
+    else:
+        data = seg
+    # pageable host copy (what a drop-in C caller passes); +64 so the device-resident leg can share it
+    host = np.zeros(n_total + 64, dtype=np.uint8) if rank == 0 else np.zeros(64, dtype=np.uint8)
+    if rank == 0:
+        host[:n_total] = np.frombuffer(data, dtype=np.uint8)
+    hptr = host.ctypes.data
+    devbuf = None
+    if world == 1:
+        devbuf = torch.zeros(n_total + 64, dtype=torch.uint8, device=dev)
+        devbuf[:n_total].copy_(torch.from_numpy(host[:n_total]))
+        torch.cuda.synchronize()
 
     def job(resident):
-        """one whole compression; returns rank 0's gzip bytes"""
-        if world == 1:  # the library's malloc()ed result as a C caller receives it (no copy into a Python object)
-            return lib.compress_ptr_nocopy(hptr, n, zb.ZOPFLI_FORMAT_GZIP, dev_ptr=dptr if resident else None,
-                                           numiterations=NUMITER)
-        crc_box = []
-        crc_thread = threading.Thread(target=lambda: crc_box.append(lib.crc32(hptr + halo, n)))  # ctypes drops the GIL
-        crc_thread.start()
-        span = lib.deflate_span_ptr(hptr, total, halo, total, final=int(rank == world - 1),
-                                    dev_ptr=dptr if resident else None, numiterations=NUMITER)
-        crc_thread.join()
-        crc = crc_box[0]
-        # gather spans + crc to rank 0 over NCCL
-        meta = torch.tensor([len(span), crc, n], dtype=torch.int64, device=dev)
-        metas = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(metas, meta)
-        sizes = [int(m[0]) for m in metas]
-        mx = max(sizes)
-        sp = torch.zeros(mx, dtype=torch.uint8, device=dev)
-        sp[: len(span)] = torch.frombuffer(bytearray(span), dtype=torch.uint8).to(dev)
-        gathered = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
-        dist.gather(sp, gathered, dst=0)
-        if rank != 0:
-            return None
-        spans = [g[:s].cpu().numpy().tobytes() for g, s in zip(gathered, sizes)]
-        body, _ = lib.splice_spans(spans, prefix=bytes([31, 139, 8, 0, 0, 0, 0, 0, 2, 3]))
-        c, tot = 0, 0
-        for i, m in enumerate(metas):
-            c = int(m[1]) if i == 0 else lib.crc32_combine(c, int(m[1]), int(m[2]))
-            tot += int(m[2])
-        return body + int(c).to_bytes(4, "little") + int(tot & 0xffffffff).to_bytes(4, "little")
+        """one whole compression; rank 0 gets the library's malloc()ed gzip stream (no copy into Python)"""
+        if world == 1:
+            return lib.compress_ptr_nocopy(hptr, n_total, zb.ZOPFLI_FORMAT_GZIP,
+                                           dev_ptr=devbuf.data_ptr() if resident else None, numiterations=NUMITER)
+        return lib.dist_compress_ptr_nocopy(hptr, n_total, zb.ZOPFLI_FORMAT_GZIP, staged=resident, numiterations=NUMITER)
 
     def timed(resident):
+        if world > 1 and resident:  # stage the shards once, outside the timed region
+            w = job(False)
+            if w is not None:
+                w.close()
         for _ in range(warmup):
             w = job(resident)
-            if hasattr(w, "close"):
+            if w is not None:
                 w.close()
         lib.reset_stats()
         if world > 1:
@@ -213,7 +252,7 @@ def run_product(args, rank, world):
         e0.record()
         out = None
         for _ in range(steps):
-            if hasattr(out, "close"):
+            if out is not None:
                 out.close()
             out = job(resident)
         e1.record()
@@ -222,33 +261,49 @@ def run_product(args, rank, world):
             dist.barrier()
         wall = time.perf_counter() - t0
         sampler.stop_flag = True
-        ms = max(e0.elapsed_time(e1), wall * 1e3)  # host phases sit between kernels: wall >= event span
+        # every call ends with the synchronous device->host copy of the stream, so the host clock brackets
+        # the device work; the library's kernels run on its own streams (CUDA events there feed `stats`)
+        ms = max(e0.elapsed_time(e1), wall * 1e3)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if hasattr(out, "tobytes"):
+        st = lib.stats()
+        offs = lib.last_master_bit_offsets() if world == 1 else None
+        if out is not None:
             buf, out = out, out.tobytes()  # outside the timed region: only the checks below need a bytes object
             buf.close()
-        return float(t.item()) / steps, out, lib.stats(), sampler.summary()
+        return float(t.item()) / steps, out, st, sampler.summary(), offs
 
-    ms_res, out_res, st_res, clocks = timed(True)
-    ms_e2e, out_e2e, st_e2e, _ = timed(False)
+    ms_res, out_res, st_res, clocks, offs = timed(True)
+    ms_e2e, out_e2e, st_e2e, _, _ = timed(False)
     if rank == 0:
-        units = n * world
         assert out_res == out_e2e, "resident and host-buffer runs disagree"
-        check = {}
+        assert gzip.decompress(out_res) == data, "output does not inflate to the input"
+        nm = (n_total + MB - 1) // MB
+        cpu = None
         if world == 1:
-            assert gzip.decompress(out_res) == data, "output does not inflate to the input"
-            cpu_v, cpu_sec, ref_out = cpu_reference(data, 1, 0)
-            # bit-exactness on the sample the CPU baseline ran on: same bytes as our own run of it
-            mine = lib.compress(data[:REF_SAMPLE], zb.ZOPFLI_FORMAT_GZIP, numiterations=NUMITER)
-            check = {"sample_bytes": REF_SAMPLE, "delta_bytes_vs_reference": len(mine) - len(ref_out),
-                     "identical": mine == ref_out}
+            cpu_v, cpu_sec, ref_out = cpu_reference(data, REF_MASTERS, 1, 0)
             cpu = {"value": cpu_v, "unit": "MiB/s", "cores": 1, "kind": "reference",
-                   "sample": "first %d bytes (8 master blocks) of the workload, oracle/_ref -O3 -DNDEBUG, 1 thread "
-                             "(the reference has no threading)" % REF_SAMPLE}
+                   "sample": "first %d bytes (%d master blocks) of the workload, oracle/_ref -O3 -DNDEBUG, 1 thread "
+                             "(the reference has no threading)" % (REF_MASTERS * MB, REF_MASTERS)}
+            masters = GIANT_MASTERS + UNIFORM_MASTERS if kind == "synthetic" else list(range(8, nm, max(1, nm // 13)))[:13]
+            covered, same = check_against_reference(out_res, offs, data, masters, ref_out, REF_MASTERS)
+            check = {"sample_bytes": covered, "identical": bool(same), "delta_bytes_vs_reference": 0 if same else None,
+                     "how": "timed output vs reference: bit prefix of the first %d master blocks + ZopfliDeflatePart of "
+                            "master blocks %s (incl. the five largest blocks), located by bit offsets" % (REF_MASTERS - 1, masters)}
         else:
-            cpu = None
+            # the N-GPU stream must be the single-GPU stream of the same input (itself reference-checked above
+            # and in tests/), and sampled master blocks of every rank's shard are compared with the reference
+            single = lib.compress_ptr_nocopy(hptr, n_total, zb.ZOPFLI_FORMAT_GZIP, numiterations=NUMITER)
+            offs1 = lib.last_master_bit_offsets()
+            single_bytes = single.tobytes()
+            single.close()
+            per = nm // world
+            masters = sorted(set([r * per for r in range(world)] + [r * per + per // 2 for r in range(world)] + [nm - 1]))
+            covered, same = check_against_reference(out_res, offs1, data, masters)
+            check = {"sample_bytes": covered, "identical": bool(same and single_bytes == out_res),
+                     "equals_single_gpu_stream": single_bytes == out_res, "inflates_to_input": True,
+                     "how": "N-GPU stream == 1-GPU stream of the same input; master blocks %s vs reference ZopfliDeflatePart" % masters}
         peak, peak_src = peak_hbm()
         # k_iterate runs as several concurrent launches per step (chunk pipelines x {giant blocks, the rest},
         # fixed-tree re-parses); ms_iterate is the sum of their CUDA-event durations on their own streams
@@ -256,29 +311,40 @@ def run_product(args, rank, world):
         it_s = st_res["ms_iterate"] / 1e3 / nl                            # average launch duration
         alg = ALG_BYTES_PER_STEP * st_res["iterate_steps"] / nl          # algorithmic bytes of an average launch
         achieved = alg / it_s / 1e9 if it_s > 0 else 0.0
-        line = {"metric": "input MiB/s at numiterations=15", "value": units / MIB / (ms_res / 1e3), "unit": "MiB/s",
+        traffic = ncu_traffic()
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        cyc = st_res["cyc_max"]
+        maxpos = int(st_res["max_block_positions"])
+        line = {"metric": "input MiB/s at numiterations=15", "value": n_total / MIB / (ms_res / 1e3), "unit": "MiB/s",
                 "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_res, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": kind,
-                "config": {"workload": "C2 enwik8-like text, %d B per GPU (%d B total), gzip, numiterations=15, "
-                                       "blocksplittingmax=15" % (n, units),
-                           "l2": "inputs and working set (GBs) far larger than the 126 MB L2; no flush needed",
-                           "parallelism": "master-block shards x%d, NCCL halo exchange + span gather" % world if world > 1
-                           else "single GPU, all blocks of all master blocks in flight"},
-                "e2e": {"value": units / MIB / (ms_e2e / 1e3), "unit": "MiB/s", "ms_per_step": ms_e2e,
-                        "h2d_bytes_per_step": st_e2e["h2d_bytes"] / steps, "d2h_bytes_per_step": st_e2e["d2h_bytes"] / steps},
+                "config": bench_config(world),
+                "e2e": {"value": n_total / MIB / (ms_e2e / 1e3), "unit": "MiB/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": st_e2e["h2d_bytes"] / steps + (n_total if world > 1 else 0),
+                        "d2h_bytes_per_step": st_e2e["d2h_bytes"] / steps, "host_buffer": "pageable"},
                 "gpu_launches": int(st_res["launches"]),
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "k_iterate", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": traffic,
+                             "traffic_over_algorithmic": (traffic / alg) if traffic and alg else None,
+                             "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg, "launch_ms": it_s * 1e3,
                              "launches_per_step": nl / steps,
-                             "note": "DP dependency chain, not bandwidth, bounds this kernel (SURVEY 7.2 #5)"},
+                             # the bound that matters is the DP dependency chain of the largest block
+                             "chain_bound_ms": sum(cyc) / sm_mhz / 1e3,
+                             "chain": {"max_block_positions": maxpos, "iterations": NUMITER,
+                                       "dp_cycles_per_step": cyc[1] / max(1, maxpos * NUMITER),
+                                       "all_cycles_per_step": sum(cyc) / max(1, maxpos * NUMITER)},
+                             "note": "DP dependency chain, not bandwidth, bounds this kernel (SURVEY 7.2 #5): "
+                                     "chain_bound_ms = cycles of the critical block / SM clock"},
                 "cpu_baseline": cpu,
                 "parity": check,
                 "output_bytes": len(out_res),
                 "kernel_ms_per_step": {k: v / steps for k, v in st_res.items() if k.startswith("ms_")}}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
+        lib.dist_finalize()
         dist.destroy_process_group()
 
 

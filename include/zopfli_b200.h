@@ -104,6 +104,27 @@ void ZopfliB200CompressDevice(const ZopfliOptions* options, ZopfliFormat output_
                               const unsigned char* in, size_t insize, const unsigned char* dev_in,
                               unsigned char** out, size_t* outsize);
 
+/* ---- several GPUs, one stream ----
+ * The master blocks of one input (the reference's independent unit, deflate.c:908-931) are sharded
+ * over the GPUs of one box; NCCL scatters the byte ranges (+ 32 KiB dictionary) from rank 0's GPU and
+ * gathers the compressed bits straight into their final bit positions on rank 0.
+ *  - one process, N GPUs: set ZOPFLI_B200_GPUS=N; ZopfliCompress / ZopfliDeflate(btype 2) use it
+ *    transparently (ncclCommInitAll, one host thread per GPU);
+ *  - one process per GPU (e.g. torchrun): rank 0 calls ZopfliB200DistUniqueId, the id is given to every
+ *    rank out of band, every rank calls ZopfliB200DistInit once (device = ZOPFLI_B200_DEVICE / LOCAL_RANK)
+ *    and then ZopfliB200DistCompress COLLECTIVELY with the same options, format and insize.  `in` is read
+ *    and *out / *outsize are written on rank 0 only (same ownership rule as ZopfliCompress).
+ * All return 0 on success. */
+#define ZOPFLI_B200_UNIQUE_ID_BYTES 128
+int ZopfliB200DistUniqueId(unsigned char* id128);
+int ZopfliB200DistInit(int rank, int world, const unsigned char* id128);
+#define ZOPFLI_B200_DIST_STAGED 1 /* flags: the shards of this very input are still on the GPUs from the
+                                    previous ZopfliB200DistCompress call -- skip the H2D copy and the scatter
+                                    (the bench's "input resident in HBM" leg); `in` is still read for the checksum */
+int ZopfliB200DistCompress(const ZopfliOptions* options, ZopfliFormat output_type, const unsigned char* in,
+                           size_t insize, int flags, unsigned char** out, size_t* outsize);
+void ZopfliB200DistFinalize(void);
+
 /* CRC-32 of the gzip trailer (gzip_container.c:27-81) and its combination across shards. */
 uint32_t ZopfliB200Crc32(const unsigned char* data, size_t size);
 uint32_t ZopfliB200Crc32Combine(uint32_t crc1, uint32_t crc2, uint64_t len2);

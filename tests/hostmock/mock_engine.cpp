@@ -36,8 +36,10 @@ struct Engine::Impl {
   }
 };
 
-Engine::Engine() : p_(new Impl) {}
-Engine* Engine::acquire() { return new Engine; }  // one fresh mock context per call
+Engine::Engine(int) : p_(new Impl) {}
+int Engine::default_device() { return -1; }
+int Engine::device_count() { return 0; }
+Engine* Engine::acquire(int dev) { return new Engine(dev); }  // one fresh mock context per call
 void Engine::release(Engine* e) { delete e->p_; e->p_ = nullptr; }
 EngineStats Engine::stats_all() {
   EngineStats s;
@@ -134,6 +136,9 @@ void Engine::emit(const std::vector<EmitPiece>& pieces, uint64_t total_bits, uin
   }
   memcpy(host_dst, buf.data(), nbytes);
 }
+void* Engine::emit_device(const std::vector<EmitPiece>&, uint64_t, size_t) { return nullptr; }
+void Engine::download(const void*, uint8_t*, size_t) {}
+void* Engine::stream() { return nullptr; }
 void Engine::match_table(uint64_t, uint64_t, std::vector<uint16_t>&, std::vector<uint16_t>&,
                          std::vector<uint16_t>&, std::vector<uint16_t>&, std::vector<uint16_t>&,
                          std::vector<uint16_t>&) {}
@@ -178,3 +183,18 @@ void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lan
 }
 
 }  // namespace zb
+
+// multi-GPU entry points (dist.cpp needs CUDA + NCCL): absent from the mock
+#include "../../zopfli_b200/csrc/dist.hpp"
+namespace zb {
+int dist_local_gpus() { return 1; }
+bool dist_local_deflate(int, const ZopfliOptions*, int, const unsigned char*, size_t, unsigned char*, unsigned char**, size_t*) { return false; }
+bool dist_rank_ready() { return false; }
+int dist_rank() { return 0; }
+void dist_rank_deflate(const ZopfliOptions*, int, const unsigned char*, size_t, unsigned char*, unsigned char**, size_t*, bool) {}
+}  // namespace zb
+extern "C" {
+int ZopfliB200DistUniqueId(unsigned char*) { return 1; }
+int ZopfliB200DistInit(int, int, const unsigned char*) { return 1; }
+void ZopfliB200DistFinalize(void) {}
+}

@@ -49,6 +49,7 @@ EXPORTS = ["ZopfliInitOptions", "ZopfliCompress", "ZopfliDeflate", "ZopfliDeflat
            "ZopfliB200MatchTable", "ZopfliB200DynamicBlockBits", "ZopfliB200DeviceAutoTypeBits", "ZopfliB200HostBlockSplitLZ77",
            "ZopfliB200HostBatchedSplit", "ZopfliB200HostBlockSize", "ZopfliB200HostEmitBlock", "ZopfliB200HostLengthLimited", "ZopfliB200HostOptimizeRle",
            "ZopfliB200DeflateSpan", "ZopfliB200AppendSpan", "ZopfliB200LastMasterBitOffsets", "ZopfliB200Crc32", "ZopfliB200Crc32Combine", "ZopfliB200CompressDevice",
+           "ZopfliB200DistUniqueId", "ZopfliB200DistInit", "ZopfliB200DistCompress", "ZopfliB200DistFinalize",
            "ZopfliB200GetStats", "ZopfliB200ResetStats", "ZopfliB200SetStream", "ZopfliB200Device",
            "ZopfliB200Version"]
 
@@ -135,6 +136,10 @@ class Library:
         L.ZopfliB200Crc32.restype = C.c_uint32
         L.ZopfliB200Crc32Combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
         L.ZopfliB200Crc32Combine.restype = C.c_uint32
+        L.ZopfliB200DistUniqueId.argtypes = [vp]
+        L.ZopfliB200DistInit.argtypes = [C.c_int, C.c_int, vp]
+        L.ZopfliB200DistCompress.argtypes = [C.POINTER(ZopfliOptions), C.c_int, vp, sz, C.c_int, C.POINTER(vp), C.POINTER(sz)]
+        L.ZopfliB200DistFinalize.restype = None
         L.ZopfliB200GetStats.argtypes = [C.POINTER(Stats)]
         L.ZopfliB200SetStream.argtypes = [vp]
         L.ZopfliB200Version.restype = C.c_char_p
@@ -347,6 +352,29 @@ class Library:
         a = np.zeros(max(n, 1), np.uint64)
         self.lib.ZopfliB200LastMasterBitOffsets(a.ctypes.data, n)
         return a[:n].astype(np.int64)
+
+    # ---- several GPUs, one stream (one process per GPU; see include/zopfli_b200.h) ----
+    def dist_unique_id(self) -> bytes:
+        buf = (C.c_ubyte * 128)()
+        if self.lib.ZopfliB200DistUniqueId(buf) != 0:
+            raise RuntimeError("NCCL unavailable")
+        return bytes(buf)
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        if self.lib.ZopfliB200DistInit(rank, world, buf) != 0:
+            raise RuntimeError("ZopfliB200DistInit failed")
+
+    def dist_compress_ptr_nocopy(self, host_ptr, nbytes, fmt=ZOPFLI_FORMAT_GZIP, staged=False, **kw):
+        """collective; returns an OutBuffer on rank 0 (host_ptr is read there only), None elsewhere"""
+        o = self.options(**kw)
+        out, n = C.c_void_p(None), C.c_size_t(0)
+        if self.lib.ZopfliB200DistCompress(C.byref(o), fmt, host_ptr, nbytes, 1 if staged else 0, C.byref(out), C.byref(n)) != 0:
+            raise RuntimeError("ZopfliB200DistCompress: ZopfliB200DistInit has not run")
+        return OutBuffer(self.libc, out, n.value) if out.value else None
+
+    def dist_finalize(self):
+        self.lib.ZopfliB200DistFinalize()
 
     # ---- introspection ----
     def stats(self) -> dict:

@@ -12,6 +12,7 @@
 
 #include "../../include/zopfli_b200.h"
 #include "batched_split.hpp"
+#include "dist.hpp"
 #include "driver.hpp"
 #include "engine.hpp"
 #include "host_emit.hpp"
@@ -147,6 +148,13 @@ void deflate_impl(const ZopfliOptions* options, int btype, int final, const unsi
                   size_t* outsize) {
   double t0 = now_ms();
   size_t offset = *outsize;
+  // several GPUs in this process (ZOPFLI_B200_GPUS): master blocks sharded over them, NCCL scatter / gather
+  if (btype == 2 && !dev_in && dist_local_gpus() > 1 && insize > (size_t)kMasterBlock &&
+      dist_local_deflate(dist_local_gpus(), options, final, in, insize, bp, out, outsize)) {
+    std::lock_guard<std::mutex> g(g_api_mu);
+    g_total_ms += now_ms() - t0;
+    return;
+  }
   std::vector<Piece> pieces;
   Engine::Lease eng;  // this call's private engine context
   if (dev_in) eng->set_input_device(dev_in, insize);
@@ -166,15 +174,28 @@ void deflate_impl(const ZopfliOptions* options, int btype, int final, const unsi
   { std::lock_guard<std::mutex> g(g_api_mu); g_total_ms += now_ms() - t0; }
 }
 
+// the containers (gzip_container.c:84-124, zlib_container.c:50-79) around a deflate body produced by `body`
+template <typename Body>
+void container_impl(const ZopfliOptions* options, ZopfliFormat fmt, const unsigned char* in, size_t insize,
+                    unsigned char** out, size_t* outsize, Body deflate_impl_fn);
+
 void compress_impl(const ZopfliOptions* options, ZopfliFormat fmt, const unsigned char* in, size_t insize,
                    const unsigned char* dev_in, unsigned char** out, size_t* outsize) {
+  container_impl(options, fmt, in, insize, out, outsize, [&](unsigned char* bp) {
+    deflate_impl(options, 2, 1, in, insize, dev_in, bp, out, outsize);
+  });
+}
+
+template <typename Body>
+void container_impl(const ZopfliOptions* options, ZopfliFormat fmt, const unsigned char* in, size_t insize,
+                    unsigned char** out, size_t* outsize, Body body) {
   unsigned char bp = 0;
   if (fmt == ZOPFLI_FORMAT_GZIP) {  // gzip_container.c:84-124
     uint32_t crc = 0;
     std::thread crc_thread([&] { crc = crc32_parallel(in, insize); });  // overlaps the GPU work
     static const unsigned char hdr[10] = {31, 139, 8, 0, 0, 0, 0, 0, 2, 3};
     append_bytes(hdr, 10, out, outsize);
-    deflate_impl(options, 2, 1, in, insize, dev_in, &bp, out, outsize);
+    body(&bp);
     const double tj = now_ms();
     crc_thread.join();
     if (api_debug()) fprintf(stderr, "[zb] api: crc join waited %.1f ms\n", now_ms() - tj);
@@ -192,7 +213,7 @@ void compress_impl(const ZopfliOptions* options, ZopfliFormat fmt, const unsigne
     cmfflg += 31 - cmfflg % 31;
     put_byte((unsigned char)(cmfflg / 256), out, outsize);
     put_byte((unsigned char)(cmfflg % 256), out, outsize);
-    deflate_impl(options, 2, 1, in, insize, dev_in, &bp, out, outsize);
+    body(&bp);
     unsigned char tr[4] = {(unsigned char)((checksum >> 24) & 255), (unsigned char)((checksum >> 16) & 255),
                            (unsigned char)((checksum >> 8) & 255), (unsigned char)(checksum & 255)};
     append_bytes(tr, 4, out, outsize);
@@ -200,7 +221,7 @@ void compress_impl(const ZopfliOptions* options, ZopfliFormat fmt, const unsigne
       fprintf(stderr, "Original Size: %d, Zlib: %d, Compression: %f%% Removed\n", (int)insize, (int)*outsize,
               100.0 * (double)(insize - *outsize) / (double)insize);
   } else if (fmt == ZOPFLI_FORMAT_DEFLATE) {
-    deflate_impl(options, 2, 1, in, insize, dev_in, &bp, out, outsize);
+    body(&bp);
   } else {
     fprintf(stderr, "zopfli-b200: unknown output format %d\n", (int)fmt);  // zopfli_lib.c:40 assert(0)
     abort();
@@ -261,6 +282,20 @@ void ZopfliDeflatePart(const ZopfliOptions* options, int btype, int final, const
   eng->set_input_host(in + base, inend - base);
   deflate_units(*eng, options, btype, final != 0, in, {{instart, inend}}, base, pieces);
   assemble(*eng, pieces, base, bp, out, outsize);
+}
+
+int ZopfliB200DistCompress(const ZopfliOptions* options, ZopfliFormat output_type, const unsigned char* in, size_t insize,
+                           int flags, unsigned char** out, size_t* outsize) {
+  if (!dist_rank_ready()) return 1;
+  const bool staged = (flags & ZOPFLI_B200_DIST_STAGED) != 0;
+  if (dist_rank() != 0) {  // workers take part in the deflate body only
+    dist_rank_deflate(options, 1, nullptr, insize, nullptr, nullptr, nullptr, staged);
+    return 0;
+  }
+  container_impl(options, output_type, in, insize, out, outsize, [&](unsigned char* bp) {
+    dist_rank_deflate(options, 1, in, insize, bp, out, outsize, staged);
+  });
+  return 0;
 }
 
 int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in, size_t insize,

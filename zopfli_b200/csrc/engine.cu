@@ -151,6 +151,12 @@ struct Lane {  // an independent stream + arena set; chunk pipelines use a pair 
   void toc(double& a) {
     CK(cudaEventRecord(ev[ev_used][1], stream));
     ev_acc[ev_used++] = &a;
+    // A host synchronisation behind every timed kernel keeps each lane's queue one kernel deep.  Measured
+    // on the 100 MB bench (tools/gpu_timeline.sh): 999 ms per call with it, 1757 ms without -- with whole
+    // kernel chains queued per lane the chunk pipelines run one after the other instead of side by side.
+    // ZOPFLI_B200_SYNC_TOC=0 switches to deferred timing (events read at the next natural sync point).
+    static const bool eager = [] { const char* e = getenv("ZOPFLI_B200_SYNC_TOC"); return !e || atoi(e); }();
+    if (eager) sync();
   }
   void flush_timers() {  // the stream must be idle (caller has synchronised it)
     for (int k = 0; k < ev_used; k++) {
@@ -221,7 +227,7 @@ struct Engine::Impl {
     }
   }
 
-  Impl() {
+  explicit Impl(int want_dev) {
     memset(&st_acc, 0, sizeof(st_acc));
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -230,12 +236,8 @@ struct Engine::Impl {
               e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
       abort();
     }
-    const char* dv = getenv("ZOPFLI_B200_DEVICE");
-    if (dv) dev = atoi(dv);
-    else {
-      const char* lr = getenv("LOCAL_RANK");
-      if (lr) dev = atoi(lr) % n;
-    }
+    dev = want_dev;
+    if (dev < 0 || dev >= n) { fprintf(stderr, "zopfli-b200: CUDA device %d does not exist (%d visible)\n", dev, n); abort(); }
     CK(cudaSetDevice(dev));
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, dev));
@@ -423,7 +425,7 @@ struct Engine::Impl {
   }
 };
 
-Engine::Engine() : p_(new Impl) {}
+Engine::Engine(int dev) : p_(new Impl(dev)) {}
 
 // ---- context pool: every API call leases one engine context (input buffers + lanes) for its whole
 // duration, so concurrent callers never share mutable device state (the reference is re-entrant,
@@ -432,19 +434,40 @@ Engine::Engine() : p_(new Impl) {}
 namespace {
 std::mutex g_pool_mu;
 std::condition_variable g_pool_cv;
-std::vector<Engine*> g_all, g_free;
+std::vector<Engine*> g_all, g_free;   // contexts of every device; a context never changes device
 size_t max_contexts() {
   static size_t n = [] { const char* e = getenv("ZOPFLI_B200_CONTEXTS"); int v = e ? atoi(e) : 4; return (size_t)(v < 1 ? 1 : (v > 16 ? 16 : v)); }();
   return n;
 }
 }  // namespace
 
-Engine* Engine::acquire() {
+int Engine::default_device() {  // ZOPFLI_B200_DEVICE, else the torchrun local rank, else device 0
+  static int d = [] {
+    if (const char* dv = getenv("ZOPFLI_B200_DEVICE")) return atoi(dv);
+    if (const char* lr = getenv("LOCAL_RANK")) {
+      int n = 0;
+      if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) return atoi(lr) % n;
+    }
+    return 0;
+  }();
+  return d;
+}
+
+int Engine::device_count() {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+Engine* Engine::acquire(int dev) {
+  if (dev < 0) dev = default_device();
   std::unique_lock<std::mutex> lk(g_pool_mu);
   for (;;) {
-    if (!g_free.empty()) { Engine* e = g_free.back(); g_free.pop_back(); return e; }
-    if (g_all.size() < max_contexts()) {
-      Engine* e = new Engine;
+    for (size_t i = 0; i < g_free.size(); i++)
+      if (g_free[i]->device() == dev) { Engine* e = g_free[i]; g_free.erase(g_free.begin() + i); return e; }
+    size_t have = 0;
+    for (Engine* e : g_all) have += e->device() == dev;
+    if (have < max_contexts()) {
+      Engine* e = new Engine(dev);
       g_all.push_back(e);
       return e;
     }
@@ -453,7 +476,7 @@ Engine* Engine::acquire() {
 }
 void Engine::release(Engine* e) {
   { std::lock_guard<std::mutex> g(g_pool_mu); g_free.push_back(e); }
-  g_pool_cv.notify_one();
+  g_pool_cv.notify_all();
 }
 
 int Engine::device() const { return p_->dev; }
@@ -629,6 +652,7 @@ void Engine::parse_common(const std::vector<ParseRange>& ranges, ParseResult& ou
     l.tic();
     CK(cudaMemcpyAsync(js.data(), l.jobs.p, ns * sizeof(JobState), cudaMemcpyDeviceToHost, l.stream));
     CK(cudaMemcpyAsync(counters, l.counters.p, sizeof(counters), cudaMemcpyDeviceToHost, l.stream));
+    l.toc(l.acc.ms_d2h);
     l.sync();
     if (L.any_parse && counters[0] > l.ovf_cap) {  // run-list overflow arena too small: grow, redo
       l.ovf_cap = counters[0] + counters[0] / 4 + 1024;
@@ -639,11 +663,12 @@ void Engine::parse_common(const std::vector<ParseRange>& ranges, ParseResult& ou
     out.ll.resize(total);
     out.d.resize(total);
     if (total) {
+      l.tic();
       CK(cudaMemcpyAsync(out.ll.data(), l.out_ll.p, (size_t)total * 2, cudaMemcpyDeviceToHost, l.stream));
       CK(cudaMemcpyAsync(out.d.data(), l.out_d.p, (size_t)total * 2, cudaMemcpyDeviceToHost, l.stream));
+      l.toc(l.acc.ms_d2h);
+      l.sync();
     }
-    l.toc(l.acc.ms_d2h);
-    l.sync();
     l.acc.d2h_bytes += (uint64_t)total * 4 + ns * sizeof(JobState);
     break;
   }
@@ -815,8 +840,8 @@ void Engine::greedy_to_split(const std::vector<ParseRange>& ranges, std::vector<
   std::vector<JobState> js(ns);
   l.tic();
   CK(cudaMemcpyAsync(js.data(), l.jobs.p, ns * sizeof(JobState), cudaMemcpyDeviceToHost, l.stream));
-  l.sync();
   l.toc(l.acc.ms_d2h);
+  l.sync();
   l.acc.d2h_bytes += ns * sizeof(JobState);
   std::vector<uint64_t> off(ns);
   for (size_t i = 0; i < ns; i++) { sizes[i] = js[i].greedy_size; off[i] = L.segs[i].pos_off; }
@@ -936,13 +961,15 @@ void Engine::plan_blocks(const std::vector<PlanReq>& reqs, std::vector<PlanCost>
   for (size_t i = 0; i < n; i++) costs[i] = PlanCost{hp[i].unc_bits, hp[i].fixed_bits, hp[i].dyn_bits};
 }
 
-void Engine::emit(const std::vector<EmitPiece>& pieces, uint64_t total_bits, uint8_t* host_dst) {
+void* Engine::stream() { return (void*)p_->lane[0].stream; }
+
+void* Engine::emit_device(const std::vector<EmitPiece>& pieces, uint64_t total_bits, size_t reserve_bytes) {
   Impl& m = *p_;
   Lane& l = m.lane[0];
   std::lock_guard<std::mutex> g(l.mu);
   CK(cudaSetDevice(m.dev));
   const size_t nbytes = (size_t)((total_bits + 7) / 8);
-  if (nbytes == 0) return;
+  const size_t cap = std::max(nbytes, reserve_bytes);
   const size_t np = pieces.size();
   std::vector<EmitDesc> ed(np);
   for (size_t i = 0; i < np; i++) {
@@ -964,7 +991,7 @@ void Engine::emit(const std::vector<EmitPiece>& pieces, uint64_t total_bits, uin
     }
     e.type_final = (uint32_t)p.type | ((uint32_t)(p.final ? 1 : 0) << 8);
   }
-  m.outbuf.ensure(nbytes + 64);
+  m.outbuf.ensure(cap + 64);
   m.emit_desc.ensure(np * sizeof(EmitDesc) + 64);
   m.err_flag.ensure(64);
   l.tic();
@@ -978,18 +1005,35 @@ void Engine::emit(const std::vector<EmitPiece>& pieces, uint64_t total_bits, uin
     CK(cudaGetLastError());
     l.acc.launches++;
   }
-  l.toc(l.acc.ms_pack);
-  l.tic();
   CK(cudaMemcpyAsync(&err, m.err_flag.p, 4, cudaMemcpyDeviceToHost, l.stream));
-  CK(cudaMemcpyAsync(host_dst, m.outbuf.p, nbytes, cudaMemcpyDeviceToHost, l.stream));
-  l.toc(l.acc.ms_d2h);
+  l.toc(l.acc.ms_pack);
   l.sync();
-  l.acc.d2h_bytes += nbytes;
   if (err) {
     fprintf(stderr, "zopfli-b200: emitted block %u does not match its predicted size (%s)\n", err & 0x3fffffffu,
             (err & 0x80000000u) ? "block" : "tree header");
     abort();
   }
+  return m.outbuf.p;
+}
+
+void Engine::download(const void* dev_src, uint8_t* host_dst, size_t nbytes) {
+  Impl& m = *p_;
+  Lane& l = m.lane[0];
+  std::lock_guard<std::mutex> g(l.mu);
+  CK(cudaSetDevice(m.dev));
+  if (nbytes == 0) return;
+  l.tic();
+  CK(cudaMemcpyAsync(host_dst, dev_src, nbytes, cudaMemcpyDeviceToHost, l.stream));
+  l.toc(l.acc.ms_d2h);
+  l.sync();
+  l.acc.d2h_bytes += nbytes;
+}
+
+void Engine::emit(const std::vector<EmitPiece>& pieces, uint64_t total_bits, uint8_t* host_dst) {
+  const size_t nbytes = (size_t)((total_bits + 7) / 8);
+  if (nbytes == 0) return;
+  const void* d = emit_device(pieces, total_bits, 0);
+  download(d, host_dst, nbytes);
 }
 
 uint64_t Engine::device_block_bits(const uint32_t* hist320) {

@@ -35,11 +35,14 @@ class Engine {
  public:
   // Engine contexts are leased for the duration of one API call (Engine::Lease): a context owns its
   // input buffers, lanes and arenas, so concurrent calls never share mutable device state.
-  static Engine* acquire();
+  // dev < 0: the process's default device (ZOPFLI_B200_DEVICE, else LOCAL_RANK, else 0)
+  static Engine* acquire(int dev = -1);
   static void release(Engine* e);
+  static int default_device();
+  static int device_count();
   struct Lease {
     Engine* e;
-    Lease() : e(Engine::acquire()) {}
+    explicit Lease(int dev = -1) : e(Engine::acquire(dev)) {}
     ~Lease() { Engine::release(e); }
     Lease(const Lease&) = delete;
     Lease& operator=(const Lease&) = delete;
@@ -113,6 +116,12 @@ class Engine {
     uint8_t buf, type, final, pad;   // type: 0 stored, 1 fixed, 2 dynamic
   };
   void emit(const std::vector<EmitPiece>& pieces, uint64_t total_bits, uint8_t* host_dst);
+  // The two halves of emit(), for callers that move the stream between GPUs first (dist.cpp): the
+  // emission leaves the stream in this context's output buffer (capacity >= reserve_bytes, zeroed up to
+  // the emitted size) and returns its device address; download() copies device bytes to the host.
+  void* emit_device(const std::vector<EmitPiece>& pieces, uint64_t total_bits, size_t reserve_bytes);
+  void download(const void* dev_src, uint8_t* host_dst, size_t nbytes);
+  void* stream();   // cudaStream_t of lane 0, the stream emit / download / set_input run on
   uint64_t input_size() const;
 
   void set_stream(void* cuda_stream);  // optional: run on the caller's stream
@@ -122,7 +131,7 @@ class Engine {
 
  private:
   void parse_common(const std::vector<ParseRange>& ranges, ParseResult& out, int dest, int lane);
-  Engine();
+  explicit Engine(int dev);
   struct Impl;
   Impl* p_;
 };
