@@ -183,7 +183,8 @@ def run_reference(args, rank):
 
 
 def run_product(args, rank, world):
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: one JSON line only
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner must not land on stdout: one JSON line only
     import torch
     import torch.distributed as dist
     import zopfli_b200 as zb

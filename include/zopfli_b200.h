@@ -128,6 +128,8 @@ void ZopfliB200DistFinalize(void);
 /* CRC-32 of the gzip trailer (gzip_container.c:27-81) and its combination across shards. */
 uint32_t ZopfliB200Crc32(const unsigned char* data, size_t size);
 uint32_t ZopfliB200Crc32Combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
+/* Adler-32 of the zlib trailer (zlib_container.c:29-48), threaded with an exact combination. */
+uint32_t ZopfliB200Adler32(const unsigned char* data, size_t size);
 
 /* Engine control / introspection. */
 typedef struct ZopfliB200Stats {

@@ -337,3 +337,15 @@ def test_optimize_for_rle_restatement(ref, host):
         if len(c) < n:
             c = np.pad(c, (0, n - len(c)))
         assert np.array_equal(ref.optimize_rle(c), host.host_optimize_rle(c)), (t, c.tolist())
+
+
+def test_checksums_threaded_and_combined(mock):
+    """CRC-32 / Adler-32 of the container trailers (gzip_container.c:27-81, zlib_container.c:29-48): the
+    threaded versions with their exact combination rules against zlib, across the threading threshold."""
+    import zlib
+    rng = np.random.default_rng(8)
+    for n in (0, 1, 5551, 5553, 70000, (4 << 20) - 1, (4 << 20) + 12345, 9000001):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes() if n % 2 else bytes([255]) * n
+        assert mock.adler32(d) == zlib.adler32(d), n
+        a = np.frombuffer(d, np.uint8)
+        assert mock.crc32(a.ctypes.data if n else 0, n) == zlib.crc32(d), n

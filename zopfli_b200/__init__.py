@@ -48,7 +48,7 @@ EXPORTS = ["ZopfliInitOptions", "ZopfliCompress", "ZopfliDeflate", "ZopfliDeflat
            "ZopfliGzipCompress", "ZopfliZlibCompress", "ZopfliB200LZ77", "ZopfliB200LZ77Batch",
            "ZopfliB200MatchTable", "ZopfliB200DynamicBlockBits", "ZopfliB200DeviceAutoTypeBits", "ZopfliB200HostBlockSplitLZ77",
            "ZopfliB200HostBatchedSplit", "ZopfliB200HostBlockSize", "ZopfliB200HostEmitBlock", "ZopfliB200HostLengthLimited", "ZopfliB200HostOptimizeRle",
-           "ZopfliB200DeflateSpan", "ZopfliB200AppendSpan", "ZopfliB200LastMasterBitOffsets", "ZopfliB200Crc32", "ZopfliB200Crc32Combine", "ZopfliB200CompressDevice",
+           "ZopfliB200DeflateSpan", "ZopfliB200AppendSpan", "ZopfliB200LastMasterBitOffsets", "ZopfliB200Crc32", "ZopfliB200Crc32Combine", "ZopfliB200Adler32", "ZopfliB200CompressDevice",
            "ZopfliB200DistUniqueId", "ZopfliB200DistInit", "ZopfliB200DistCompress", "ZopfliB200DistFinalize",
            "ZopfliB200GetStats", "ZopfliB200ResetStats", "ZopfliB200SetStream", "ZopfliB200Device",
            "ZopfliB200Version"]
@@ -136,6 +136,8 @@ class Library:
         L.ZopfliB200Crc32.restype = C.c_uint32
         L.ZopfliB200Crc32Combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
         L.ZopfliB200Crc32Combine.restype = C.c_uint32
+        L.ZopfliB200Adler32.argtypes = [vp, sz]
+        L.ZopfliB200Adler32.restype = C.c_uint32
         L.ZopfliB200DistUniqueId.argtypes = [vp]
         L.ZopfliB200DistInit.argtypes = [C.c_int, C.c_int, vp]
         L.ZopfliB200DistCompress.argtypes = [C.POINTER(ZopfliOptions), C.c_int, vp, sz, C.c_int, C.POINTER(vp), C.POINTER(sz)]
@@ -324,6 +326,10 @@ class Library:
 
     def crc32(self, host_ptr, nbytes) -> int:
         return int(self.lib.ZopfliB200Crc32(host_ptr, nbytes))
+
+    def adler32(self, data: bytes) -> int:
+        a = _pad(data)
+        return int(self.lib.ZopfliB200Adler32(a.ctypes.data, len(data)))
 
     def crc32_combine(self, crc1, crc2, len2) -> int:
         return int(self.lib.ZopfliB200Crc32Combine(crc1, crc2, len2))

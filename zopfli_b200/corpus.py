@@ -256,3 +256,35 @@ def mixed_small(n: int, seed: int = 9) -> bytes:
     parts = [t[: n // 2], b"\0" * (n // 8), bytes(rng.integers(0, 256, 24, dtype=np.uint8)) * (n // 96 + 1),
              rng.integers(0, 256, n // 8 + 8, dtype=np.uint8).tobytes(), t[n // 2:]]
     return b"".join(parts)[:n]
+
+
+def synth_image_rgba(w: int, h: int, seed: int = 5) -> np.ndarray:
+    """SURVEY 8(d) C5 stand-in: smooth gradients + 8x8-tile noise + flat alpha regions, (h, w, 4) uint8."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    img = np.zeros((h, w, 4), np.uint8)
+    img[..., 0] = (x * 255 // max(1, w - 1)).astype(np.uint8)
+    img[..., 1] = (y * 255 // max(1, h - 1)).astype(np.uint8)
+    img[..., 2] = (((x + y) // 3) & 255).astype(np.uint8)
+    tiles = rng.integers(0, 24, ((h + 7) // 8, (w + 7) // 8, 3), dtype=np.uint8)
+    img[..., :3] += np.kron(tiles, np.ones((8, 8, 1), np.uint8))[:h, :w]
+    alpha = np.full((h, w), 255, np.uint8)
+    alpha[h // 4: h // 2, w // 8: w // 2] = 0
+    alpha[h // 2:, 3 * w // 4:] = 128
+    img[..., 3] = alpha
+    return img
+
+
+def write_png_rgba(img: np.ndarray) -> bytes:
+    """minimal PNG writer (8-bit RGBA, filter type 0 on every scanline, zlib level 1)"""
+    import struct
+    import zlib
+    h, w, _ = img.shape
+    raw = np.zeros((h, 1 + w * 4), np.uint8)
+    raw[:, 1:] = img.reshape(h, w * 4)
+
+    def chunk(tag, body):
+        return struct.pack(">I", len(body)) + tag + body + struct.pack(">I", zlib.crc32(tag + body) & 0xffffffff)
+
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) +
+            chunk(b"IDAT", zlib.compress(raw.tobytes(), 1)) + chunk(b"IEND", b""))

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <mutex>
 #include <thread>
@@ -110,17 +111,50 @@ uint32_t crc32_parallel(const unsigned char* p, size_t n) {
   return crc;
 }
 
-// ---- Adler-32 (zlib_container.c:29-48) ----
-uint32_t adler32(const unsigned char* data, size_t size) {
-  uint32_t s1 = 1, s2 = 0;
-  while (size > 0) {
-    size_t amount = size > 5550 ? 5550 : size;
-    size -= amount;
-    while (amount--) { s1 += *data++; s2 += s1; }
-    s1 %= 65521;
-    s2 %= 65521;
+// ---- Adler-32 (zlib_container.c:29-48 computes it serially) ----
+// s1 = 1 + sum(d_i), s2 = sum over i of s1 after byte i (both mod 65521).  Sums of byte values and of
+// position-weighted byte values are associative, so chunks are summed in 64-bit integers by threads and
+// combined: s2(A|B) = s2(A) + len(B) * (s1(A) - 1 ... ) -- written out in adler_combine below.
+struct AdlerPart { uint64_t s1, s2, len; };  // s1 = sum of bytes, s2 = sum of (len - i) * d_i, both mod 65521
+AdlerPart adler_chunk(const unsigned char* p, size_t n) {
+  // 5552 bytes is the largest run whose 32-bit running sums cannot overflow (the zlib bound the
+  // reference also relies on with 5550)
+  uint32_t a = 0, b = 0;
+  size_t left = n;
+  while (left) {
+    const size_t k = left > 5552 ? 5552 : left;
+    for (size_t i = 0; i < k; i++) { a += p[i]; b += a; }
+    a %= 65521;
+    b %= 65521;
+    p += k;
+    left -= k;
   }
-  return (s2 << 16) | s1;
+  return {a, b, n};
+}
+uint32_t adler32(const unsigned char* data, size_t size) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > 16) nt = 16;
+  if (size < (4u << 20)) nt = 1;
+  std::vector<AdlerPart> part(nt);
+  const size_t chunk = (size + nt - 1) / nt;
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nt; t++)
+    th.emplace_back([&, t] {
+      const size_t a = std::min(size, t * chunk), b = std::min(size, a + chunk);
+      part[t] = adler_chunk(data + a, b - a);
+    });
+  part[0] = adler_chunk(data, std::min(size, chunk));
+  for (auto& t : th) t.join();
+  // with a = sum of bytes and b = sum of prefix sums (both without the initial 1):
+  //   a(A|B) = a(A) + a(B),  b(A|B) = b(A) + len(B) * a(A) + b(B);  the initial s1 = 1 adds `size` to s2
+  uint64_t a = 0, b = 0;
+  for (unsigned t = 0; t < nt; t++) {
+    b = (b + (part[t].len % 65521) * a + part[t].s2) % 65521;
+    a = (a + part[t].s1) % 65521;
+  }
+  const uint64_t s1 = (1 + a) % 65521, s2 = (b + size % 65521) % 65521;
+  return (uint32_t)((s2 << 16) | s1);
 }
 
 void put_byte(unsigned char v, unsigned char** out, size_t* outsize) { append_bytes(&v, 1, out, outsize); }
@@ -208,12 +242,14 @@ void container_impl(const ZopfliOptions* options, ZopfliFormat fmt, const unsign
       fprintf(stderr, "Original Size: %d, Gzip: %d, Compression: %f%% Removed\n", (int)insize, (int)*outsize,
               100.0 * (double)(insize - *outsize) / (double)insize);
   } else if (fmt == ZOPFLI_FORMAT_ZLIB) {  // zlib_container.c:50-79
-    uint32_t checksum = adler32(in, insize);
+    uint32_t checksum = 0;
+    std::thread adler_thread([&] { checksum = adler32(in, insize); });  // overlaps the GPU work
     unsigned cmfflg = 256 * 120 + 3 * 64;
     cmfflg += 31 - cmfflg % 31;
     put_byte((unsigned char)(cmfflg / 256), out, outsize);
     put_byte((unsigned char)(cmfflg % 256), out, outsize);
     body(&bp);
+    adler_thread.join();
     unsigned char tr[4] = {(unsigned char)((checksum >> 24) & 255), (unsigned char)((checksum >> 16) & 255),
                            (unsigned char)((checksum >> 8) & 255), (unsigned char)(checksum & 255)};
     append_bytes(tr, 4, out, outsize);
@@ -355,6 +391,7 @@ int ZopfliB200DeflateSpan(const ZopfliOptions* options, const unsigned char* in,
 
 uint32_t ZopfliB200Crc32(const unsigned char* data, size_t size) { return crc32_parallel(data, size); }
 uint32_t ZopfliB200Crc32Combine(uint32_t crc1, uint32_t crc2, uint64_t len2) { return crc32_combine(crc1, crc2, len2); }
+uint32_t ZopfliB200Adler32(const unsigned char* data, size_t size) { return adler32(data, size); }
 
 int ZopfliB200AppendSpan(const unsigned char* span, size_t spansize, unsigned char* bp, unsigned char** out,
                          size_t* outsize) {
