@@ -37,9 +37,46 @@ GIANT_MASTERS = [85, 84, 78, 42, 40]            # master blocks of the C2 text w
 UNIFORM_MASTERS = [3, 15, 27, 39, 51, 63, 75, 99]  # (tools/find_giant_masters.py)
 
 
+WORKLOAD = "c2"   # c2 (default, the metric's config) | c3 (1 GiB, strong scaling) | c4 (binary, 50 iterations)
+SCALING = "weak"
+
+
+def select_workload(name, world):
+    """BASELINE.json configs: C2 = 100 MB text per GPU at 15 iterations (the bench line the driver reads);
+    C3 = one 1 GiB text stream over 1/2/4/8 GPUs (strong scaling: the same bytes at every N);
+    C4 = 51,220,480 B of redundant binary at 50 iterations on one GPU."""
+    global WORKLOAD, SHARD, NUMITER, SCALING, REF_MASTERS
+    WORKLOAD = name
+    if name == "c3":
+        assert (1 << 30) % world == 0 and 8 % world == 0
+        SHARD, NUMITER, SCALING = (1 << 30) // world, 15, "strong"
+    elif name == "c4":
+        assert world == 1
+        SHARD, NUMITER, REF_MASTERS = 51220480, 50, 2
+    elif name != "c2":
+        raise SystemExit("unknown workload " + name)
+
+
+def segment(rank, world):
+    """this rank's part of the one input (rank 0 assembles the parts in rank order)"""
+    from zopfli_b200 import corpus
+    if WORKLOAD == "c3":   # eight fixed 128 MiB segments (seeds 3..10), 8 / world of them per rank
+        per = 8 // world
+        return b"".join(corpus.synth_text(1 << 27, 3 + rank * per + k) for k in range(per)), "synthetic"
+    if WORKLOAD == "c4":
+        return corpus.synth_binary(SHARD, 4), "synthetic"
+    return workload(SHARD, 2 + rank)
+
+
 def bench_config(world):
-    return {"workload": "C2 enwik8-like text, %d B per GPU (%d B total, one stream), gzip, numiterations=15, "
-                        "blocksplittingmax=15" % (SHARD, SHARD * world),
+    if WORKLOAD == "c3":
+        what = "C3 web-text-like, 1073741824 B in one stream (%d B per GPU), gzip, numiterations=15, blocksplittingmax=15" % SHARD
+    elif WORKLOAD == "c4":
+        what = "C4 redundant binary, %d B, gzip, numiterations=50, blocksplittingmax=15" % SHARD
+    else:
+        what = ("C2 enwik8-like text, %d B per GPU (%d B total, one stream), gzip, numiterations=15, "
+                "blocksplittingmax=15" % (SHARD, SHARD * world))
+    return {"workload": what,
             "l2": "inputs and working set (GBs) far larger than the 126 MB L2; no flush needed",
             "parallelism": "master-block shards x%d inside the library: NCCL scatter of byte ranges, NCCL gather of "
                            "compressed bits at their final bit offsets" % world if world > 1
@@ -165,16 +202,16 @@ def check_against_reference(stream, offs, data, masters, prefix_out=None, prefix
 def run_reference(args, rank):
     if rank != 0:
         return
-    data, kind = workload(SHARD, 2)
+    data, kind = segment(0, 1) if WORKLOAD != "c2" else workload(SHARD, 2)
     steps, warmup = args.steps, args.warmup
     # the whole run is bounded to a few minutes: ~1.6 s of CPU per master block
     masters = min(REF_MASTERS, max(2, int(150 / max(1, steps))))
     v, sec, _ = cpu_reference(data, masters, steps, warmup)
     sample = ("first %d bytes (%d master blocks) of the workload per step, oracle/_ref -O3 -DNDEBUG, 1 thread "
               "(the reference has no threading); warm-up steps use 1 master block" % (masters * MB, masters))
-    line = {"impl": "reference", "metric": "input MiB/s at numiterations=15", "value": v, "unit": "MiB/s",
+    line = {"impl": "reference", "metric": "input MiB/s at numiterations=%d" % NUMITER, "value": v, "unit": "MiB/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": kind,
+            "higher_is_better": True, "scaling": SCALING, "vs_baseline": None, "dtype": "u8", "data": kind,
             "config": bench_config(args.gpus),
             "cpu_baseline": {"value": v, "unit": "MiB/s", "cores": 1, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "MiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,7 +236,7 @@ def run_product(args, rank, world):
     steps, warmup = args.steps, args.warmup
 
     # ---- the workload: rank r generates segment r (seed 2 + r); rank 0 assembles the one input ----
-    seg, kind = workload(SHARD, 2 + rank)
+    seg, kind = segment(rank, world)
     n_total = SHARD * world
     if world > 1:
         mine = torch.frombuffer(bytearray(seg), dtype=torch.uint8).to(dev)
@@ -287,7 +324,8 @@ def run_product(args, rank, world):
             cpu = {"value": cpu_v, "unit": "MiB/s", "cores": 1, "kind": "reference",
                    "sample": "first %d bytes (%d master blocks) of the workload, oracle/_ref -O3 -DNDEBUG, 1 thread "
                              "(the reference has no threading)" % (REF_MASTERS * MB, REF_MASTERS)}
-            masters = GIANT_MASTERS + UNIFORM_MASTERS if kind == "synthetic" else list(range(8, nm, max(1, nm // 13)))[:13]
+            masters = GIANT_MASTERS + UNIFORM_MASTERS if (kind == "synthetic" and WORKLOAD == "c2") else \
+                list(range(REF_MASTERS, nm, max(1, nm // 13)))[:13]
             covered, same = check_against_reference(out_res, offs, data, masters, ref_out, REF_MASTERS)
             check = {"sample_bytes": covered, "identical": bool(same), "delta_bytes_vs_reference": 0 if same else None,
                      "how": "timed output vs reference: bit prefix of the first %d master blocks + ZopfliDeflatePart of "
@@ -316,12 +354,12 @@ def run_product(args, rank, world):
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         cyc = st_res["cyc_max"]
         maxpos = int(st_res["max_block_positions"])
-        line = {"metric": "input MiB/s at numiterations=15", "value": n_total / MIB / (ms_res / 1e3), "unit": "MiB/s",
+        line = {"metric": "input MiB/s at numiterations=%d" % NUMITER, "value": n_total / MIB / (ms_res / 1e3), "unit": "MiB/s",
                 "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_res, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": kind,
+                "scaling": SCALING, "vs_baseline": None, "dtype": "u8", "data": kind,
                 "config": bench_config(world),
                 "e2e": {"value": n_total / MIB / (ms_e2e / 1e3), "unit": "MiB/s", "ms_per_step": ms_e2e,
-                        "h2d_bytes_per_step": st_e2e["h2d_bytes"] / steps + (n_total if world > 1 else 0),
+                        "h2d_bytes_per_step": st_e2e["h2d_bytes"] / steps,
                         "d2h_bytes_per_step": st_e2e["d2h_bytes"] / steps, "host_buffer": "pageable"},
                 "gpu_launches": int(st_res["launches"]),
                 "clocks": clocks,
@@ -355,9 +393,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="c2", help="c2 (default) | c3 (1 GiB, strong scaling) | c4 (binary, 50 iterations)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    select_workload(args.workload, world)
     if args.impl == "reference":
         run_reference(args, rank)
     else:

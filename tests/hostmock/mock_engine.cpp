@@ -138,6 +138,7 @@ void Engine::emit(const std::vector<EmitPiece>& pieces, uint64_t total_bits, uin
 }
 void* Engine::emit_device(const std::vector<EmitPiece>&, uint64_t, size_t) { return nullptr; }
 void Engine::download(const void*, uint8_t*, size_t) {}
+void Engine::upload(void*, const uint8_t*, size_t) {}
 void* Engine::stream() { return nullptr; }
 void Engine::match_table(uint64_t, uint64_t, std::vector<uint16_t>&, std::vector<uint16_t>&,
                          std::vector<uint16_t>&, std::vector<uint16_t>&, std::vector<uint16_t>&,

@@ -61,6 +61,7 @@ def test_c2_giant_and_sampled_master_blocks(lib, c2):
     masters = GIANT_MASTERS + UNIFORM_MASTERS
     parts = _slices(c2, masters)
     want = _reference_parts(parts, 15)
+    lib.reset_stats()
     for m, (piece, s, e), w in zip(masters, parts, want):
         got = lib.deflate_part(piece, s, e, final=1, numiterations=15)   # (bytes, bp)
         assert got == w, "master block %d differs from the reference (%d vs %d bytes)" % (m, len(got[0]), len(w[0]))
@@ -122,3 +123,13 @@ def test_device_auto_type_bits_seam(ref, lib):
         got = lib.device_auto_type_bits(ll, dd, lo, hi)
         for i in range(len(lo)):
             assert float(got[i]) == ref.block_size(data[s:e], ll, dd, int(lo[i]), int(hi[i]), -1), (s, e, lo[i], hi[i])
+
+
+def test_one_block_larger_than_a_master_block(ref, lib):
+    """ZopfliDeflatePart over 2.5 MB with block splitting off: ONE deflate block whose symbol counts pass
+    the default 2^21-entry log table (the table grows on demand instead of aborting)."""
+    data = corpus.synth_text(2500000, 9)
+    for kw in ({"numiterations": 7, "blocksplitting": 0},):
+        a = ref.deflate_part(data, 0, len(data), final=1, **kw)
+        b = lib.deflate_part(data, 0, len(data), final=1, **kw)
+        assert a == b, kw

@@ -3,11 +3,9 @@
 set -e
 cd "$(dirname "$0")/../zopfli_b200/csrc"
 mkdir -p ../_var
-FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -Wno-deprecated-gpu-targets -shared engine.cu driver.cpp api.cpp -Xlinker -soname=libzopfli.so.1 -lpthread"
+FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -Wno-deprecated-gpu-targets -shared engine.cu driver.cpp api.cpp dist.cpp -Xlinker -soname=libzopfli.so.1 -lpthread -ldl"
 build() { name=$1; shift; nvcc $FLAGS "$@" -o ../_var/lib_$name.so & }
-build base
 # build name -DZB_VAR_...   (add experiment variants here; the kernels pick them up with #ifdef)
-build xchsplit -DZB_VAR_XCH_SPLIT   # k_iterate: hand-off slot as 8+4 byte accesses
 build sig -DZB_VAR_SIG   # k_match: candidate prefix and hashval2 from the bucket entry (kernels.cuh)
 wait
 ls -la ../_var

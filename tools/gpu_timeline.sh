@@ -9,7 +9,7 @@ import numpy as np
 import zopfli_b200 as zb
 from zopfli_b200 import corpus
 data = corpus.synth_text(100000000, 2)
-lib = zb.library()
+lib = zb.Library(os.environ['ZB_LIB']) if os.environ.get('ZB_LIB') else zb.library()
 host = np.frombuffer(data, dtype=np.uint8).copy()
 for i in range(3):
     t = time.perf_counter()
@@ -19,8 +19,8 @@ for i in range(3):
 st = lib.stats()
 print({k: round(v, 1) for k, v in st.items() if k.startswith("ms_")}, file=sys.stderr)
 PY
-for v in "base" "conn CUDA_DEVICE_MAX_CONNECTIONS=32" "eager ZOPFLI_B200_SYNC_TOC=1" "both CUDA_DEVICE_MAX_CONNECTIONS=32 ZOPFLI_B200_SYNC_TOC=1"; do
-  set -- $v; name=$1; shift
-  env ZOPFLI_B200_DEBUG=1 "$@" python /tmp/tl.py 2> gpurun_out/timeline_$name.txt
-  grep "call\|ms_" gpurun_out/timeline_$name.txt | sed "s/^/$name: /"
-done
+run() { name=$1; shift; env ZOPFLI_B200_DEBUG=1 "$@" python /tmp/tl.py 2> gpurun_out/timeline_$name.txt; grep "call\|ms_" gpurun_out/timeline_$name.txt | sed "s/^/$name: /"; }
+run base ZB_X=0
+[ -f zopfli_b200/_var/lib_sig.so ] && run sig ZB_LIB=zopfli_b200/_var/lib_sig.so
+[ -n "$TL_DEFERRED" ] && run deferred ZOPFLI_B200_SYNC_TOC=0
+exit 0

@@ -40,4 +40,4 @@ if len(sys.argv) > 3:
         json.dump({"k_iterate_bytes_per_launch": (a["rd"] + a["wr"]) / a["n"], "k_iterate_launches_captured": a["n"],
                    "dram_read_bytes_per_launch": a["rd"] / a["n"], "dram_write_bytes_per_launch": a["wr"] / a["n"],
                    "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the k_iterate launches of one bench.py step "
-                             "(profiles/r1_launches.txt)"}, open(sys.argv[3], "w"), indent=1)
+                             "(profiles/r2_launches.txt)"}, open(sys.argv[3], "w"), indent=1)

@@ -138,7 +138,7 @@ void rank_deflate(Rank& rk, const ZopfliOptions* opt, int final, const unsigned 
   } else if (r == 0) {
     uint8_t* d = (uint8_t*)rk.input.ensure(insize + 64);
     DCK(cudaMemsetAsync(d + insize, 0, 64, st));
-    if (insize) DCK(cudaMemcpyAsync(d, in, insize, cudaMemcpyHostToDevice, st));
+    eng->upload(d, in, insize);  // threaded pinned staging; synchronous
     NCK(g_nccl.GroupStart());
     for (int q = 1; q < W; q++) {
       size_t qa, qb, qbase;

@@ -76,35 +76,136 @@ struct LogService {
   std::vector<double> host;
   bool started = false, joined = false;
   double* dev[64] = {nullptr};
+  uint32_t dev_n[64] = {0};
+  static void fill(std::vector<double>& t, uint32_t from, uint32_t to) {
+    static const double kInvLog2 = 1.4426950408889;
+    for (uint32_t i = from; i < to; i++) {
+      volatile double l = i ? log((double)i) : 0.0;
+      t[i] = i ? l * kInvLog2 : 0.0;
+    }
+  }
   void start() {
     std::lock_guard<std::mutex> g(mu);
     if (started) return;
     started = true;
     filler = std::thread([this]() {
       host.resize(kLogTabN);
-      static const double kInvLog2 = 1.4426950408889;
-      host[0] = 0.0;
-      for (uint32_t i = 1; i < kLogTabN; i++) {
-        volatile double l = log((double)i);
-        host[i] = l * kInvLog2;
-      }
+      fill(host, 0, kLogTabN);
     });
   }
-  const double* get(int device, cudaStream_t st) {
+  // table with at least need_n entries on `device`.  The default 2^21 entries cover every count a master
+  // block can produce (symbols <= 10^6, blended statistics < 2x that); larger single ranges
+  // (ZopfliDeflatePart with block splitting off) grow the table on demand.  An outgrown device copy is
+  // left allocated: other contexts may still be reading it.
+  const double* get(int device, cudaStream_t st, uint32_t need_n, uint32_t* have_n) {
     std::lock_guard<std::mutex> g(mu);
     if (!joined) { filler.join(); joined = true; }
-    double*& d = dev[device & 63];
-    if (!d) {
-      CK(cudaMalloc(&d, kLogTabN * sizeof(double)));
-      CK(cudaMemcpyAsync(d, host.data(), kLogTabN * sizeof(double), cudaMemcpyHostToDevice, st));
-      CK(cudaStreamSynchronize(st));
+    if (need_n < kLogTabN) need_n = kLogTabN;
+    if (host.size() < need_n) {
+      const uint32_t old = (uint32_t)host.size();
+      host.resize(need_n);
+      fill(host, old, need_n);
     }
+    double*& d = dev[device & 63];
+    if (!d || dev_n[device & 63] < need_n) {
+      CK(cudaMalloc(&d, (size_t)need_n * sizeof(double)));
+      CK(cudaMemcpyAsync(d, host.data(), (size_t)need_n * sizeof(double), cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+      dev_n[device & 63] = need_n;
+    }
+    *have_n = dev_n[device & 63];
     return d;
   }
 };
 LogService g_log;
 
 }  // namespace
+
+struct PinBuf {  // grow-only page-locked host staging: round trips through it skip the driver's own staging copy
+  void* p = nullptr;
+  size_t cap = 0;
+  void* ensure(size_t bytes) {
+    if (bytes > cap) {
+      if (p) CK(cudaFreeHost(p));
+      cap = bytes + bytes / 4 + 4096;
+      CK(cudaMallocHost(&p, cap));
+    }
+    return p;
+  }
+};
+
+// Pageable host memory <-> device through page-locked staging, several host threads deep: a pageable
+// cudaMemcpy is one thread's memcpy into the driver's staging buffer (~10 GB/s); here kThreads threads
+// each shuttle 8 MB chunks through their own pinned double buffer and stream, so the copy runs at
+// whatever the link sustains.  Buffers that are already page-locked go straight to the DMA engine.
+struct Stager {
+  static constexpr int kThreads = 6;
+  static constexpr size_t kChunk = 8u << 20;
+  int dev = 0;
+  bool ready = false;
+  std::mutex mu;
+  cudaStream_t st[kThreads];
+  cudaEvent_t ev[kThreads][2];
+  uint8_t* pin[kThreads][2];
+  void init(int device) {
+    if (ready) return;
+    dev = device;
+    for (int t = 0; t < kThreads; t++) {
+      CK(cudaStreamCreateWithFlags(&st[t], cudaStreamNonBlocking));
+      for (int k = 0; k < 2; k++) {
+        CK(cudaEventCreateWithFlags(&ev[t][k], cudaEventDisableTiming));
+        CK(cudaMallocHost((void**)&pin[t][k], kChunk));
+      }
+    }
+    ready = true;
+  }
+  static bool page_locked(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  }
+  // synchronous: returns when all n bytes have arrived
+  void copy(uint8_t* dst, const uint8_t* src, size_t n, bool to_device, int device) {
+    if (n == 0) return;
+    std::lock_guard<std::mutex> g(mu);
+    CK(cudaSetDevice(device));
+    init(device);
+    if (n < 2 * kChunk || page_locked(to_device ? (const void*)src : (const void*)dst)) {
+      CK(cudaMemcpyAsync(dst, src, n, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, st[0]));
+      CK(cudaStreamSynchronize(st[0]));
+      return;
+    }
+    const size_t nchunks = (n + kChunk - 1) / kChunk;
+    const int nt = (int)std::min<size_t>(kThreads, nchunks);
+    auto work = [&](int t) {
+      CK(cudaSetDevice(device));
+      int slot = 0;
+      size_t pend_off[2] = {0, 0}, pend_len[2] = {0, 0};  // device->host: chunks whose DMA is in flight
+      for (size_t c = (size_t)t; c < nchunks; c += (size_t)nt, slot ^= 1) {
+        const size_t off = c * kChunk, len = std::min(kChunk, n - off);
+        CK(cudaEventSynchronize(ev[t][slot]));  // the slot's previous transfer is done
+        if (to_device) {
+          memcpy(pin[t][slot], src + off, len);
+          CK(cudaMemcpyAsync(dst + off, pin[t][slot], len, cudaMemcpyHostToDevice, st[t]));
+        } else {
+          if (pend_len[slot]) memcpy(dst + pend_off[slot], pin[t][slot], pend_len[slot]);
+          CK(cudaMemcpyAsync(pin[t][slot], src + off, len, cudaMemcpyDeviceToHost, st[t]));
+          pend_off[slot] = off;
+          pend_len[slot] = len;
+        }
+        CK(cudaEventRecord(ev[t][slot], st[t]));
+      }
+      CK(cudaStreamSynchronize(st[t]));
+      if (!to_device)
+        for (int k = 0; k < 2; k++)
+          if (pend_len[k]) memcpy(dst + pend_off[k], pin[t][k], pend_len[k]);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+  }
+};
 
 struct Lane {  // an independent stream + arena set; chunk pipelines use a pair each (giant blocks beside the rest)
   std::mutex mu;
@@ -122,6 +223,7 @@ struct Lane {  // an independent stream + arena set; chunk pipelines use a pair 
       ovf, la, path, st[4], jobs, out_ll, out_d, counters, misc;
   // split service
   DevBuf sp_ll, sp_d, sp_llsym, sp_dsym, sp_pos, sp_snaps, sp_stores, sp_work, sp_evals, sp_out;
+  PinBuf pin_req, pin_out;
   std::vector<SplitStoreDesc> sp_desc;
   SplitBatch sp_batch;
   uint32_t ovf_cap = 1u << 22;
@@ -184,6 +286,7 @@ struct Engine::Impl {
   // input (shared, read-only while parses run)
   DevBuf in_buf, same_buf, tile_first, next_tile;
   const double* logtab = nullptr;  // shared per-device table (LogService)
+  uint32_t logtab_n = 0;
   const uint8_t* d_in = nullptr;
   uint64_t insize = 0;
   EngineStats st_acc;  // input-side counters; lane counters are merged in stats()
@@ -194,6 +297,7 @@ struct Engine::Impl {
   std::vector<Slab> slabs;
   size_t slab_idx = 0, slab_used = 0;
   DevBuf outbuf, emit_desc, err_flag;
+  Stager stager;
 
   void begin_call() {  // a new input: plans of the previous call are dead
     std::lock_guard<std::mutex> g(fin_mu);
@@ -256,8 +360,9 @@ struct Engine::Impl {
     g_log.start();
   }
 
+  uint32_t log_need = 0;  // entries the current batch asks for (0: the default size)
   void ensure_log() {  // caller holds mu
-    if (!logtab) logtab = g_log.get(dev, lane[0].stream);
+    if (!logtab || logtab_n < log_need) logtab = g_log.get(dev, lane[0].stream, log_need, &logtab_n);
   }
 
   void compute_same() {  // caller holds mu; runs on lane 0's stream and completes before returning
@@ -392,7 +497,7 @@ struct Engine::Impl {
     b.st_d[2] = nullptr;
     b.jobs = l.jobs.as<JobState>();
     b.logtab = logtab;
-    b.logtab_n = kLogTabN;
+    b.logtab_n = logtab_n;
     b.out_ll = l.out_ll.as<uint16_t>();
     b.out_d = l.out_d.as<uint16_t>();
     b.out_used = l.counters.as<uint32_t>() + 1;
@@ -558,8 +663,9 @@ void Engine::set_input_host(const uint8_t* in, size_t insize) {
   m.in_buf.ensure(insize + 64);
   l.tic();
   CK(cudaMemsetAsync((uint8_t*)m.in_buf.p + insize, 0, 64, l.stream));
-  if (insize) CK(cudaMemcpyAsync(m.in_buf.p, in, insize, cudaMemcpyHostToDevice, l.stream));
   l.toc(m.st_acc.ms_h2d);
+  l.sync();  // the buffer exists (stream-ordered allocation) before other streams write into it
+  m.stager.copy((uint8_t*)m.in_buf.p, in, insize, true, m.dev);
   m.st_acc.h2d_bytes += insize;
   m.d_in = m.in_buf.as<uint8_t>();
   m.insize = insize;
@@ -616,10 +722,19 @@ void Engine::parse_common(const std::vector<ParseRange>& ranges, ParseResult& ou
   m.build_layout(ranges, L);
   std::vector<JobState> js(ns);
   uint32_t counters[2] = {0, 0};
+  {  // statistics counts stay below 2 x symbols (blended statistics, squeeze.c:70-75): size the log table for it
+    uint64_t need = 0;
+    for (const SegDesc& sg : L.segs)
+      if (sg.mode == 1) need = std::max<uint64_t>(need, 2ull * sg.npos + 16);
+    if (need > kLogTabN) {
+      std::lock_guard<std::mutex> g(m.mu);
+      if (need > m.log_need) m.log_need = (uint32_t)std::min<uint64_t>(need, 0xfffffff0ull);
+    }
+  }
   for (int attempt = 0;; attempt++) {
     Batch b = m.prepare(L, l);
     l.tic();
-    k_greedy<<<(unsigned)ns, 32, 0, l.stream>>>(b, 0);
+    k_greedy<<<(unsigned)ns, kGreedyThreads, 0, l.stream>>>(b, 0);
     CK(cudaGetLastError());
     l.toc(l.acc.ms_greedy);
     l.acc.launches++;
@@ -682,8 +797,8 @@ void Engine::parse_common(const std::vector<ParseRange>& ranges, ParseResult& ou
       abort();
     }
     if (js[i].flags & 1) {
-      fprintf(stderr, "zopfli-b200: symbol count beyond the %u-entry log table in block %zu "
-              "(iteration %u); not supported yet\n", kLogTabN, i, js[i].iters_done);
+      fprintf(stderr, "zopfli-b200: symbol count beyond the %u-entry log table in block %zu (iteration %u)\n",
+              m.logtab_n, i, js[i].iters_done);
       abort();
     }
     if (js[i].flags & 2) { fprintf(stderr, "zopfli-b200: corrupted length chain in block %zu\n", i); abort(); }
@@ -833,7 +948,7 @@ void Engine::greedy_to_split(const std::vector<ParseRange>& ranges, std::vector<
   m.build_layout(ranges, L);
   Batch b = m.prepare(L, l);
   l.tic();
-  k_greedy<<<(unsigned)ns, 32, 0, l.stream>>>(b, 0);
+  k_greedy<<<(unsigned)ns, kGreedyThreads, 0, l.stream>>>(b, 0);
   CK(cudaGetLastError());
   l.toc(l.acc.ms_greedy);
   l.acc.launches++;
@@ -883,10 +998,13 @@ void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lan
   const size_t kChunk = 32768;  // scratch is per evaluation: bound it
   l.sp_evals.ensure(n * sizeof(SplitEval) + 64);
   l.sp_out.ensure(n * 8 + 64);
-  std::vector<SplitEval> ev(n);
+  // one round of the split search = one latency-bound round trip: requests and answers go through
+  // page-locked staging so that neither copy waits for the driver's pageable path
+  SplitEval* ev = (SplitEval*)l.pin_req.ensure(n * sizeof(SplitEval));
+  uint64_t* res = (uint64_t*)l.pin_out.ensure(n * 8);
   for (size_t i = 0; i < n; i++) ev[i] = {reqs[i].store, reqs[i].lstart, reqs[i].lend, 0};
   l.tic();
-  CK(cudaMemcpyAsync(l.sp_evals.p, ev.data(), n * sizeof(SplitEval), cudaMemcpyHostToDevice, l.stream));
+  CK(cudaMemcpyAsync(l.sp_evals.p, ev, n * sizeof(SplitEval), cudaMemcpyHostToDevice, l.stream));
   SplitBatch b = l.sp_batch;
   for (size_t o = 0; o < n; o += kChunk) {
     const size_t c = std::min(kChunk, n - o);
@@ -895,9 +1013,10 @@ void Engine::split_eval(const SplitReq* reqs, size_t n, uint64_t* costs, int lan
     l.acc.launches++;
   }
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(costs, l.sp_out.p, n * 8, cudaMemcpyDeviceToHost, l.stream));
+  CK(cudaMemcpyAsync(res, l.sp_out.p, n * 8, cudaMemcpyDeviceToHost, l.stream));
   l.toc(l.acc.ms_split);
   l.sync();
+  memcpy(costs, res, n * 8);
   l.acc.split_evals += n;
   l.acc.split_rounds++;
 }
@@ -1022,11 +1141,15 @@ void Engine::download(const void* dev_src, uint8_t* host_dst, size_t nbytes) {
   std::lock_guard<std::mutex> g(l.mu);
   CK(cudaSetDevice(m.dev));
   if (nbytes == 0) return;
-  l.tic();
-  CK(cudaMemcpyAsync(host_dst, dev_src, nbytes, cudaMemcpyDeviceToHost, l.stream));
-  l.toc(l.acc.ms_d2h);
-  l.sync();
+  m.stager.copy(host_dst, (const uint8_t*)dev_src, nbytes, false, m.dev);
   l.acc.d2h_bytes += nbytes;
+}
+
+void Engine::upload(void* dev_dst, const uint8_t* host_src, size_t nbytes) {
+  Impl& m = *p_;
+  m.stager.copy((uint8_t*)dev_dst, host_src, nbytes, true, m.dev);
+  std::lock_guard<std::mutex> g(m.mu);
+  m.st_acc.h2d_bytes += nbytes;
 }
 
 void Engine::emit(const std::vector<EmitPiece>& pieces, uint64_t total_bits, uint8_t* host_dst) {

@@ -121,6 +121,8 @@ class Engine {
   // the emitted size) and returns its device address; download() copies device bytes to the host.
   void* emit_device(const std::vector<EmitPiece>& pieces, uint64_t total_bits, size_t reserve_bytes);
   void download(const void* dev_src, uint8_t* host_dst, size_t nbytes);
+  // host -> device through the context's threaded pinned staging (synchronous)
+  void upload(void* dev_dst, const uint8_t* host_src, size_t nbytes);
   void* stream();   // cudaStream_t of lane 0, the stream emit / download / set_input run on
   uint64_t input_size() const;
 

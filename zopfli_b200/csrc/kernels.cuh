@@ -551,7 +551,7 @@ __device__ __forceinline__ uint32_t table_dist(const Batch& b, uint64_t o, uint3
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_greedy: ZopfliLZ77Greedy (lz77.c:544-630) over the (len,dist) table; one warp per segment.
+// k_greedy: ZopfliLZ77Greedy (lz77.c:544-630) over the (len,dist) table; one CTA of four warps per segment.
 //
 // The reference's lazy-matching loop is a state machine with two kinds of state per position:
 // B(i) "at i, nothing pending" and H(j) "at j, the match found at j-1 is pending".  Everything
@@ -595,16 +595,19 @@ __device__ __forceinline__ uint32_t greedy_walk(const uint32_t* T, const uint8_t
   }
 }
 
-__global__ void __launch_bounds__(32) k_greedy(Batch b, int buf) {
+constexpr int kGreedyThreads = 128;
+
+__global__ void __launch_bounds__(kGreedyThreads) k_greedy(Batch b, int buf) {
   __shared__ uint32_t wld[kGreedyWin + kGreedyLook];
   __shared__ uint8_t wby[kGreedyWin + kGreedyLook];
   __shared__ uint32_t wf[kGreedyWin];      // distance to the next B state (16) | symbols emitted (16)
   __shared__ uint32_t bl[kGreedyWin];      // visited B states: relative position (16) | output offset (16)
   __shared__ uint16_t oll[kGreedyWin + 512], od[kGreedyWin + 512];
-  const uint32_t seg = blockIdx.x, lane = threadIdx.x;
+  __shared__ uint32_t hop_r, hop_k, hop_off;
+  const uint32_t seg = blockIdx.x, tid = threadIdx.x;
   const SegDesc sd = b.segs[seg];
   if (sd.mode == 2) {  // fixed-tree parse needs no greedy seed
-    if (lane == 0) b.jobs[seg].greedy_size = 0;
+    if (tid == 0) b.jobs[seg].greedy_size = 0;
     return;
   }
   const uint32_t* ld = b.ld + sd.pos_off;
@@ -617,34 +620,35 @@ __global__ void __launch_bounds__(32) k_greedy(Batch b, int buf) {
     const uint32_t wb = i;
     const uint32_t wn = (n - wb) < (uint32_t)(kGreedyWin + kGreedyLook) ? (n - wb) : (uint32_t)(kGreedyWin + kGreedyLook);
     const uint32_t nchain = wn < (uint32_t)kGreedyWin ? wn : (uint32_t)kGreedyWin;
-    for (uint32_t tb = 0; tb < wn; tb += 32 * 8) {  // 16 loads in flight per lane: the refill is pure latency
-      uint32_t v[8], c[8];
+    for (uint32_t tb = 0; tb < wn; tb += kGreedyThreads * 4) {  // several loads in flight per thread: the refill is pure latency
+      uint32_t v[4], c[4];
 #pragma unroll
-      for (int u = 0; u < 8; u++) { const uint32_t t = tb + u * 32 + lane; v[u] = t < wn ? ld[wb + t] : 0u; c[u] = t < wn ? (uint32_t)in[wb + t] : 0u; }
+      for (int u = 0; u < 4; u++) { const uint32_t t = tb + u * kGreedyThreads + tid; v[u] = t < wn ? ld[wb + t] : 0u; c[u] = t < wn ? (uint32_t)in[wb + t] : 0u; }
 #pragma unroll
-      for (int u = 0; u < 8; u++) { const uint32_t t = tb + u * 32 + lane; if (t < wn) { wld[t] = v[u]; wby[t] = (uint8_t)c[u]; } }
+      for (int u = 0; u < 4; u++) { const uint32_t t = tb + u * kGreedyThreads + tid; if (t < wn) { wld[t] = v[u]; wby[t] = (uint8_t)c[u]; } }
     }
-    __syncwarp();
-    for (uint32_t r = lane; r < nchain; r += 32) {  // 1: every position as a B state
+    __syncthreads();
+    for (uint32_t r = tid; r < nchain; r += kGreedyThreads) {  // 1: every position as a B state
       uint32_t cnt;
       const uint32_t nx = greedy_walk(wld, wby, r, cnt, [](uint32_t, uint32_t, uint32_t) {});
       wf[r] = (nx - r) | (cnt << 16);
     }
-    __syncwarp();
-    uint32_t r = 0, k = 0, off = 0;
-    if (lane == 0) {  // 2: hop through the B states that are actually reached
+    __syncthreads();
+    if (tid == 0) {  // 2: hop through the B states that are actually reached
+      uint32_t r = 0, k = 0, off = 0;
       while (r < nchain) {
         const uint32_t e = wf[r];
         bl[k++] = r | (off << 16);
         off += e >> 16;
         r += e & 0xffffu;
       }
+      hop_r = r;
+      hop_k = k;
+      hop_off = off;
     }
-    r = __shfl_sync(0xffffffffu, r, 0);
-    k = __shfl_sync(0xffffffffu, k, 0);
-    off = __shfl_sync(0xffffffffu, off, 0);
-    __syncwarp();
-    for (uint32_t q = lane; q < k; q += 32) {  // 3: emit
+    __syncthreads();
+    const uint32_t r = hop_r, k = hop_k, off = hop_off;
+    for (uint32_t q = tid; q < k; q += kGreedyThreads) {  // 3: emit
       const uint32_t e = bl[q], o = e >> 16;
       uint32_t cnt;
       greedy_walk(wld, wby, e & 0xffffu, cnt, [&](uint32_t t, uint32_t l, uint32_t d) {
@@ -652,13 +656,13 @@ __global__ void __launch_bounds__(32) k_greedy(Batch b, int buf) {
         od[o + t] = (uint16_t)d;
       });
     }
-    __syncwarp();
-    for (uint32_t t = lane; t < off; t += 32) { out_ll[nout + t] = oll[t]; out_d[nout + t] = od[t]; }
+    __syncthreads();
+    for (uint32_t t = tid; t < off; t += kGreedyThreads) { out_ll[nout + t] = oll[t]; out_d[nout + t] = od[t]; }
     nout += off;
     i = wb + r;
-    __syncwarp();
+    __syncthreads();
   }
-  if (lane == 0) b.jobs[seg].greedy_size = nout;
+  if (tid == 0) b.jobs[seg].greedy_size = nout;
 }
 
 }  // namespace zb
