@@ -124,6 +124,12 @@ int ZopfliB200DistInit(int rank, int world, const unsigned char* id128);
 int ZopfliB200DistCompress(const ZopfliOptions* options, ZopfliFormat output_type, const unsigned char* in,
                            size_t insize, int flags, unsigned char** out, size_t* outsize);
 void ZopfliB200DistFinalize(void);
+/* The placement arithmetic of the multi-GPU path as pure functions (csrc/dist_layout.hpp; no GPU needed):
+ * the byte range [a, b) rank `rank` owns and the start `base` of its device copy (shard + dictionary);
+ * and, from len8[world][8] (bits of every rank's blocks for each start phase), the absolute bit offsets
+ * start[0..world] of the ranks in the one stream. */
+void ZopfliB200DistShard(size_t insize, int world, int rank, size_t* a, size_t* b, size_t* base);
+void ZopfliB200DistPlacement(const uint64_t* len8, int world, unsigned phase0, uint64_t* start);
 
 /* CRC-32 of the gzip trailer (gzip_container.c:27-81) and its combination across shards. */
 uint32_t ZopfliB200Crc32(const unsigned char* data, size_t size);

@@ -67,3 +67,87 @@ def test_two_rank_shards_equal_single_stream(ref, tmp_path):
     assert got == ref.compress(whole, 0, numiterations=1)
     import gzip
     assert gzip.decompress(got) == whole
+
+
+WORKER2 = r'''
+import os, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import zopfli_b200 as zb
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+lib = zb.Library(os.path.join(%(root)r, "tests", "_build", "libzopfli_hostmock.so"))
+data = open(os.environ["ZB_IN"], "rb").read() if rank == 0 else None
+insize = int(os.environ["ZB_INSIZE"])
+# --- scatter: rank 0 sends every rank its shard + dictionary (csrc/dist.cpp, dist_layout.hpp) ---
+a, b, base = lib.dist_shard(insize, world, rank)
+if rank == 0:
+    for q in range(1, world):
+        qa, qb, qbase = lib.dist_shard(insize, world, q)
+        if qb > qbase:
+            dist.send(torch.frombuffer(bytearray(data[qbase:qb]), dtype=torch.uint8), q)
+    mine = data[:b]
+    base = 0
+else:
+    t = torch.empty(b - base, dtype=torch.uint8)
+    if b > base:
+        dist.recv(t, 0)
+    mine = t.numpy().tobytes()
+buf = np.zeros(len(mine) + 64, np.uint8)
+buf[:len(mine)] = np.frombuffer(mine, np.uint8)
+span = lib.deflate_span_ptr(buf.ctypes.data, len(mine), a - base, b - base, final=int(b == insize), numiterations=1) if b > a else b""
+
+def place(phase):   # this rank's blocks with their first bit at bit `phase` of byte 0 -> (bytes, bits)
+    if not span:
+        return b"", 0
+    out, bp = lib.splice_spans([span], prefix=b"\0", bp0=phase) if phase else lib.splice_spans([span])
+    end = (len(out) - 1) * 8 + bp if bp else len(out) * 8
+    return out, end - phase
+
+# --- placement: lengths for all 8 phases, all_gather, absolute bit offsets ---
+len8 = torch.tensor([place(p)[1] for p in range(8)], dtype=torch.int64)
+alls = [torch.zeros(8, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(alls, len8)
+start = lib.dist_placement(np.stack([t.numpy() for t in alls]).astype(np.uint64))
+local, nbits = place(start[rank] & 7)
+assert nbits == start[rank + 1] - start[rank]
+# --- gather: bytes go to their final place; the byte two ranks share is ORed ---
+sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(sizes, torch.tensor([len(local)], dtype=torch.int64))
+mx = max(int(s) for s in sizes)
+pad = torch.zeros(mx, dtype=torch.uint8)
+pad[:len(local)] = torch.frombuffer(bytearray(local), dtype=torch.uint8)
+got = [torch.zeros(mx, dtype=torch.uint8) for _ in range(world)] if rank == 0 else None
+dist.gather(pad, got, dst=0)
+if rank == 0:
+    out = bytearray((start[world] + 7) // 8)
+    for q in range(world):
+        nb = int(sizes[q])
+        if nb == 0:
+            continue
+        piece = got[q][:nb].numpy().tobytes()
+        gs = start[q] >> 3
+        out[gs] |= piece[0]
+        out[gs + 1: gs + nb] = piece[1:]
+    open(os.environ["ZB_OUT"], "wb").write(bytes(out))
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_library_protocol_scatter_placement_gather(ref, tmp_path, world):
+    """The protocol of csrc/dist.cpp over gloo instead of NCCL: shard ranges, per-phase stream lengths,
+    absolute bit offsets (dist_layout.hpp through the C ABI) and the in-place gather with the shared
+    boundary byte -- stored blocks included, whose padding makes a rank's length depend on its phase."""
+    from zopfli_b200 import corpus
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "hostmock")])
+    data = corpus.synth_text(1100000, 50) + corpus.random_bytes(500000, 3) + corpus.synth_text(700001, 51)
+    src = tmp_path / "in.bin"
+    src.write_bytes(data)
+    script = tmp_path / "worker2.py"
+    script.write_text(WORKER2 % {"root": ROOT})
+    out = tmp_path / "out.deflate"
+    env = dict(os.environ, ZB_OUT=str(out), ZB_IN=str(src), ZB_INSIZE=str(len(data)), ZOPFLI_B200_THREADS="2")
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
+                           "--master-addr", "127.0.0.1", "--master-port", str(29540 + world), str(script)], env=env, timeout=900)
+    assert out.read_bytes() == ref.compress(data, 2, numiterations=1)

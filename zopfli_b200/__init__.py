@@ -49,7 +49,7 @@ EXPORTS = ["ZopfliInitOptions", "ZopfliCompress", "ZopfliDeflate", "ZopfliDeflat
            "ZopfliB200MatchTable", "ZopfliB200DynamicBlockBits", "ZopfliB200DeviceAutoTypeBits", "ZopfliB200HostBlockSplitLZ77",
            "ZopfliB200HostBatchedSplit", "ZopfliB200HostBlockSize", "ZopfliB200HostEmitBlock", "ZopfliB200HostLengthLimited", "ZopfliB200HostOptimizeRle",
            "ZopfliB200DeflateSpan", "ZopfliB200AppendSpan", "ZopfliB200LastMasterBitOffsets", "ZopfliB200Crc32", "ZopfliB200Crc32Combine", "ZopfliB200Adler32", "ZopfliB200CompressDevice",
-           "ZopfliB200DistUniqueId", "ZopfliB200DistInit", "ZopfliB200DistCompress", "ZopfliB200DistFinalize",
+           "ZopfliB200DistUniqueId", "ZopfliB200DistInit", "ZopfliB200DistCompress", "ZopfliB200DistFinalize", "ZopfliB200DistShard", "ZopfliB200DistPlacement",
            "ZopfliB200GetStats", "ZopfliB200ResetStats", "ZopfliB200SetStream", "ZopfliB200Device",
            "ZopfliB200Version"]
 
@@ -142,6 +142,10 @@ class Library:
         L.ZopfliB200DistInit.argtypes = [C.c_int, C.c_int, vp]
         L.ZopfliB200DistCompress.argtypes = [C.POINTER(ZopfliOptions), C.c_int, vp, sz, C.c_int, C.POINTER(vp), C.POINTER(sz)]
         L.ZopfliB200DistFinalize.restype = None
+        L.ZopfliB200DistShard.argtypes = [sz, C.c_int, C.c_int, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+        L.ZopfliB200DistShard.restype = None
+        L.ZopfliB200DistPlacement.argtypes = [vp, C.c_int, C.c_uint, vp]
+        L.ZopfliB200DistPlacement.restype = None
         L.ZopfliB200GetStats.argtypes = [C.POINTER(Stats)]
         L.ZopfliB200SetStream.argtypes = [vp]
         L.ZopfliB200Version.restype = C.c_char_p
@@ -334,8 +338,9 @@ class Library:
     def crc32_combine(self, crc1, crc2, len2) -> int:
         return int(self.lib.ZopfliB200Crc32Combine(crc1, crc2, len2))
 
-    def splice_spans(self, spans, prefix=b"") -> tuple[bytes, int]:
-        out, n, bp = C.c_void_p(None), C.c_size_t(0), C.c_ubyte(0)
+    def splice_spans(self, spans, prefix=b"", bp0=0) -> tuple[bytes, int]:
+        """appends spans behind `prefix`, whose last byte has bp0 bits in use -> (bytes, final bp)"""
+        out, n, bp = C.c_void_p(None), C.c_size_t(0), C.c_ubyte(bp0)
         if prefix:
             # seed the zopfli-style buffer with the container header
             hdr = np.frombuffer(prefix, np.uint8)
@@ -378,6 +383,17 @@ class Library:
         if self.lib.ZopfliB200DistCompress(C.byref(o), fmt, host_ptr, nbytes, 1 if staged else 0, C.byref(out), C.byref(n)) != 0:
             raise RuntimeError("ZopfliB200DistCompress: ZopfliB200DistInit has not run")
         return OutBuffer(self.libc, out, n.value) if out.value else None
+
+    def dist_shard(self, insize, world, rank):
+        a, b, base = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        self.lib.ZopfliB200DistShard(insize, world, rank, C.byref(a), C.byref(b), C.byref(base))
+        return a.value, b.value, base.value
+
+    def dist_placement(self, len8, phase0=0):
+        t = np.ascontiguousarray(len8, np.uint64)
+        start = np.zeros(t.shape[0] + 1, np.uint64)
+        self.lib.ZopfliB200DistPlacement(t.ctypes.data, t.shape[0], phase0, start.ctypes.data)
+        return [int(v) for v in start]
 
     def dist_finalize(self):
         self.lib.ZopfliB200DistFinalize()

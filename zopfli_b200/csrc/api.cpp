@@ -14,6 +14,7 @@
 #include "../../include/zopfli_b200.h"
 #include "batched_split.hpp"
 #include "dist.hpp"
+#include "dist_layout.hpp"
 #include "driver.hpp"
 #include "engine.hpp"
 #include "host_emit.hpp"
@@ -584,6 +585,14 @@ int ZopfliB200HostLengthLimited(const uint32_t* freq, int n, int maxbits, unsign
   length_limited<kNumLL, 15>(freq, n, maxbits, out.data(), s);
   for (int i = 0; i < n; i++) bitlengths[i] = out[i];
   return 0;
+}
+
+void ZopfliB200DistShard(size_t insize, int world, int rank, size_t* a, size_t* b, size_t* base) {
+  dist_shard(insize, world, rank, a, b, base);
+}
+
+void ZopfliB200DistPlacement(const uint64_t* len8, int world, unsigned phase0, uint64_t* start) {
+  dist_placement(len8, 8, world, phase0, start);
 }
 
 void ZopfliB200HostOptimizeRle(uint32_t* counts, int n) {

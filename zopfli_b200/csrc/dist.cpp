@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "../../include/zopfli_b200.h"
+#include "dist_layout.hpp"
 #include "driver.hpp"
 #include "engine.hpp"
 #include "symbols.hpp"
@@ -107,7 +108,6 @@ struct Rank {
 
 constexpr int kMetaPerRank = 9;  // stream length for each of the 8 start phases + (rank 0) the caller's bit phase
 
-size_t num_master_blocks(size_t insize) { return insize == 0 ? 1 : (insize + kMasterBlock - 1) / kMasterBlock; }
 
 // One rank of a distributed ZopfliDeflate(btype 2).  `in`, `bp`, `out`, `outsize` are used on rank 0 only.
 void rank_deflate(Rank& rk, const ZopfliOptions* opt, int final, const unsigned char* in, size_t insize, unsigned char* bp,
@@ -116,14 +116,8 @@ void rank_deflate(Rank& rk, const ZopfliOptions* opt, int final, const unsigned 
   DCK(cudaSetDevice(rk.dev));
   Engine::Lease eng(rk.dev);
   cudaStream_t st = (cudaStream_t)eng->stream();
-  const size_t nm = num_master_blocks(insize);
-  auto shard = [&](int q, size_t& a, size_t& b, size_t& base) {  // bytes [a, b) of rank q; its device copy starts at `base`
-    const size_t lo = (size_t)q * nm / W, hi = (size_t)(q + 1) * nm / W;
-    a = std::min(insize, lo * (size_t)kMasterBlock);
-    b = std::min(insize, hi * (size_t)kMasterBlock);
-    base = a > (size_t)kWindow ? (a - kWindow) & ~(size_t)15 : 0;
-    if (lo == hi) base = a = b;
-  };
+  const size_t nm = dist_num_master_blocks(insize);
+  auto shard = [&](int q, size_t& a, size_t& b, size_t& base) { dist_shard(insize, W, q, &a, &b, &base); };
   size_t a, b, base;
   shard(r, a, b, base);
   const size_t lo = (size_t)r * nm / W, hi = (size_t)(r + 1) * nm / W;
@@ -184,8 +178,7 @@ void rank_deflate(Rank& rk, const ZopfliOptions* opt, int final, const unsigned 
   DCK(cudaMemcpyAsync(hall, d_all, (size_t)kMetaPerRank * W * 8, cudaMemcpyDeviceToHost, st));
   DCK(cudaStreamSynchronize(st));
   std::vector<uint64_t> start(W + 1);
-  start[0] = hall[8];
-  for (int q = 0; q < W; q++) start[q + 1] = start[q] + hall[(size_t)q * kMetaPerRank + (start[q] & 7)];
+  dist_placement(hall, kMetaPerRank, W, (unsigned)hall[8], start.data());
   const uint64_t total_bits = start[W];
   const size_t total_bytes = (size_t)((total_bits + 7) / 8);
 
@@ -195,10 +188,7 @@ void rank_deflate(Rank& rk, const ZopfliOptions* opt, int final, const unsigned 
   const size_t local_bytes = pieces.empty() ? 0 : (size_t)((local_end + 7) / 8);
   if (pieces.empty()) ep.clear();
   uint8_t* d_out = (uint8_t*)eng->emit_device(ep, pieces.empty() ? 0 : local_end, r == 0 ? total_bytes + 64 : 0);
-  auto bytes_of = [&](int q) -> size_t {  // bytes rank q's stream touches
-    if (start[q + 1] == start[q]) return 0;
-    return (size_t)(((start[q] & 7) + (start[q + 1] - start[q]) + 7) / 8);
-  };
+  auto bytes_of = [&](int q) -> size_t { return dist_bytes_touched(start.data(), q); };
   if (r == 0) {
     DCK(cudaMemsetAsync(d_first, 0, (size_t)W, st));
     if (total_bytes > local_bytes) DCK(cudaMemsetAsync(d_out + local_bytes, 0, total_bytes - local_bytes, st));
