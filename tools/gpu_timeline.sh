@@ -21,6 +21,6 @@ print({k: round(v, 1) for k, v in st.items() if k.startswith("ms_")}, file=sys.s
 PY
 run() { name=$1; shift; env ZOPFLI_B200_DEBUG=1 "$@" python /tmp/tl.py 2> gpurun_out/timeline_$name.txt; grep "call\|ms_" gpurun_out/timeline_$name.txt | sed "s/^/$name: /"; }
 run base ZB_X=0
-[ -f zopfli_b200/_var/lib_sig.so ] && run sig ZB_LIB=zopfli_b200/_var/lib_sig.so
+for v in $TL_VARIANTS; do run "$(echo $v | tr -c 'A-Za-z0-9\n' '_')" $v; done
 [ -n "$TL_DEFERRED" ] && run deferred ZOPFLI_B200_SYNC_TOC=0
 exit 0

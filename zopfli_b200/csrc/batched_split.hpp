@@ -14,6 +14,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <functional>
@@ -67,8 +68,13 @@ struct StoreState {
 }  // namespace bsplit
 
 // budget: probes per round up to which deeper speculation is worth its kernel time
+inline size_t default_split_budget() {
+  static size_t v = [] { const char* e = getenv("ZOPFLI_B200_SPLIT_BUDGET"); return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)6000; }();
+  return v;
+}
+
 inline std::vector<std::vector<size_t>> batched_block_split(const std::vector<size_t>& sizes, size_t maxblocks,
-                                                             const BatchEvalFn& eval, size_t budget = 6000) {
+                                                             const BatchEvalFn& eval, size_t budget = default_split_budget()) {
   using namespace bsplit;
   const size_t ns = sizes.size();
   std::vector<StoreState> S(ns);
