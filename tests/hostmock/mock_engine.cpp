@@ -115,7 +115,7 @@ void Engine::plan_blocks(const std::vector<PlanReq>& reqs, std::vector<PlanCost>
   for (size_t i = 0; i < reqs.size(); i++) {
     std::unique_ptr<BlockPlan> p(new BlockPlan);
     host_block_plan(p_->sym_ll[reqs[i].buf].data() + reqs[i].off, p_->sym_d[reqs[i].buf].data() + reqs[i].off, reqs[i].n, *p);
-    costs[i] = PlanCost{p->unc_bits, p->fixed_bits, p->dyn_bits};
+    costs[i] = PlanCost{p->unc_bits, p->fixed_bits, p->dyn_bits, p->tree_bits};
     handles[i] = (uint64_t)(uintptr_t)p.get();
     std::lock_guard<std::mutex> g(p_->mu);
     p_->plans.push_back(std::move(p));

@@ -7,6 +7,7 @@ bug, not a kernel bug.  The shipped libzopfli.so.1 contains no such path.
 """
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -349,3 +350,28 @@ def test_checksums_threaded_and_combined(mock):
         assert mock.adler32(d) == zlib.adler32(d), n
         a = np.frombuffer(d, np.uint8)
         assert mock.crc32(a.ctypes.data if n else 0, n) == zlib.crc32(d), n
+
+
+def test_verbose_reports_match_the_reference(tmp_path):
+    """options.verbose: the split-point, tree-size and block-size reports (blocksplitter.c:148-180,
+    deflate.c:718-744) come out byte for byte as the reference prints them; only the per-iteration lines
+    of squeeze.c:493-495 are not mirrored (they would need every iteration's cost back from the device)."""
+    script = tmp_path / "verb.py"
+    script.write_text('''
+import sys, ctypes as C, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import zopfli_b200 as zb, zref
+from zopfli_b200 import corpus
+d = corpus.synth_text(300000, 3) + corpus.random_bytes(40000) + corpus.synth_text(100000, 4)
+if sys.argv[1] == "ref":
+    r = zref.Ref(); o = r.options(numiterations=2); o.verbose = 1
+    a = np.frombuffer(d, np.uint8); out = C.c_void_p(None); n = C.c_size_t(0)
+    r.lib.ZopfliCompress(C.byref(o), 2, a.ctypes.data, len(d), C.byref(out), C.byref(n))
+else:
+    zb.Library(%r).compress(d, 2, numiterations=2, verbose=1)
+''' % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "_build", "libzopfli_hostmock.so")))
+    outs = {}
+    for which in ("ref", "mock"):
+        r = subprocess.run([sys.executable, str(script), which], capture_output=True, text=True, check=True)
+        outs[which] = [l for l in r.stderr.splitlines() if not l.startswith("Iteration")]
+    assert outs["mock"] == outs["ref"] and len(outs["ref"]) > 10

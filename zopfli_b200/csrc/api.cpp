@@ -198,7 +198,7 @@ void deflate_impl(const ZopfliOptions* options, int btype, int final, const unsi
   deflate_units(*eng, options, btype, final != 0, in, master_units(insize, 0, num_master_blocks(insize)), 0, pieces);
   const double t2 = now_ms();
   std::vector<uint64_t> layout;
-  assemble(*eng, pieces, 0, bp, out, outsize, &layout);
+  assemble(*eng, pieces, 0, bp, out, outsize, &layout, options->verbose != 0);
   { std::lock_guard<std::mutex> g(g_api_mu); g_last_layout.swap(layout); }
   if (api_debug())
     fprintf(stderr, "[zb] api: set_input %.1f ms, deflate_units %.1f ms, emit %.1f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
@@ -318,7 +318,7 @@ void ZopfliDeflatePart(const ZopfliOptions* options, int btype, int final, const
   Engine::Lease eng;
   eng->set_input_host(in + base, inend - base);
   deflate_units(*eng, options, btype, final != 0, in, {{instart, inend}}, base, pieces);
-  assemble(*eng, pieces, base, bp, out, outsize);
+  assemble(*eng, pieces, base, bp, out, outsize, nullptr, options->verbose != 0);
 }
 
 int ZopfliB200DistCompress(const ZopfliOptions* options, ZopfliFormat output_type, const unsigned char* in, size_t insize,

@@ -117,6 +117,17 @@ struct Master {
   std::vector<Piece> pieces;
 };
 
+// PrintBlockSplitPoints (blocksplitter.c:148-180): byte offsets of the split points from the start of the
+// store that was split (the master block), decimal then hex
+void print_split_points(const std::vector<size_t>& cuts, size_t origin) {
+  std::lock_guard<std::mutex> g(g_time_mu);  // chunk pipelines print concurrently: keep lines whole
+  fprintf(stderr, "block split points: ");
+  for (size_t c = 1; c + 1 < cuts.size(); c++) fprintf(stderr, "%d ", (int)(cuts[c] - origin));
+  fprintf(stderr, "(hex:");
+  for (size_t c = 1; c + 1 < cuts.size(); c++) fprintf(stderr, " %x", (int)(cuts[c] - origin));
+  fprintf(stderr, ")\n");
+}
+
 // ZopfliCalculateBlockSizeAutoType (deflate.c:610-621) from the three sizes; `store_size` is the symbol
 // count of the store the range belongs to (the reference tests lz77->size)
 uint64_t auto_type(const Engine::PlanCost& c, size_t store_size) {
@@ -165,6 +176,8 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
       p.off = M[m].ms - in_base;
       p.n = sizes[m];
       p.nbits = pc[m].fixed;
+      p.instart = M[m].ms;
+      p.inend = M[m].me;
       p.final = final_last && m + 1 == nm;
       p.unit = (uint32_t)m;
       pieces.push_back(p);
@@ -209,11 +222,7 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
       mb.cuts.push_back(mb.ms);
       for (size_t k = 0; k < lps[q].size(); k++) mb.cuts.push_back(mb.ms + bytepos[w++]);
       mb.cuts.push_back(mb.me);
-      if (opt->verbose) {
-        fprintf(stderr, "block split points: ");
-        for (size_t c = 1; c + 1 < mb.cuts.size(); c++) fprintf(stderr, "%d ", (int)mb.cuts[c]);
-        fprintf(stderr, "\n");
-      }
+      if (opt->verbose) print_split_points(mb.cuts, mb.ms);
     }
     double t2 = now_ms();
     debug_mark(cid, "B split done");
@@ -327,7 +336,7 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
           for (size_t i = 0; i <= second[q].size(); i++) totalcost2 += auto_type(c2[rq2_base[q] + i], (size_t)total[q]);
           use2[q] = totalcost2 < totalcost[q];
           want_base[k] = want.size();
-          if (use2[q])
+          if (use2[q] || opt->verbose)
             for (size_t p : second[q]) want.push_back({(uint32_t)k, (uint32_t)p});
         }
         // byte positions of the adopted second-pass split points (lz77->pos, deflate.c:769)
@@ -335,11 +344,13 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
         eng.split_positions(want, bytepos, lane);
         for (size_t k = 0; k < who.size(); k++) {
           const size_t q = who[k];
-          if (!use2[q]) continue;
+          if (!use2[q] && !opt->verbose) continue;
           Master& mb = M[ms[q]];
-          mb.cuts.assign(1, mb.ms);
-          for (size_t i = 0; i < second[q].size(); i++) mb.cuts.push_back(mb.ms + bytepos[want_base[k] + i]);
-          mb.cuts.push_back(mb.me);
+          std::vector<size_t> cuts2(1, mb.ms);
+          for (size_t i = 0; i < second[q].size(); i++) cuts2.push_back(mb.ms + bytepos[want_base[k] + i]);
+          cuts2.push_back(mb.me);
+          if (opt->verbose) print_split_points(cuts2, mb.ms);  // ZopfliBlockSplitLZ77 reports its points whether or not they win
+          if (use2[q]) mb.cuts.swap(cuts2);
         }
       }
       // final blocks and the fixed-tree re-parses they ask for (AddLZ77BlockAutoType deflate.c:747-800)
@@ -387,6 +398,8 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
           Piece p;
           p.final = final_last && ms[q] + 1 == nm && i + 1 == finals[q].size();
           p.unit = (uint32_t)ms[q];
+          p.instart = fb.a;
+          p.inend = fb.b;
           if (fb.lstart == fb.lend) {  // deflate.c:763-768: the smallest empty block is a fixed one
             p.type = 1;
             p.n = 0;
@@ -407,6 +420,7 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
           } else {
             p.type = 2;
             p.nbits = fb.c.dyn;
+            p.tree_bits = (uint32_t)fb.c.tree;
             p.buf = Engine::kFin;
             p.off = moff[q] + fb.lstart;
             p.n = (uint32_t)(fb.lend - fb.lstart);
@@ -518,10 +532,20 @@ uint64_t layout_pieces(const std::vector<Piece>& pieces, size_t in_base, uint64_
 }
 
 void assemble(Engine& eng, const std::vector<Piece>& pieces, size_t in_base, unsigned char* bp, unsigned char** out,
-              size_t* outsize, std::vector<uint64_t>* unit_bits) {
+              size_t* outsize, std::vector<uint64_t>* unit_bits, bool verbose) {
   const unsigned phase = (*outsize > 0) ? (*bp & 7u) : 0u;  // bits in use in the last byte (deflate.h:50-53)
   std::vector<Engine::EmitPiece> ep;
   const uint64_t total = layout_pieces(pieces, in_base, phase, ep, unit_bits);
+  if (verbose) {  // AddLZ77Block's reports (deflate.c:718-744): growth of *outsize (= bytes touched so far) per part
+    for (size_t i = 0; i < pieces.size(); i++) {
+      const Piece& p = pieces[i];
+      if (p.type == 0 || p.n == 0) continue;  // stored blocks return before the report (deflate.c:696-702); empty blocks never get there
+      const uint64_t h = ep[i].bit_start + 3, t = h + p.tree_bits, e = ep[i].bit_start + ep[i].nbits;
+      if (p.type == 2) fprintf(stderr, "treesize: %d\n", (int)((t + 7) / 8 - (h + 7) / 8));
+      const size_t grown = (size_t)((e + 7) / 8 - (t + 7) / 8);
+      fprintf(stderr, "compressed block size: %d (%dk) (unc: %d)\n", (int)grown, (int)(grown / 1024), (int)(p.inend - p.instart));
+    }
+  }
   const size_t nbytes = (size_t)((total + 7) / 8);
   if (nbytes == 0) return;
   unsigned char keep = 0;

@@ -23,6 +23,7 @@ struct Piece {
   uint64_t off = 0;          // first symbol in `buf`
   uint64_t plan = 0;         // Engine::plan_blocks handle (dynamic blocks)
   uint64_t nbits = 0;        // exact size (compressed blocks)
+  uint32_t tree_bits = 0;    // dynamic blocks: size of the tree header inside nbits (verbose report only)
   size_t instart = 0, inend = 0;  // stored blocks: absolute input positions
 };
 
@@ -52,7 +53,7 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
 // the bytes to *out.  unit_bits (optional) receives the bit offset of every unit's first piece relative
 // to the first bit written, plus the end offset as last entry.
 void assemble(Engine& eng, const std::vector<Piece>& pieces, size_t in_base, unsigned char* bp, unsigned char** out,
-              size_t* outsize, std::vector<uint64_t>* unit_bits = nullptr);
+              size_t* outsize, std::vector<uint64_t>* unit_bits = nullptr, bool verbose = false);
 
 // bit position of every piece when the first one starts at bit0; returns the end position
 uint64_t layout_pieces(const std::vector<Piece>& pieces, size_t in_base, uint64_t bit0, std::vector<Engine::EmitPiece>& ep,

@@ -351,7 +351,6 @@ struct Engine::Impl {
     DevBuf* shared[] = {&in_buf, &same_buf, &tile_first, &next_tile, &sym_ll[0], &sym_ll[1], &sym_ll[2], &sym_d[0],
                         &sym_d[1], &sym_d[2], &outbuf, &emit_desc, &err_flag};
     for (DevBuf* d : shared) d->st = lane[0].stream;
-    CK(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * 4));
     {
       cudaFuncAttributes fa;
       CK(cudaFuncGetAttributes(&fa, k_iterate));
@@ -516,7 +515,7 @@ struct Engine::Impl {
       CK(cudaGetLastError());
       l.toc(l.acc.ms_scan);
       l.tic();
-      k_scatter<<<(unsigned)(2 * ns), 32, 32768 * 4, l.stream>>>(b);
+      k_scatter<<<(unsigned)(2 * ns * kScatterParts), 32, 0, l.stream>>>(b);
       CK(cudaGetLastError());
       l.toc(l.acc.ms_scatter);
       l.tic();
@@ -1052,7 +1051,7 @@ void Engine::plan_blocks(const std::vector<PlanReq>& reqs, std::vector<PlanCost>
   std::lock_guard<std::mutex> g(l.mu);
   CK(cudaSetDevice(m.dev));
   const size_t n = reqs.size();
-  costs.assign(n, PlanCost{0, 0, 0});
+  costs.assign(n, PlanCost{0, 0, 0, 0});
   handles.assign(n, 0);
   if (n == 0) return;
   BlockPlan* plans = m.plan_alloc(n);
@@ -1077,7 +1076,7 @@ void Engine::plan_blocks(const std::vector<PlanReq>& reqs, std::vector<PlanCost>
   l.sync();
   l.acc.launches++;
   l.acc.d2h_bytes += n * sizeof(BlockPlan);
-  for (size_t i = 0; i < n; i++) costs[i] = PlanCost{hp[i].unc_bits, hp[i].fixed_bits, hp[i].dyn_bits};
+  for (size_t i = 0; i < n; i++) costs[i] = PlanCost{hp[i].unc_bits, hp[i].fixed_bits, hp[i].dyn_bits, hp[i].tree_bits};
 }
 
 void* Engine::stream() { return (void*)p_->lane[0].stream; }

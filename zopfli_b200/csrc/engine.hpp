@@ -101,7 +101,7 @@ class Engine {
   // stored / fixed / dynamic sizes of symbol ranges + the emission plan of each (kept on the device);
   // handles[i] identifies range i's plan in emit()
   struct PlanReq { uint64_t off; uint32_t n; uint32_t buf; };
-  struct PlanCost { uint64_t unc, fixed, dyn; };
+  struct PlanCost { uint64_t unc, fixed, dyn, tree; };  // tree: bits of the dynamic block's tree header (part of dyn)
   void plan_blocks(const std::vector<PlanReq>& reqs, std::vector<PlanCost>& costs, std::vector<uint64_t>& handles,
                    int lane = 1);
   // Writes every piece at its final bit position and copies bytes [0, ceil(total_bits / 8)) of the

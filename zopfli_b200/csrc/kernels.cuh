@@ -295,14 +295,22 @@ __global__ void k_bucket_scan(Batch b) {
   if (threadIdx.x == 1023) c[32768] = run;
 }
 
-// Stable scatter: one warp per (segment, chain) walks the keys in position order; the running
-// bucket cursors live in 128 KiB of shared memory.  idx[dest] = position, rank[position] = dest.
+// Stable scatter.  kScatterParts warps per (segment, chain): warp r owns the buckets whose top bits are r
+// (a contiguous 1/kScatterParts of the 32768), walks ALL keys of the segment in position order and places
+// the ones that fall into its range -- every bucket is filled by exactly one warp in position order, so
+// the sort stays stable, and the serial walk that was one warp's 8 ms per master block is shared by
+// kScatterParts warps.  The running bucket cursors of a warp's range live in shared memory.
+// idx[dest] = position, rank[position] = dest.
+constexpr int kScatterParts = 8;
+constexpr int kScatterBuckets = 32768 / kScatterParts;
 __global__ void __launch_bounds__(32) k_scatter(Batch b) {
-  extern __shared__ uint32_t cursor[];  // 32768
-  uint32_t seg = blockIdx.x >> 1;
-  bool second = blockIdx.x & 1;
+  __shared__ uint32_t cursor[kScatterBuckets];
+  const uint32_t part = blockIdx.x % kScatterParts;
+  const uint32_t sc = blockIdx.x / kScatterParts;
+  uint32_t seg = sc >> 1;
+  bool second = sc & 1;
   const SegDesc sd = b.segs[seg];
-  const uint32_t* bs = (second ? b.bkt2 : b.bkt1) + (uint64_t)seg * 32769;
+  const uint32_t* bs = (second ? b.bkt2 : b.bkt1) + (uint64_t)seg * 32769 + part * kScatterBuckets;
   const uint16_t* key = (second ? b.hv2 : b.hv) + sd.key_off;
   uint32_t* idx = (second ? b.idx2 : b.idx1) + sd.key_off;
   uint32_t* rank = (second ? b.rank2 : b.rank1) + sd.key_off;
@@ -311,7 +319,7 @@ __global__ void __launch_bounds__(32) k_scatter(Batch b) {
   const uint8_t* kbytes = b.in + sd.winstart;  // byte of key index 0
 #endif
   const uint32_t lane = threadIdx.x;
-  for (uint32_t i = lane; i < 32768; i += 32) cursor[i] = bs[i];
+  for (uint32_t i = lane; i < (uint32_t)kScatterBuckets; i += 32) cursor[i] = bs[i];
   __syncwarp();
   // keys of 8 rounds are fetched up front so that the global-load latency is paid once per 256
   // positions instead of once per round
@@ -320,13 +328,15 @@ __global__ void __launch_bounds__(32) k_scatter(Batch b) {
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       const uint32_t i = base0 + u * 32 + lane;
-      kreg[u] = i < sd.nkeys ? key[i] : 0xffffffffu;  // inactive lanes get a key no active lane has
+      kreg[u] = i < sd.nkeys ? key[i] : 0xffffffffu;
     }
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       const uint32_t i = base0 + u * 32 + lane;
-      const bool act = i < sd.nkeys;
-      const uint32_t k = kreg[u];
+      const uint32_t kk = kreg[u];
+      const bool act = kk != 0xffffffffu && (kk / (uint32_t)kScatterBuckets) == part;
+      if (!__any_sync(0xffffffffu, act)) continue;
+      const uint32_t k = act ? kk - part * kScatterBuckets : 0x80000000u + lane;  // inactive lanes get a key no other lane has
       const uint32_t peers = __match_any_sync(0xffffffffu, k);
       const uint32_t before = __popc(peers & ((1u << lane) - 1));
       const uint32_t cur = act ? cursor[k] : 0;
