@@ -249,7 +249,16 @@ def run_product(args, rank, world):
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(lib.dist_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
-        lib.dist_init(rank, world, idt.cpu().numpy().tobytes())
+        # NCCL prints its version banner with printf when a communicator is created (NCCL_DEBUG=WARN):
+        # stdout carries exactly one JSON line, so fd 1 points at stderr while the library initialises
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            lib.dist_init(rank, world, idt.cpu().numpy().tobytes())
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     else:
         data = seg
     # pageable host copy (what a drop-in C caller passes); +64 so the device-resident leg can share it

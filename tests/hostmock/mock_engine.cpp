@@ -62,6 +62,7 @@ void Engine::set_input_host(const uint8_t* in, size_t n) {
   p_->ensure_sym();
 }
 uint64_t Engine::input_size() const { return p_->insize; }
+uint64_t Engine::device_memory_total() const { return 16ull << 30; }
 void Engine::set_input_device(const uint8_t*, size_t) {}
 void Engine::parse(const std::vector<ParseRange>& r, ParseResult& out, int) {
   out.off.assign(r.size(), 0);

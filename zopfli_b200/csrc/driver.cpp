@@ -468,15 +468,19 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
     if (nchunks < 1) nchunks = 1;
     std::vector<std::vector<size_t>> chunks(nchunks);
     for (size_t m = 0; m < nm; m++) chunks[m * nchunks / nm].push_back(m);
-    // A pipeline takes its master blocks in batches: device memory is ~100 B per position of a
-    // batch per lane pair, so 32 master blocks per batch keep a 1 GiB input (C3) at ~13 GB of arenas
-    // where one batch per pipeline would need ~110 GB.  The 100 MB bench runs one batch per pipeline.
-    size_t batch = 32;
+    // A pipeline takes its master blocks in batches because the lane arenas cost ~140 MB per master
+    // block in flight (~100 B per parse position + ~22 B per key position, two lanes).  The batch is as
+    // large as a quarter of the device memory allows (180 GB: ~80 master blocks per pipeline), so the
+    // 100 MB bench and a 134 MB shard of the 1 GiB config run as ONE wave per pipeline -- every extra
+    // wave costs a whole A + B + longest-chain latency -- and the batches of a longer input are balanced.
+    size_t batch = std::max<size_t>(8, (size_t)(eng.device_memory_total() / 4 / ((uint64_t)nchunks * 140000000ull)));
     if (const char* e = getenv("ZOPFLI_B200_BATCH")) batch = std::max<size_t>(1, (size_t)atoi(e));
     auto run_pipeline = [&](size_t c) {
       const std::vector<size_t>& all = chunks[c];
-      for (size_t a = 0; a < all.size(); a += batch) {
-        std::vector<size_t> part(all.begin() + a, all.begin() + std::min(all.size(), a + batch));
+      const size_t nbatches = (all.size() + batch - 1) / batch;
+      const size_t per = nbatches ? (all.size() + nbatches - 1) / nbatches : 0;
+      for (size_t a = 0; a < all.size(); a += per) {
+        std::vector<size_t> part(all.begin() + a, all.begin() + std::min(all.size(), a + per));
         run_chunk(part, (int)(2 * c), (int)(2 * c + 1));
       }
     };

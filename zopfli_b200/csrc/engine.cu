@@ -704,6 +704,13 @@ void Engine::parse_keep(const std::vector<ParseRange>& ranges, int dest, std::ve
 
 uint64_t Engine::input_size() const { return p_->insize; }
 
+uint64_t Engine::device_memory_total() const {
+  size_t fr = 0, tot = 0;
+  CK(cudaSetDevice(p_->dev));
+  CK(cudaMemGetInfo(&fr, &tot));
+  return tot;
+}
+
 // dest < 0: the symbols come back to the host (test seams); otherwise they stay in symbol buffer `dest`
 void Engine::parse_common(const std::vector<ParseRange>& ranges, ParseResult& out, int dest, int lane_id) {
   Impl& m = *p_;

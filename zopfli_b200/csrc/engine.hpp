@@ -125,6 +125,7 @@ class Engine {
   void upload(void* dev_dst, const uint8_t* host_src, size_t nbytes);
   void* stream();   // cudaStream_t of lane 0, the stream emit / download / set_input run on
   uint64_t input_size() const;
+  uint64_t device_memory_total() const;   // bytes of device memory (sizes the master-block batches of a pipeline)
 
   void set_stream(void* cuda_stream);  // optional: run on the caller's stream
   EngineStats stats();
