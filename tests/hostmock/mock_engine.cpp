@@ -84,7 +84,8 @@ void Engine::parse(const std::vector<ParseRange>& r, ParseResult& out, int) {
   }
 }
 void Engine::parse_keep(const std::vector<ParseRange>& r, int dest, std::vector<uint32_t>& sizes,
-                        std::vector<uint64_t>& costs, int lane) {
+                        std::vector<uint64_t>& costs, int lane, std::vector<uint64_t>* iter_costs) {
+  if (iter_costs) iter_costs->clear();  // the oracle does not expose per-iteration costs
   ParseResult res;
   parse(r, res, lane);
   sizes = res.size;

@@ -208,3 +208,36 @@ def test_reentrant_concurrent_calls(ref, lib):
         t.join()
     assert not errs, errs
     assert got == want
+
+
+def test_verbose_output_matches_reference(tmp_path):
+    """options.verbose / verbose_more on a one-block input (so the order of the lines is fixed): the
+    split-point, per-iteration (squeeze.c:493-495), tree-size and block-size lines on stderr are the
+    reference's, byte for byte."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "verb.py"
+    script.write_text('''
+import sys, ctypes as C, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import zopfli_b200 as zb, zref
+from zopfli_b200 import corpus
+d = corpus.synth_text(120000, 3)
+more = int(sys.argv[2])
+def opts(o):
+    o.verbose = 1; o.verbose_more = more; o.numiterations = 9; o.blocksplitting = 0
+    return o
+if sys.argv[1] == "ref":
+    r = zref.Ref(); lib = r.lib; o = opts(r.options())
+else:
+    z = zb.library(); lib = z.lib; o = opts(z.options())
+a = np.zeros(len(d) + 64, np.uint8); a[:len(d)] = np.frombuffer(d, np.uint8)
+out = C.c_void_p(None); n = C.c_size_t(0)
+lib.ZopfliCompress(C.byref(o), 2, C.c_void_p(a.ctypes.data), C.c_size_t(len(d)), C.byref(out), C.byref(n))
+''' % (root, os.path.join(root, "tests")))
+    for more in (0, 1):
+        outs = {}
+        for which in ("ref", "b200"):
+            r = subprocess.run([sys.executable, str(script), which, str(more)], capture_output=True, text=True, check=True)
+            outs[which] = r.stderr.splitlines()
+        assert outs["b200"] == outs["ref"] and any(l.startswith("Iteration") for l in outs["ref"]), more

@@ -254,13 +254,27 @@ void deflate_units(Engine& eng, const ZopfliOptions* opt, int btype, bool final_
       idx[lane].push_back(k);
     }
     for (size_t m : cm) M[m].bsize.assign(M[m].cuts.size() - 1, 0);
+    const bool want_iters = opt->verbose || opt->verbose_more;
     auto parse_lane = [&](int which, int lane) {
       std::vector<uint32_t> sizes;
-      std::vector<uint64_t> costs;
-      eng.parse_keep(prs[which], Engine::kPack, sizes, costs, lane);
+      std::vector<uint64_t> costs, itc;
+      eng.parse_keep(prs[which], Engine::kPack, sizes, costs, lane, want_iters ? &itc : nullptr);
       for (size_t q = 0; q < idx[which].size(); q++) {
         const size_t k = idx[which][q];
         M[owner[k].first].bsize[owner[k].second] = sizes[q];
+      }
+      if (want_iters && !itc.empty()) {  // squeeze.c:493-495, block after block
+        std::lock_guard<std::mutex> g(g_time_mu);
+        const size_t stride = itc.size() / idx[which].size();
+        for (size_t q = 0; q < idx[which].size(); q++) {
+          uint64_t best = ~(uint64_t)0;
+          for (size_t i = 0; i < stride && i < (size_t)opt->numiterations; i++) {
+            const uint64_t c = itc[q * stride + i];
+            if (c == ~(uint64_t)0) break;
+            if (opt->verbose_more || c < best) fprintf(stderr, "Iteration %d: %d bit\n", (int)i, (int)c);
+            if (c < best) best = c;
+          }
+        }
       }
     };
 

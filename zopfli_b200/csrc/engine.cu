@@ -220,7 +220,7 @@ struct Lane {  // an independent stream + arena set; chunk pipelines use a pair 
   DevBuf sig1, sig2, h2b;
 #endif
   DevBuf segs, keywork, poswork, order, hv, hv2, idx1, idx2, rank1, rank2, bkt1, bkt2, ld, mlen, runs, dsx,
-      ovf, la, path, st[4], jobs, out_ll, out_d, counters, misc;
+      ovf, la, path, st[4], jobs, out_ll, out_d, counters, misc, iterc;
   // split service
   DevBuf sp_ll, sp_d, sp_llsym, sp_dsym, sp_pos, sp_snaps, sp_stores, sp_work, sp_evals, sp_out;
   PinBuf pin_req, pin_out;
@@ -239,7 +239,7 @@ struct Lane {  // an independent stream + arena set; chunk pipelines use a pair 
     for (int k = 0; k < kTimerPairs; k++) { CK(cudaEventCreate(&ev[k][0])); CK(cudaEventCreate(&ev[k][1])); }
     DevBuf* all[] = {&segs, &keywork, &poswork, &order, &hv, &hv2, &idx1, &idx2, &rank1, &rank2, &bkt1, &bkt2, &ld,
                      &mlen, &runs, &dsx, &ovf, &la, &path, &st[0], &st[1], &st[2], &st[3], &jobs, &out_ll,
-                     &out_d, &counters, &misc, &sp_ll, &sp_d, &sp_llsym, &sp_dsym, &sp_pos, &sp_snaps, &sp_stores,
+                     &out_d, &counters, &misc, &iterc, &sp_ll, &sp_d, &sp_llsym, &sp_dsym, &sp_pos, &sp_snaps, &sp_stores,
                      &sp_work, &sp_evals, &sp_out};
     for (DevBuf* d : all) d->st = stream;
 #ifdef ZB_VAR_SIG
@@ -594,7 +594,7 @@ void Engine::set_stream(void* s) {
     l.stream = (cudaStream_t)s;
     DevBuf* all[] = {&l.segs, &l.keywork, &l.poswork, &l.order, &l.hv, &l.hv2, &l.idx1, &l.idx2, &l.rank1, &l.rank2,
                      &l.bkt1, &l.bkt2, &l.ld, &l.mlen, &l.runs, &l.dsx, &l.ovf, &l.la, &l.path, &l.st[0], &l.st[1],
-                     &l.st[2], &l.st[3], &l.jobs, &l.out_ll, &l.out_d, &l.counters, &l.misc, &l.sp_ll,
+                     &l.st[2], &l.st[3], &l.jobs, &l.out_ll, &l.out_d, &l.counters, &l.misc, &l.iterc, &l.sp_ll,
                      &l.sp_d, &l.sp_llsym, &l.sp_dsym, &l.sp_pos, &l.sp_snaps, &l.sp_stores, &l.sp_work, &l.sp_evals,
                      &l.sp_out, &p_->in_buf, &p_->same_buf, &p_->tile_first, &p_->next_tile, &p_->sym_ll[0], &p_->sym_ll[1],
                      &p_->sym_ll[2], &p_->sym_d[0], &p_->sym_d[1], &p_->sym_d[2], &p_->outbuf, &p_->emit_desc, &p_->err_flag};
@@ -693,11 +693,11 @@ void Engine::parse(const std::vector<ParseRange>& ranges, ParseResult& out, int 
 }
 
 void Engine::parse_keep(const std::vector<ParseRange>& ranges, int dest, std::vector<uint32_t>& sizes,
-                        std::vector<uint64_t>& costs, int lane_id) {
+                        std::vector<uint64_t>& costs, int lane_id, std::vector<uint64_t>* iter_costs) {
   for (const ParseRange& r : ranges)
     if (r.mode == 0) { fprintf(stderr, "zopfli-b200: parse_keep takes optimal-parse ranges only\n"); abort(); }
   ParseResult res;
-  parse_common(ranges, res, dest, lane_id);
+  parse_common(ranges, res, dest, lane_id, iter_costs);
   sizes.swap(res.size);
   costs.swap(res.cost);
 }
@@ -712,7 +712,8 @@ uint64_t Engine::device_memory_total() const {
 }
 
 // dest < 0: the symbols come back to the host (test seams); otherwise they stay in symbol buffer `dest`
-void Engine::parse_common(const std::vector<ParseRange>& ranges, ParseResult& out, int dest, int lane_id) {
+void Engine::parse_common(const std::vector<ParseRange>& ranges, ParseResult& out, int dest, int lane_id,
+                          std::vector<uint64_t>* iter_costs) {
   Impl& m = *p_;
   Lane& l = m.lane[(unsigned)lane_id % Engine::kLanes];
   std::lock_guard<std::mutex> g(l.mu);
@@ -737,8 +738,17 @@ void Engine::parse_common(const std::vector<ParseRange>& ranges, ParseResult& ou
       if (need > m.log_need) m.log_need = (uint32_t)std::min<uint64_t>(need, 0xfffffff0ull);
     }
   }
+  uint32_t it_stride = 0;
+  if (iter_costs)
+    for (const ParseRange& r : ranges) it_stride = std::max<uint32_t>(it_stride, r.mode == 1 ? (uint32_t)std::max(r.numiterations, 0) : 0u);
   for (int attempt = 0;; attempt++) {
     Batch b = m.prepare(L, l);
+    if (it_stride) {
+      l.iterc.ensure((size_t)ns * it_stride * 8 + 64);
+      CK(cudaMemsetAsync(l.iterc.p, 0xff, (size_t)ns * it_stride * 8, l.stream));
+      b.iter_cost = l.iterc.as<uint64_t>();
+      b.iter_stride = it_stride;
+    }
     l.tic();
     k_greedy<<<(unsigned)ns, kGreedyThreads, 0, l.stream>>>(b, 0);
     CK(cudaGetLastError());
@@ -773,6 +783,10 @@ void Engine::parse_common(const std::vector<ParseRange>& ranges, ParseResult& ou
     l.tic();
     CK(cudaMemcpyAsync(js.data(), l.jobs.p, ns * sizeof(JobState), cudaMemcpyDeviceToHost, l.stream));
     CK(cudaMemcpyAsync(counters, l.counters.p, sizeof(counters), cudaMemcpyDeviceToHost, l.stream));
+    if (it_stride) {
+      iter_costs->assign((size_t)ns * it_stride, ~0ull);
+      CK(cudaMemcpyAsync(iter_costs->data(), l.iterc.p, (size_t)ns * it_stride * 8, cudaMemcpyDeviceToHost, l.stream));
+    }
     l.toc(l.acc.ms_d2h);
     l.sync();
     if (L.any_parse && counters[0] > l.ovf_cap) {  // run-list overflow arena too small: grow, redo

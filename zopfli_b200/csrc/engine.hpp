@@ -91,8 +91,10 @@ class Engine {
   //   kFix   fixed-tree re-parse of a final block at [block start ...)
   enum StoreBuf { kPack = 0, kFin = 1, kFix = 2 };
   // parse() whose results stay on the device in buffer `dest`; sizes / costs as in ParseResult
+  // iter_costs (optional, for the verbose report of squeeze.c:493-495): cost of iteration i of range r at
+  // [r * numiterations_max + i], ~0 where an iteration did not run
   void parse_keep(const std::vector<ParseRange>& ranges, int dest, std::vector<uint32_t>& sizes,
-                  std::vector<uint64_t>& costs, int lane = 0);
+                  std::vector<uint64_t>& costs, int lane = 0, std::vector<uint64_t>* iter_costs = nullptr);
   // kPack -> kFin copies (ZopfliAppendLZ77Store), then the split service of `lane` over the kFin stores
   // [store_off[i], store_off[i] + store_size[i]) (skipped when store_off is empty)
   struct SymCopy { uint64_t src_off, dst_off; uint32_t n, pad; };
@@ -133,7 +135,8 @@ class Engine {
   int device() const;
 
  private:
-  void parse_common(const std::vector<ParseRange>& ranges, ParseResult& out, int dest, int lane);
+  void parse_common(const std::vector<ParseRange>& ranges, ParseResult& out, int dest, int lane,
+                    std::vector<uint64_t>* iter_costs = nullptr);
   explicit Engine(int dev);
   struct Impl;
   Impl* p_;

@@ -1029,6 +1029,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
 
     // ------------------------------------------------------------------ block size, best, statistics
     const uint64_t cost = warp_dynamic_bits(s.hist, s.u.cs, lane);  // squeeze.c:492
+    if (b.iter_cost && lane == 0 && (uint32_t)it < b.iter_stride) b.iter_cost[(uint64_t)seg * b.iter_stride + it] = cost;
     ZB_TICK(4);
     if (cost < bestcost) {  // squeeze.c:496-501
       int t = curbuf; curbuf = bestbuf; bestbuf = t;

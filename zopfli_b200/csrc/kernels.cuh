@@ -109,6 +109,9 @@ struct Batch {
   uint16_t* out_ll;
   uint16_t* out_d;
   uint32_t* out_used;
+  // verbose: cost of every iteration of every block (squeeze.c:492-495), [nsegs][iter_stride]; null otherwise
+  uint64_t* iter_cost;
+  uint32_t iter_stride;
 };
 
 
