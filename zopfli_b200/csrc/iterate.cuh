@@ -697,8 +697,9 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         cj = cnext_;                                                                                        \
         tv = tv1; tv1 = tv2_; ds2 = ds3_; llb = llb1; llb1 = llb2_;                                         \
       }
-#define ZB_DP_FAST_8(R, M) ZB_DP_FAST_STEP(0, R, M) ZB_DP_FAST_STEP(1, R, M) ZB_DP_FAST_STEP(2, R, M) ZB_DP_FAST_STEP(3, R, M) \
-                           ZB_DP_FAST_STEP(4, R, M) ZB_DP_FAST_STEP(5, R, M) ZB_DP_FAST_STEP(6, R, M) ZB_DP_FAST_STEP(7, R, M)
+#define ZB_DP_FAST_4A(R, M) ZB_DP_FAST_STEP(0, R, M) ZB_DP_FAST_STEP(1, R, M) ZB_DP_FAST_STEP(2, R, M) ZB_DP_FAST_STEP(3, R, M)
+#define ZB_DP_FAST_4B(R, M) ZB_DP_FAST_STEP(4, R, M) ZB_DP_FAST_STEP(5, R, M) ZB_DP_FAST_STEP(6, R, M) ZB_DP_FAST_STEP(7, R, M)
+#define ZB_DP_FAST_8(R, M) ZB_DP_FAST_4A(R, M) ZB_DP_FAST_4B(R, M)
 #define ZB_DP_FAST_GROUP(R, M)                                                                               \
       {                                                                                                     \
         uint32_t t0_s = t0_l, dsx_s = dsx_c, gl_s = gl_c, lac_s = lac_c, ring_s = ring_c;                   \
@@ -742,19 +743,21 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
           else if (j0 + 35 > dirty_until) ZB_DP_FAST_GROUP(false, false)
           else ZB_DP_FAST_GROUP(true, false)
         } else {
-          // ---- general group, in blocks of eight steps: a block without a flagged position still
-          // runs the straight-line code (ring-joining variant); only the others check per step ----
-          for (uint32_t sb = 0; sb < 4; sb++) {
-          const uint32_t jb = j0 + sb * 8;
+          // ---- general group, in half-blocks of four steps: a half without a flagged position still
+          // runs the straight-line code (ring-joining variant); only the others check per step.  (Halves
+          // rather than whole eight-step blocks: a flagged position drags three neighbours through the
+          // slow loop instead of seven.) ----
+          for (uint32_t hb = 0; hb < 8; hb++) {
+          const uint32_t sb = hb >> 1, jb = j0 + hb * 4;
           if (jb >= nb) break;
-          if (skip_noop && ((flag_cur >> (sb * 8)) & 0xffu) == 0 && skip_left == 0 && !just_finished && jb + 8 <= nb) {
+          if (skip_noop && ((flag_cur >> (hb * 4)) & 0xfu) == 0 && skip_left == 0 && !just_finished && jb + 4 <= nb) {
             uint32_t t0_s = t0_l - sb * 64, dsx_s = dsx_c + sb * 256, gl_s = gl_c + sb * 64, lac_s = lac_c + sb * 16;
-            uint32_t ring_s = ring_c + sb * 128, lane_rot = (lane - 3u - sb * 8u) & 31u, sidx = 3u + sb * 8u;
-            ZB_DP_FAST_8(true, false)
+            uint32_t ring_s = ring_c + sb * 128, lane_rot = (lane - 3u - sb * 8u) & 31u, sidx = 3u + hb * 4u;
+            if (hb & 1) { ZB_DP_FAST_4B(true, false) } else { ZB_DP_FAST_4A(true, false) }
             (void)lane_rot;
             continue;
           }
-          const uint32_t jend = jb + 8 < nb ? jb + 8 : nb;
+          const uint32_t jend = jb + 4 < nb ? jb + 4 : nb;
           for (uint32_t j = jb; j < jend; j++) {
             const uint32_t jl = j & 31u;
             const double tv2 = lds_f64(t0_l + ds2 * 512 - (jl + 2) * 8);
@@ -852,6 +855,8 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
       }
 #undef ZB_DP_FAST_GROUP
 #undef ZB_DP_FAST_8
+#undef ZB_DP_FAST_4A
+#undef ZB_DP_FAST_4B
 #undef ZB_DP_FAST_STEP
       if (lane == 0) la[nb] = (uint16_t)decode_len(lfin_prev, nb);
       seq_base += ngroups;
