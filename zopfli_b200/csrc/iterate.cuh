@@ -712,10 +712,12 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         }                                                                                                   \
       }
 
+      uint32_t flag_pref = lds_u32(flag_r + (seq_base & 3u) * 4);  // flags of a group are fetched one group ahead
       for (uint32_t g = 0; g < ngroups; g++) {
         const uint32_t j0 = g * 32, q = seq_base + g, st = q & 3u, stn = (q + 1) & 3u;
         if (g + 1 < ngroups) mbar_wait_a(full_r + stn * 8, ((q + 1) >> 2) & 1u);  // the operand pipeline runs into the next group
-        const uint32_t flag_cur = lds_u32(flag_r + st * 4);
+        const uint32_t flag_cur = flag_pref;
+        if (g + 1 < ngroups) flag_pref = lds_u32(flag_r + stn * 4);
         const uint32_t dsx_c = dsx_r + st * 1024, gl_c = gl_r + st * 256;
         const uint32_t lac_c = lac_r + st * 64;
         const uint32_t ring_c = ring_r + ((j0 + 32) & 511u) * 16;  // slot of target j0 + 35
