@@ -216,9 +216,6 @@ struct Lane {  // an independent stream + arena set; chunk pipelines use a pair 
   cudaEvent_t ev[kTimerPairs][2];
   double* ev_acc[kTimerPairs];
   int ev_used = 0;
-#ifdef ZB_VAR_SIG
-  DevBuf sig1, sig2, h2b;
-#endif
   DevBuf segs, keywork, poswork, order, hv, hv2, idx1, idx2, rank1, rank2, bkt1, bkt2, ld, mlen, runs, dsx,
       ovf, la, path, st[4], jobs, out_ll, out_d, counters, misc, iterc;
   // split service
@@ -242,9 +239,6 @@ struct Lane {  // an independent stream + arena set; chunk pipelines use a pair 
                      &out_d, &counters, &misc, &iterc, &sp_ll, &sp_d, &sp_llsym, &sp_dsym, &sp_pos, &sp_snaps, &sp_stores,
                      &sp_work, &sp_evals, &sp_out};
     for (DevBuf* d : all) d->st = stream;
-#ifdef ZB_VAR_SIG
-    sig1.st = sig2.st = h2b.st = stream;
-#endif
   }
   void tic() {
     if (ev_used == kTimerPairs) { CK(cudaStreamSynchronize(stream)); flush_timers(); }
@@ -351,6 +345,7 @@ struct Engine::Impl {
     DevBuf* shared[] = {&in_buf, &same_buf, &tile_first, &next_tile, &sym_ll[0], &sym_ll[1], &sym_ll[2], &sym_d[0],
                         &sym_d[1], &sym_d[2], &outbuf, &emit_desc, &err_flag};
     for (DevBuf* d : shared) d->st = lane[0].stream;
+    CK(cudaFuncSetAttribute(k_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kMatchSmemBytes));
     {
       cudaFuncAttributes fa;
       CK(cudaFuncGetAttributes(&fa, k_iterate));
@@ -435,11 +430,6 @@ struct Engine::Impl {
     l.hv2.ensure(L.nkeys * 2 + 64);
     l.idx1.ensure(L.nkeys * 4 + 64);
     l.idx2.ensure(L.nkeys * 4 + 64);
-#ifdef ZB_VAR_SIG
-    l.sig1.ensure(L.nkeys * 8 + 64);
-    l.sig2.ensure(L.nkeys * 8 + 64);
-    l.h2b.ensure(L.nkeys * 2 + 64);
-#endif
     l.rank1.ensure(L.nkeys * 4 + 64);
     l.rank2.ensure(L.nkeys * 4 + 64);
     l.bkt1.ensure(ns * 32769 * 4 + 64);
@@ -470,11 +460,6 @@ struct Engine::Impl {
     b.hv2 = l.hv2.as<uint16_t>();
     b.idx1 = l.idx1.as<uint32_t>();
     b.idx2 = l.idx2.as<uint32_t>();
-#ifdef ZB_VAR_SIG
-    b.sig1 = l.sig1.as<uint64_t>();
-    b.sig2 = l.sig2.as<uint64_t>();
-    b.h2b = l.h2b.as<uint16_t>();
-#endif
     b.rank1 = l.rank1.as<uint32_t>();
     b.rank2 = l.rank2.as<uint32_t>();
     b.bkt1 = l.bkt1.as<uint32_t>();
@@ -519,7 +504,7 @@ struct Engine::Impl {
       CK(cudaGetLastError());
       l.toc(l.acc.ms_scatter);
       l.tic();
-      k_match<<<(unsigned)L.pw.size(), kMatchWarps * 32, 0, l.stream>>>(b, l.poswork.as<PosWork>());
+      k_match<<<(unsigned)L.pw.size(), kMatchWarps * 32, kMatchSmemBytes, l.stream>>>(b, l.poswork.as<PosWork>());
       CK(cudaGetLastError());
       l.toc(l.acc.ms_match);
       l.acc.launches += 4;
@@ -599,9 +584,6 @@ void Engine::set_stream(void* s) {
                      &l.sp_out, &p_->in_buf, &p_->same_buf, &p_->tile_first, &p_->next_tile, &p_->sym_ll[0], &p_->sym_ll[1],
                      &p_->sym_ll[2], &p_->sym_d[0], &p_->sym_d[1], &p_->sym_d[2], &p_->outbuf, &p_->emit_desc, &p_->err_flag};
     for (DevBuf* d : all) d->st = l.stream;
-#ifdef ZB_VAR_SIG
-    l.sig1.st = l.sig2.st = l.h2b.st = l.stream;
-#endif
   }
 }
 

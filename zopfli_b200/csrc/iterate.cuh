@@ -76,20 +76,7 @@ struct IterSmem {
   uint32_t stats[320], last[320], bests[320];
 };
 
-// ---- mbarrier / bulk-copy (TMA 1-D) primitives ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
+// ---- mbarrier / bulk-copy (TMA 1-D) primitives: smem_u32, mbar_init, mbar_expect_tx, bulk_g2s, mbar_wait live in kernels.cuh ----
 __device__ __forceinline__ double lds_f64(uint32_t a) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
@@ -169,16 +156,6 @@ __device__ __forceinline__ void lds_ring(uint32_t a, double& c, uint32_t& code) 
   c = __longlong_as_double((long long)x);
   code = (uint32_t)y;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(done)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-  } while (!done);
-}
-
 __device__ __forceinline__ double warp_min_first(double v, int& idx) {
   // minimum with the smallest index among equals (sequential strict-< scan order)
 #pragma unroll

@@ -79,13 +79,6 @@ struct Batch {
   uint32_t* rank2;
   uint32_t* bkt1;   // [nsegs][32769] counts -> starts
   uint32_t* bkt2;
-#ifdef ZB_VAR_SIG
-  // experiment (off by default): the first eight bytes of every bucket entry's position and its
-  // hashval2 travel with the bucket, so a candidate is read at random only when those agree
-  uint64_t* sig1;
-  uint64_t* sig2;
-  uint16_t* h2b;    // hv2 of idx1's entries, in bucket order
-#endif
   // match table
   uint32_t* ld;     // [npos] (len << 16) | dist of the longest match (raw, len may be 0/1/2)
   uint16_t* mlen;   // [npos] longest length or 0 (optimal segments only); bit 15 = long-run
@@ -143,6 +136,31 @@ __device__ __forceinline__ uint32_t match_len(const uint8_t* a, const uint8_t* b
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// ---- mbarrier / bulk-copy (TMA 1-D) primitives ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // k_same_*: same_g[p] = min(65535, #{t>=1: in[p+t]==in[p] contiguous}) over the whole input.
@@ -304,6 +322,7 @@ __global__ void k_bucket_scan(Batch b) {
 // the sort stays stable, and the serial walk that was one warp's 8 ms per master block is shared by
 // kScatterParts warps.  The running bucket cursors of a warp's range live in shared memory.
 // idx[dest] = position, rank[position] = dest.
+constexpr uint32_t kPackedIdxLimit = 1u << 24;  // chain-1 entries of smaller segments: position | s8 << 24
 constexpr int kScatterParts = 8;
 constexpr int kScatterBuckets = 32768 / kScatterParts;
 __global__ void __launch_bounds__(32) k_scatter(Batch b) {
@@ -317,21 +336,20 @@ __global__ void __launch_bounds__(32) k_scatter(Batch b) {
   const uint16_t* key = (second ? b.hv2 : b.hv) + sd.key_off;
   uint32_t* idx = (second ? b.idx2 : b.idx1) + sd.key_off;
   uint32_t* rank = (second ? b.rank2 : b.rank1) + sd.key_off;
-#ifdef ZB_VAR_SIG
-  uint64_t* sig = (second ? b.sig2 : b.sig1) + sd.key_off;
-  const uint8_t* kbytes = b.in + sd.winstart;  // byte of key index 0
-#endif
   const uint32_t lane = threadIdx.x;
+  const uint16_t* other = b.hv2 + sd.key_off;
+  const bool pack = !second && sd.nkeys < kPackedIdxLimit;
   for (uint32_t i = lane; i < (uint32_t)kScatterBuckets; i += 32) cursor[i] = bs[i];
   __syncwarp();
   // keys of 8 rounds are fetched up front so that the global-load latency is paid once per 256
   // positions instead of once per round
   for (uint32_t base0 = 0; base0 < sd.nkeys; base0 += 256) {
-    uint32_t kreg[8];
+    uint32_t kreg[8], sreg[8];
 #pragma unroll
     for (int u = 0; u < 8; u++) {
       const uint32_t i = base0 + u * 32 + lane;
       kreg[u] = i < sd.nkeys ? key[i] : 0xffffffffu;
+      sreg[u] = (pack && i < sd.nkeys) ? (uint32_t)other[i] : 0u;
     }
 #pragma unroll
     for (int u = 0; u < 8; u++) {
@@ -348,12 +366,11 @@ __global__ void __launch_bounds__(32) k_scatter(Batch b) {
       __syncwarp();
       if (act) {
         const uint32_t d = cur + before;
-        idx[d] = i;
+        // chain 1 entries carry (hashval2 ^ hashval) & 255 = (same - 3) & 255 of their position in the top byte:
+        // inside one hashval bucket that byte decides hashval2 equality (hash.c:129), so k_match's
+        // chain-switch test (lz77.c:509-519) needs no second random read
+        idx[d] = pack ? (i | (((sreg[u] ^ kk) & 255u) << 24)) : i;
         rank[i] = d;
-#ifdef ZB_VAR_SIG
-        sig[d] = ld_u64_unaligned(kbytes + i);
-        if (!second) b.h2b[sd.key_off + d] = b.hv2[sd.key_off + i];
-#endif
       }
     }
   }
@@ -362,12 +379,42 @@ __global__ void __launch_bounds__(32) k_scatter(Batch b) {
 // ---------------------------------------------------------------------------------------------
 // k_match: ZopfliFindLongestMatch for every parse position, cache-free (lz77.c:407-542).
 
+// One CTA takes kMatchPosPerCta consecutive positions.  Everything a position's walk compares -- its own
+// bytes and every candidate within the 32 KiB window (lz77.c:464) -- lies in one contiguous stretch of
+// the input: [first position - 32767, last position + 258].  That stretch (~34 KB) is staged into shared
+// memory with ONE TMA bulk copy (cp.async.bulk + mbarrier) per CTA, so the byte compares of the walk
+// (the src[best] == cand[best] pre-check that most candidates fail, and the common-prefix loop) hit shared
+// memory instead of a random 32-byte sector of L2 each.  The chain lists themselves (bucket slices of idx)
+// are read coalesced from global memory, 32 candidates per round; the chain-switch test reads the
+// candidate's (same-3)&255 from the top byte of its bucket entry (k_scatter) instead of hashval2[candidate].
 constexpr int kMatchWarps = 8;
-constexpr int kMatchPosPerCta = 128;
+constexpr int kMatchPosPerCta = 512;
+constexpr int kMatchWinBytes = 32768 + kMatchPosPerCta + kMaxMatch + 78;  // window + tile + longest match + alignment slack (multiple of 16)
+static_assert(kMatchWinBytes % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+constexpr int kMatchSmemBytes = kMatchWinBytes + kMatchWarps * 256 * 4;
 struct PosWork { uint32_t seg, first; };
 
+__device__ __forceinline__ uint32_t lds32_unaligned(const uint8_t* p) {  // p points into shared memory
+  const uint32_t a = smem_u32(p);
+  uint32_t lo, hi;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(a & ~3u));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"((a & ~3u) + 4u));
+  return __funnelshift_r(lo, hi, (a & 3u) * 8u);
+}
+__device__ __forceinline__ uint32_t match_len_smem(const uint8_t* a, const uint8_t* b, uint32_t limit) {
+  uint32_t m = 0;
+  while (m < limit) {
+    const uint32_t x = lds32_unaligned(a + m) ^ lds32_unaligned(b + m);
+    if (x) { m += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+    m += 4;
+  }
+  return m < limit ? m : limit;
+}
+
 __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWork* __restrict__ work) {
-  __shared__ uint32_t stage[kMatchWarps][256];  // run list of the position being walked
+  extern __shared__ __align__(16) uint8_t win[];           // kMatchWinBytes, then the run-list staging
+  uint32_t (*stage)[256] = (uint32_t (*)[256])(win + kMatchWinBytes);
+  __shared__ __align__(8) uint64_t win_bar;
   const PosWork w = work[blockIdx.x];
   const SegDesc sd = b.segs[w.seg];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -376,10 +423,31 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
   const uint32_t* bs1 = b.bkt1 + (uint64_t)w.seg * 32769;
   const uint32_t* bs2 = b.bkt2 + (uint64_t)w.seg * 32769;
   const uint32_t woff = (uint32_t)(sd.instart - sd.winstart);  // key index of parse position 0
-  const uint8_t* wbase = b.in + sd.winstart;                   // byte of key index 0
+  const bool packed = sd.nkeys < kPackedIdxLimit;
   uint32_t* myruns = stage[warp];
 
-  for (uint32_t t = warp; t < kMatchPosPerCta; t += kMatchWarps) {
+  // ---- stage the window: key indices [wlo, whi) of the segment, wlo 16-byte aligned in the input ----
+  const uint32_t ip0 = woff + w.first;                        // key index of the tile's first position
+  const uint64_t g0 = sd.winstart + (ip0 > 32767u ? ip0 - 32767u : 0u);  // absolute input byte of the oldest candidate
+  const uint64_t gal = g0 & ~(uint64_t)15;                    // the input buffer itself is 16-byte aligned
+  const int64_t wlo = (int64_t)gal - (int64_t)sd.winstart;    // key index of window byte 0 (>= -15: winstart need not be aligned)
+  uint64_t gend = sd.winstart + (uint64_t)ip0 + kMatchPosPerCta + kMaxMatch + 8;
+  const uint64_t gmax = (b.insize + 16) & ~(uint64_t)15;      // the engine keeps >= 16 readable bytes behind the input
+  if (gend > gmax) gend = gmax;
+  const uint32_t nbytes = (uint32_t)(((gend - gal) + 15) & ~(uint64_t)15) <= (uint32_t)kMatchWinBytes
+                              ? (uint32_t)(((gend - gal) + 15) & ~(uint64_t)15) : (uint32_t)kMatchWinBytes;
+  if (threadIdx.x == 0) {
+    mbar_init(&win_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&win_bar, nbytes);
+    bulk_g2s(win, b.in + gal, nbytes, &win_bar);
+  }
+  __syncthreads();
+  mbar_wait(&win_bar, 0);
+  const uint8_t* wsm = win - wlo;                             // wsm[key index] = input byte of that key position
+
+  for (uint32_t t = warp; t < (uint32_t)kMatchPosPerCta; t += kMatchWarps) {
     const uint32_t j = w.first + t;  // parse position within the segment
     if (j >= sd.npos) break;
     const uint32_t ip = woff + j;    // key index of pos
@@ -390,16 +458,13 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
       uint32_t same0 = b.same_g[sd.winstart + ip];
       { uint64_t clip = sd.inend - 1 - (sd.winstart + ip); if (same0 > clip) same0 = (uint32_t)clip; }
       const uint32_t v2 = hv2[ip];
+      const uint32_t s8p = (v2 ^ hv[ip]) & 255u;
       int hops = kMaxChainHits;
       bool chain2 = false;
       const uint32_t* idx = b.idx1 + sd.key_off;
       uint32_t lo = bs1[hv[ip]];
       uint32_t cur = b.rank1[sd.key_off + ip];  // next candidate is idx[cur-1]
-      const uint8_t* src = wbase + ip;
-#ifdef ZB_VAR_SIG
-      const uint64_t src8 = ld_u64_unaligned(src);
-      const uint64_t* sig = b.sig1 + sd.key_off;
-#endif
+      const uint8_t* src = wsm + ip;
       for (;;) {
         uint32_t avail = cur - lo;
         uint32_t take = avail < 32u ? avail : 32u;
@@ -407,31 +472,19 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
         if (take == 0) break;  // bucket exhausted == self link lz77.c:523
         uint32_t iq = 0, dist = 0, m = 0;
         bool valid = lane < take;
+        bool h2eq = false;
         if (valid) {
-          iq = idx[cur - 1 - lane];
+          const uint32_t e = idx[cur - 1 - lane];
+          iq = (!chain2 && packed) ? (e & 0xffffffu) : e;
           dist = ip - iq;
           valid = dist < (uint32_t)kWindow;  // lz77.c:464
+          if (valid) {
+            const uint8_t* cand = wsm + iq;
+            // lz77.c:478-479: a candidate that differs at offset `best` cannot beat it
+            if (src[best] == cand[best]) m = match_len_smem(src, cand, limit);
+            if (!chain2) h2eq = packed ? ((e >> 24) == s8p) : (hv2[iq] == v2);
+          }
         }
-        bool h2eq = false;
-#ifdef ZB_VAR_SIG
-        if (valid) {
-          // common prefix from the bucket's own copy of the candidate's first eight bytes; the
-          // candidate itself is read only when all eight agree (the lz77.c:478 pre-check is
-          // implied: a candidate that differs at offset `best` has m <= best)
-          const uint64_t x = sig[cur - 1 - lane] ^ src8;
-          const uint32_t m8 = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8u;
-          if (m8 < 8u || limit <= 8u) m = m8 < limit ? m8 : limit;
-          else m = match_len(src, wbase + iq, 8, limit);
-          if (!chain2) h2eq = b.h2b[sd.key_off + cur - 1 - lane] == v2;
-        }
-#else
-        if (valid) {
-          const uint8_t* cand = wbase + iq;
-          // lz77.c:478-479: a candidate that differs at offset `best` cannot beat it
-          if (src[best] == cand[best]) m = match_len(src, cand, 0, limit);
-          if (!chain2) h2eq = hv2[iq] == v2;
-        }
-#endif
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
         const uint32_t nv = __popc(vmask);  // valid lanes form a prefix (distances increase)
         if (nv == 0) break;
@@ -474,9 +527,6 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_match(Batch b, const PosWo
         if (do_switch) {  // lz77.c:509-519: continue from this candidate along chain 2
           uint32_t iqs = __shfl_sync(0xffffffffu, iq, s);
           chain2 = true;
-#ifdef ZB_VAR_SIG
-          sig = b.sig2 + sd.key_off;
-#endif
           idx = b.idx2 + sd.key_off;
           lo = bs2[v2];
           cur = b.rank2[sd.key_off + iqs];
