@@ -136,11 +136,11 @@ struct PinBuf {  // grow-only page-locked host staging: round trips through it s
 
 // Pageable host memory <-> device through page-locked staging, several host threads deep: a pageable
 // cudaMemcpy is one thread's memcpy into the driver's staging buffer (~10 GB/s); here kThreads threads
-// each shuttle 8 MB chunks through their own pinned double buffer and stream, so the copy runs at
+// each shuttle 4 MB chunks through their own pinned double buffer and stream, so the copy runs at
 // whatever the link sustains.  Buffers that are already page-locked go straight to the DMA engine.
 struct Stager {
-  static constexpr int kThreads = 6;
-  static constexpr size_t kChunk = 8u << 20;
+  static constexpr int kThreads = 12;
+  static constexpr size_t kChunk = 4u << 20;
   int dev = 0;
   bool ready = false;
   std::mutex mu;
