@@ -640,9 +640,22 @@ static unsigned table_dist(const ZoTable* t, size_t j, unsigned len) {
   return 0;
 }
 
-/* GetBestLengths squeeze.c:217-309 */
+/* Optional observer of every DP pass (oracle/dp_int_model.c checks the kernels' integer restatement
+ * of the cost arithmetic against the result computed below).  NULL in the oracle library proper. */
+typedef void (*ZoDpObserver)(const ZoSegment* seg, const ZoTable* t, const ZoStats* st,
+                             const uint16_t* length_array, const float* costs);
+static ZoDpObserver zo_dp_observer = NULL;
+static void best_lengths_ref(const ZoSegment* seg, const ZoTable* t, const ZoStats* st,
+                             uint16_t* length_array, float* costs);
 static void best_lengths(const ZoSegment* seg, const ZoTable* t, const ZoStats* st,
                          uint16_t* length_array, float* costs) {
+  best_lengths_ref(seg, t, st, length_array, costs);
+  if (zo_dp_observer) zo_dp_observer(seg, t, st, length_array, costs);
+}
+
+/* GetBestLengths squeeze.c:217-309 */
+static void best_lengths_ref(const ZoSegment* seg, const ZoTable* t, const ZoStats* st,
+                             uint16_t* length_array, float* costs) {
   const uint8_t* in = seg->in;
   size_t nb = seg->inend - seg->instart, j, k;
   double mincost = model_min_cost(st);

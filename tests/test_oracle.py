@@ -5,6 +5,8 @@ from /root/reference (oracle/_ref), at the seams of SURVEY.md section 4:
 plus the integer helpers the iterate loop drags in (katajainen.c, tree.c, deflate.c estimators).
 Bit-exact everywhere (integer/byte work; the fp64 entropy must match to the last bit too).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -113,3 +115,39 @@ def test_entropy_and_rle(ref, oracle):
         if t % 3 == 0:
             c = np.repeat(rng.integers(0, 9, n // 8 + 1), 8)[:n].astype(np.uint64)
         assert np.array_equal(ref.optimize_rle(c), oracle.optimize_rle(c))
+
+
+# ---- the integer formulation of the forward DP (k_iterate's "integer window", iterate.cuh) ----
+# oracle/dp_int_model.c runs a sequential model of it next to the oracle's reference DP on every pass of
+# ZopfliLZ77Optimal / OptimalFixed and counts positions whose cost or length_array entry differs.
+INT_DP_CASES = [
+    ("text", TXT, 32768, 300000, 5),
+    ("text-fixed", TXT, 32768, 300000, 0),
+    ("binary", corpus.synth_binary(300000, 4), 0, 300000, 8),
+    ("binary-fixed", corpus.synth_binary(300000, 4), 0, 300000, 0),
+    ("collide", corpus.adv_collide(), 0, len(corpus.adv_collide()), 4),
+    ("runs", corpus.adv_runs(), 0, len(corpus.adv_runs()), 4),
+    ("longrun-cut", corpus.adv_longrun(), 1000, 68000, 3),
+    ("random", corpus.random_bytes(200000), 0, 200000, 3),
+]
+
+
+@pytest.mark.parametrize("name,data,s,e,iters", INT_DP_CASES, ids=[c[0] for c in INT_DP_CASES])
+def test_integer_dp_model_equals_reference_dp(name, data, s, e, iters):
+    import ctypes as C
+    zref.ensure_built()
+    path = os.path.join(zref.ORACLE_DIR, "_build", "libdp_int_model.so")
+    if not os.path.exists(path):
+        import subprocess
+        subprocess.check_call(["make", "-s", "-C", zref.ORACLE_DIR, "oracle"])
+    lib = C.CDLL(path)
+    lib.zo_dp_int_check.restype = C.c_uint64
+    lib.zo_dp_int_check.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
+    buf = np.frombuffer(data, dtype=np.uint8).copy()
+    out = np.zeros(8, dtype=np.uint64)
+    mism = lib.zo_dp_int_check(buf.ctypes.data, s, e, iters, out.ctypes.data)
+    steps_total, steps_int = int(out[0]), int(out[1])
+    assert mism == 0
+    assert steps_total > 0
+    if name in ("text", "random"):
+        assert steps_int > 0.8 * steps_total   # the model really ran in the integer representation

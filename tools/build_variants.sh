@@ -6,6 +6,6 @@ mkdir -p ../_var
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -Wno-deprecated-gpu-targets -shared engine.cu driver.cpp api.cpp dist.cpp -Xlinker -soname=libzopfli.so.1 -lpthread -ldl"
 build() { name=$1; shift; nvcc $FLAGS "$@" -o ../_var/lib_$name.so & }
 # build name -DZB_VAR_...   (add experiment variants here; the kernels pick them up with #ifdef)
-build sig -DZB_VAR_SIG   # k_match: candidate prefix and hashval2 from the bucket entry (kernels.cuh)
+build kinds -DZB_DP_KINDS   # k_iterate: DP cycles by kind of group (tools/one_block.py, tools/gpu_perf.py print them)
 wait
 ls -la ../_var

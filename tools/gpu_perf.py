@@ -16,7 +16,8 @@ for rep in range(2):
     L.reset_stats()
     t = time.time(); z = L.compress(data, 0, numiterations=iters); dt = time.time() - t
     st = L.stats()
-    print("rep %d: %.1f MB in %.3fs = %.2f MiB/s, out %d" % (rep, mb, dt, n / 1048576 / dt, len(z)))
+    import zlib
+    print("rep %d: %.1f MB in %.3fs = %.2f MiB/s, out %d (crc %08x)" % (rep, mb, dt, n / 1048576 / dt, len(z), zlib.crc32(z)))
 names = ["model", "dp", "trace", "follow", "cost", "stats"]
 print({k: round(v, 2) for k, v in st.items() if k.startswith("ms_")})
 tot = sum(st["cyc_sum"]) or 1
@@ -26,4 +27,11 @@ print("critical block: %d positions, %.1f Mcycles total = %.3fs @1.965GHz:" % (s
       {nm: "%.1f%%" % (100.0 * c / mx) for nm, c in zip(names, st["cyc_max"])})
 print("cycles per DP step (critical block): %.1f ; all blocks avg: %.1f" % (
     st["cyc_max"][1] / max(1, st["max_block_positions"] * iters), st["cyc_sum"][1] / max(1, st["iterate_steps"])))
-print("launches", st["launches"], "steps", st["iterate_steps"])
+print("launches", st["launches"], "steps", st["iterate_steps"], "integer-window share of DP steps: %.1f%%" % (100.0 * st["int_steps"] / max(1, st["iterate_steps"])))
+kinds = ["int", "magic", "plain", "ring", "general"]
+for tag in ("sum", "max"):
+    cy, cn = st["dp_cyc_" + tag], st["dp_cnt_" + tag]
+    tot = sum(cy) or 1
+    print("DP by group kind (%s):" % ("all blocks" if tag == "sum" else "critical block"),
+          {k: "%.1f%% of cycles, %d groups, %.1f cyc/step" % (100.0 * c / tot, n, c / max(1, n) / 32) for k, c, n in zip(kinds, cy, cn)},
+          "positions in the per-step loop:", cn[5])

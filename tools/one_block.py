@@ -11,6 +11,11 @@ data = corpus.synth_text(n, 5)
 lib = zb.Library(os.environ["ZB_LIB"]) if os.environ.get("ZB_LIB") else zb.Library()
 t = time.time()
 out = lib.compress(data, zb.ZOPFLI_FORMAT_DEFLATE, numiterations=its, blocksplitting=0)
-print("one block: %d -> %d bytes, %.3fs" % (n, len(out), time.time() - t))
+import zlib
+print("one block: %d -> %d bytes (crc %08x), %.3fs" % (n, len(out), zlib.crc32(out), time.time() - t))
 st = lib.stats()
 print({k: v for k, v in st.items() if k in ("ms_iterate", "cyc_max", "iterate_steps")})
+kinds = ["int", "magic", "plain", "ring", "general"]
+print("DP %.1f cycles/step;" % (st["cyc_max"][1] / max(1, st["iterate_steps"])),
+      {k: "%.1f%% of cycles, %.1f cyc/step" % (100.0 * c / max(1, sum(st["dp_cyc_max"])), c / max(1, m) / 32)
+       for k, c, m in zip(kinds, st["dp_cyc_max"], st["dp_cnt_max"])}, "per-step loop positions:", st["dp_cnt_max"][5])

@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzopfli.so.1")
+# ZOPFLI_B200_LIB: another build of the same C ABI (developer variants from tools/build_variants.sh)
+LIB_PATH = os.environ.get("ZOPFLI_B200_LIB") or os.path.join(_HERE, "libzopfli.so.1")
 
 ZOPFLI_FORMAT_GZIP = 0
 ZOPFLI_FORMAT_ZLIB = 1
@@ -37,10 +38,12 @@ class Stats(C.Structure):
                                           "iterate_steps", "h2d_bytes", "d2h_bytes")] + \
                [("cyc_sum", C.c_uint64 * 6), ("cyc_max", C.c_uint64 * 6), ("max_block_positions", C.c_uint64),
                 ("ms_split", C.c_double), ("split_evals", C.c_uint64), ("split_rounds", C.c_uint64),
-                ("iterate_launches", C.c_uint64)]
+                ("iterate_launches", C.c_uint64), ("int_steps", C.c_uint64),
+                ("dp_cyc_sum", C.c_uint64 * 5), ("dp_cnt_sum", C.c_uint64 * 6),
+                ("dp_cyc_max", C.c_uint64 * 5), ("dp_cnt_max", C.c_uint64 * 6)]
 
     def as_dict(self):
-        return {n: (list(getattr(self, n)) if n.startswith("cyc_") else getattr(self, n)) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n.startswith(("cyc_", "dp_c")) else getattr(self, n)) for n, _ in self._fields_}
 
 
 EXPORTS = ["ZopfliInitOptions", "ZopfliCompress", "ZopfliDeflate", "ZopfliDeflatePart",

@@ -614,6 +614,9 @@ void ZopfliB200GetStats(ZopfliB200Stats* o) {
   o->max_block_positions = e.max_block_positions;
   o->ms_split = e.ms_split; o->split_evals = e.split_evals; o->split_rounds = e.split_rounds;
   o->iterate_launches = e.iterate_launches;
+  o->int_steps = e.int_steps;
+  for (int k = 0; k < 5; k++) { o->dp_cyc_sum[k] = e.dp_cyc_sum[k]; o->dp_cyc_max[k] = e.dp_cyc_max[k]; }
+  for (int k = 0; k < 6; k++) { o->dp_cnt_sum[k] = e.dp_cnt_sum[k]; o->dp_cnt_max[k] = e.dp_cnt_max[k]; }
 }
 
 void ZopfliB200ResetStats(void) {

@@ -485,6 +485,8 @@ struct Engine::Impl {
     b.out_ll = l.out_ll.as<uint16_t>();
     b.out_d = l.out_d.as<uint16_t>();
     b.out_used = l.counters.as<uint32_t>() + 1;
+    static const uint32_t dp_flags = [] { const char* e = getenv("ZOPFLI_B200_INTDP"); return (e && atoi(e) == 0) ? 0u : 1u; }();
+    b.dp_flags = dp_flags;
 
     CK(cudaMemsetAsync(l.bkt1.p, 0, ns * 32769 * 4, l.stream));
     CK(cudaMemsetAsync(l.bkt2.p, 0, ns * 32769 * 4, l.stream));
@@ -600,10 +602,17 @@ EngineStats Engine::stats_all() {
     r.ms_split += a.ms_split; r.split_evals += a.split_evals; r.split_rounds += a.split_rounds;
     r.iterate_launches += a.iterate_launches;
     r.launches += a.launches; r.match_positions += a.match_positions; r.iterate_positions += a.iterate_positions;
-    r.iterate_steps += a.iterate_steps; r.h2d_bytes += a.h2d_bytes; r.d2h_bytes += a.d2h_bytes;
+    r.iterate_steps += a.iterate_steps; r.h2d_bytes += a.h2d_bytes; r.d2h_bytes += a.d2h_bytes; r.int_steps += a.int_steps;
     uint64_t ta = 0, tr = 0;
     for (int i = 0; i < 6; i++) { r.cyc_sum[i] += a.cyc_sum[i]; ta += a.cyc_max[i]; tr += r.cyc_max[i]; }
-    if (ta > tr) { for (int i = 0; i < 6; i++) r.cyc_max[i] = a.cyc_max[i]; r.max_block_positions = a.max_block_positions; }
+    for (int i = 0; i < 5; i++) r.dp_cyc_sum[i] += a.dp_cyc_sum[i];
+    for (int i = 0; i < 6; i++) r.dp_cnt_sum[i] += a.dp_cnt_sum[i];
+    if (ta > tr) {
+      for (int i = 0; i < 6; i++) r.cyc_max[i] = a.cyc_max[i];
+      r.max_block_positions = a.max_block_positions;
+      for (int i = 0; i < 5; i++) r.dp_cyc_max[i] = a.dp_cyc_max[i];
+      for (int i = 0; i < 6; i++) r.dp_cnt_max[i] = a.dp_cnt_max[i];
+    }
   }
   return r;
 }
@@ -623,10 +632,17 @@ EngineStats Engine::stats() {
     r.ms_split += a.ms_split; r.split_evals += a.split_evals; r.split_rounds += a.split_rounds;
     r.iterate_launches += a.iterate_launches;
     r.launches += a.launches; r.match_positions += a.match_positions; r.iterate_positions += a.iterate_positions;
-    r.iterate_steps += a.iterate_steps; r.h2d_bytes += a.h2d_bytes; r.d2h_bytes += a.d2h_bytes;
+    r.iterate_steps += a.iterate_steps; r.h2d_bytes += a.h2d_bytes; r.d2h_bytes += a.d2h_bytes; r.int_steps += a.int_steps;
     uint64_t ta = 0, tr = 0;
     for (int i = 0; i < 6; i++) { r.cyc_sum[i] += a.cyc_sum[i]; ta += a.cyc_max[i]; tr += r.cyc_max[i]; }
-    if (ta > tr) { for (int i = 0; i < 6; i++) r.cyc_max[i] = a.cyc_max[i]; r.max_block_positions = a.max_block_positions; }
+    for (int i = 0; i < 5; i++) r.dp_cyc_sum[i] += a.dp_cyc_sum[i];
+    for (int i = 0; i < 6; i++) r.dp_cnt_sum[i] += a.dp_cnt_sum[i];
+    if (ta > tr) {
+      for (int i = 0; i < 6; i++) r.cyc_max[i] = a.cyc_max[i];
+      r.max_block_positions = a.max_block_positions;
+      for (int i = 0; i < 5; i++) r.dp_cyc_max[i] = a.dp_cyc_max[i];
+      for (int i = 0; i < 6; i++) r.dp_cnt_max[i] = a.dp_cnt_max[i];
+    }
   }
   return r;
 }
@@ -745,7 +761,8 @@ void Engine::parse_common(const std::vector<ParseRange>& ranges, ParseResult& ou
       static const unsigned static_smem = [] { cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, k_iterate)); return (unsigned)fa.sharedSizeBytes; }();
       static const unsigned pad_many = [] { const char* e = getenv("ZOPFLI_B200_ITER_PAD"); return e ? (unsigned)atoi(e) : 56u * 1024u - static_smem; }();
       static const unsigned pad_few = [] { const char* e = getenv("ZOPFLI_B200_ITER_PAD_FEW"); return e ? (unsigned)atoi(e) : 222u * 1024u - static_smem; }();
-      const unsigned pad = ns <= 64 ? pad_few : pad_many;
+      unsigned pad = ns <= 64 ? pad_few : pad_many;
+      if (pad < sizeof(IterDyn)) pad = (unsigned)sizeof(IterDyn);  // the integer window's tables live in the dynamic part
       k_iterate<<<(unsigned)ns, 64, pad, l.stream>>>(b, l.order.as<uint32_t>());
       CK(cudaGetLastError());
       l.toc(l.acc.ms_iterate);
@@ -807,9 +824,17 @@ void Engine::parse_common(const std::vector<ParseRange>& ranges, ParseResult& ou
     if (ranges[i].mode == 1) {
       uint64_t tot = 0, cur = 0;
       for (int k = 0; k < 6; k++) { l.acc.cyc_sum[k] += js[i].cyc[k]; tot += js[i].cyc[k]; cur += l.acc.cyc_max[k]; }
-      if (tot > cur) { for (int k = 0; k < 6; k++) l.acc.cyc_max[k] = js[i].cyc[k]; l.acc.max_block_positions = L.segs[i].npos; }
+      for (int k = 0; k < 5; k++) l.acc.dp_cyc_sum[k] += js[i].dpc[k];
+      for (int k = 0; k < 6; k++) l.acc.dp_cnt_sum[k] += js[i].dpn[k];
+      if (tot > cur) {
+        for (int k = 0; k < 6; k++) l.acc.cyc_max[k] = js[i].cyc[k];
+        l.acc.max_block_positions = L.segs[i].npos;
+        for (int k = 0; k < 5; k++) l.acc.dp_cyc_max[k] = js[i].dpc[k];
+        for (int k = 0; k < 6; k++) l.acc.dp_cnt_max[k] = js[i].dpn[k];
+      }
       l.acc.iterate_positions += L.segs[i].npos;
       l.acc.iterate_steps += (uint64_t)L.segs[i].npos * ranges[i].numiterations;
+      l.acc.int_steps += (uint64_t)js[i].int_groups * 32u;
     }
   }
 }

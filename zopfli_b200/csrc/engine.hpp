@@ -29,6 +29,9 @@ struct EngineStats {  // accumulated since the last reset; times from CUDA event
   uint64_t cyc_sum[6];   // k_iterate phase cycles summed over blocks (model, DP, trace, follow, cost, stats)
   uint64_t cyc_max[6];   // same for the block with the largest total (the critical path)
   uint64_t max_block_positions;
+  uint64_t int_steps;    // DP steps that ran in the integer window
+  uint64_t dp_cyc_sum[5], dp_cnt_sum[6];   // DP cycles / groups by kind of group (JobState::dpc, dpn), summed over blocks
+  uint64_t dp_cyc_max[5], dp_cnt_max[6];   // same for the critical-path block
 };
 
 class Engine {

@@ -32,6 +32,32 @@ __host__ __device__ __forceinline__ uint32_t decode_len(uint32_t code, uint32_t 
   if (code & kCodeLong) return code & 0x3ffu;
   return ((target - code) & 31u) + 3u;
 }
+// ---- integer window (round 2, v10) ----
+// While every cost a group of 32 positions can touch stays inside one float binade [2^e, 2^(e+1)) -- the
+// same condition the magic-constant rounding needs -- the reference's arithmetic collapses to integers:
+//   fl64(x + c) = x + c' with c' = c on the binade's double grid, (float) of that = x + k1 ulp with
+//   k1 = round(c' / ulp) independent of x (x is a multiple of ulp) unless c'/ulp is an exact tie, and
+//   the strict compare newCost < costs[t] (squeeze.c:278,296) is  x + k1 < costs[t], or equal and the
+//   float rounding went up.
+// A cost becomes (float bits - bits(2^e)); an edge is "+ k1"; and the sequential rule "first strict
+// improvement wins" becomes ONE unsigned minimum over packed words (value << 7 | tiebreak) with
+// tiebreak = up ? 63 - o : 64 + o, o = order of the edge's source among the sources of its target
+// (0: length >= 35 via the ring, 1..32: lengths 34..3, 33: the literal).  A DP step is then two
+// VIADDMNMX and one LOP3 on the chain instead of six DADDs, two DSETPs and eight selects.  Tables
+// (k1, up) are rebuilt per binade; a binade whose table holds an exact tie (or that is too narrow
+// for the safety margins) runs on the fp64 paths.  oracle/dp_int_model.c is the sequential model of
+// this formulation, checked against the reference DP on every pass (tests/test_oracle.py).
+constexpr uint32_t kIntInf = 0xffffffffu;   // no edge yet
+constexpr uint32_t kIntNoEdge = 1u << 30;   // table entry "no such length here"; any word >= this is infinite
+constexpr uint32_t kCodeInt = 0x1000u;      // length code taken from an integer word: | tiebreak bits
+struct IterDyn {                       // dynamic shared memory of k_iterate (engine.cu pads the launch to at least this)
+  uint32_t ti[31 * 64];                // integer edge table of the current binade, indexed like IterSmem::t0
+  uint32_t liti[2][256];               // integer literal edges, double-buffered by generation parity (DP warp -> feeder)
+  uint32_t gli[4 * 32 + 4];            // literal edge of each staged position; [128..129] mirror [0..1]   (feeder warp)
+  uint32_t tag[4];                     // generation of liti a stage was filled from                        (feeder warp)
+  uint32_t xchi[4];                    // hand-off slots of the integer window
+  uint32_t gen;                        // published generation of liti
+};
 struct DpStage {                       // forward-DP working set; 4 stages of 32 positions each
   RingEnt ring[512];                   // pending costs of targets >= j+35 (long edges only); slot (t-3) & 511
   uint32_t runs[4][32 * kRunSlots];    // TMA-staged run lists
@@ -46,6 +72,16 @@ struct DpStage {                       // forward-DP working set; 4 stages of 32
                                        // because the order of memory operations is the one thing the assembler keeps:
                                        // a shuffle is sunk to just before its use and its latency lands on the chain.
 };
+// length code -> length_array entry; integer words that won through a long edge find its length in the ring slot
+__device__ __forceinline__ uint32_t decode_code(uint32_t code, uint32_t target, const RingEnt* ring) {
+  if (code & kCodeInt) {
+    const uint32_t tb = code & 127u, o = tb < 64u ? 63u - tb : tb - 64u;
+    if (o == 33u) return 1u;
+    if (o == 0u) return ring[(target - 3u) & 511u].code & 0x3ffu;
+    return 35u - o;
+  }
+  return decode_len(code, target);
+}
 struct WarpPm {                        // warp-wide package-merge working set (warp_length_limited)
   uint32_t key[kNumLL];                // active symbols sorted by (weight << 9 | symbol)
   uint32_t pk[kNumLL];                 // package weights of the level being built
@@ -72,6 +108,8 @@ struct IterSmem {
   __align__(8) uint64_t full[4];   // stage filled (TMA bytes + feeder scalars)
   __align__(8) uint64_t empty[4];  // stage consumed by the DP warp
   uint32_t go;                     // DP warp -> feeder warp: another iteration follows
+  unsigned long long dpc[5];       // DP cycles / groups by kind (see JobState)
+  uint32_t dpn[6];
   uint32_t hist[320];
   uint32_t stats[320], last[320], bests[320];
 };
@@ -85,6 +123,11 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
   return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -404,6 +447,8 @@ __device__ __forceinline__ uint32_t first_dist_of_symbol(int sd) {  // squeeze.c
 // Outside the DP phase it is parked at a named barrier.
 __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restrict__ order) {
   __shared__ IterSmem s;
+  extern __shared__ __align__(16) unsigned char zb_iter_dyn[];
+  IterDyn& dyn = *reinterpret_cast<IterDyn*>(zb_iter_dyn);
   const uint32_t seg = order[blockIdx.x], lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   const SegDesc sd = b.segs[seg];
   if (sd.mode == 0) return;
@@ -423,13 +468,19 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
   int curbuf = 0, bestbuf = 1;
   uint32_t flags = 0;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < 4; i++) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], 1); dyn.tag[i] = 0; dyn.xchi[i] = kIntInf; }
+    dyn.gen = 0;
+    for (int i = 0; i < 5; i++) s.dpc[i] = 0;
+    for (int i = 0; i < 6; i++) s.dpn[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // the staged distance symbols index the cost table: keep every byte of the staging area <= 30
   for (uint32_t t = threadIdx.x; t < sizeof(s.u.dp.dsx) / 4; t += 64) ((uint32_t*)&s.u.dp.dsx[0])[t] = 0;
   __syncthreads();
   uint32_t seq_base = 0;  // running group sequence number: stage = seq & 3, parity = (seq >> 2) & 1
+  uint32_t igroups = 0;   // groups that ran in the integer window
+  const bool int_on = (b.dp_flags & 1u) != 0;
+  uint32_t i_gen = 0;     // generation of the integer tables (DP warp); a stage is usable only if its tag equals it
   const uint32_t ngroups = (nb + 31) >> 5;
 
   if (wid == 1) {
@@ -450,6 +501,14 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
           s.u.dp.gl[st * 32 + lane] = lc;
           if (st == 0 && lane < 2) s.u.dp.gl[128 + lane] = lc;
           s.u.dp.mk[st][lane] = (uint16_t)m16;
+          {  // integer literal edge from the tables of the generation published right now; the DP warp
+             // uses it only if the stage's tag still equals its own generation when it gets there
+            const uint32_t gn = *(volatile uint32_t*)&dyn.gen;
+            const uint32_t li = dyn.liti[gn & 1u][pf_byte];
+            dyn.gli[st * 32 + lane] = li;
+            if (st == 0 && lane < 2) dyn.gli[128 + lane] = li;
+            if (lane == 0) dyn.tag[st] = gn;
+          }
           const uint32_t fw = __ballot_sync(0xffffffffu, (m16 & kShortcutFlag) != 0 || (m16 & 0x7fffu) > 34u);
           if (lane == 0) s.u.dp.flag[st] = fw;
           { const uint32_t p = (g + 1) * 32 + lane; pf_m16 = 0; pf_byte = 0; if (p < nb) { pf_m16 = mlen[p]; pf_byte = in[p]; } }
@@ -469,7 +528,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
           const uint32_t st = fl & 3u;
           mbar_wait(&s.empty[st], (fl >> 2) & 1u);
           const uint32_t p = (fl - seq_base) * 32 + lane;
-          if (p < nb) la[p] = (uint16_t)decode_len(s.u.dp.lac[st][lane], p);
+          if (p < nb) la[p] = (uint16_t)decode_code(s.u.dp.lac[st][lane], p, s.u.dp.ring);
           __syncwarp();
           fl++;
         }
@@ -583,7 +642,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
       }
       skip_noop = mincost <= mn;
       margin_dn = 258.0 * ml + 1.0;
-      margin_up = 32.0 * ml + mx + 1.0;
+      margin_up = 36.0 * ml + mx + 1.0;
     }
     const double cost258 = (double)(0 + 0) + s.lencost[258] + s.dcost[0];  // costmodel(258, 1)
     ZB_TICK(0);
@@ -602,7 +661,8 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
     const double kInfD = (double)(float)1e30;  // ZOPFLI_LARGE_FLOAT stored to float, squeeze.c:243
     for (int t = lane; t < 512; t += 32) { s.u.dp.ring[t].c = kInfD; s.u.dp.ring[t].code = 0; }
     if (lane < 4) { s.u.dp.xch[lane].c = kInfD; s.u.dp.xch[lane].code = 0; }
-    if (lane == 0) s.go = 1;
+    i_gen++;  // new cost model: stages tagged with an older generation (or this one, which has no tables) are fp64-only
+    if (lane == 0) { s.go = 1; *(volatile uint32_t*)&dyn.gen = i_gen; }
     __syncwarp();
     cta_sync64();  // (A) start the feeder
     {
@@ -689,8 +749,69 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         }                                                                                                   \
       }
 
+      // ---- integer window: one step = two VIADDMNMX (literal edge against pending(j+1); this lane's length
+      // edge against its pending target) and one LOP3 (strip the tiebreak bits) on the chain ----
+#define ZB_DPI_STEP(U)                                                                                      \
+      {                                                                                                     \
+        const uint32_t tv2_ = lds_u32(ti_s + ds2 * 256 - (((U) + 2) * 4));                                  \
+        const uint32_t ds3_ = lds_u8(dsx_s + (((U) + 3) * 32));                                             \
+        const uint32_t llb2_ = lds_u32(gli_s + (((U) + 2) * 4));                                            \
+        const uint32_t en_ = lds_u32(xchi_r + ((((U) + 3) & 3) * 4));   /* pending(j+2), made at step j-1 */ \
+        sts_u16_if(lac_s + (U) * 2, lfin_prev, is_l0);                                                      \
+        const uint32_t x_ = __viaddmin_u32(CJ, llbI, e2I);   /* literal edge against pending(j+1) */        \
+        lfin_prev = (x_ & 127u) | kCodeInt;                                                                 \
+        wI = __viaddmin_u32(CJ, tvI, wI);                   /* this lane's length edge */                  \
+        const bool mine_ = lane_rot == (uint32_t)(U);   /* this lane's target is j+3: complete now */       \
+        sts_u32_if(xchi_r + (((U) & 3) * 4), wI, mine_);                                                    \
+        wI = mine_ ? kIntInf : wI;                                                                          \
+        e2I = en_; CJ = x_ & ~127u;                                                                         \
+        tvI = tv1I; tv1I = tv2_; ds2 = ds3_; llbI = llb1I; llb1I = llb2_;                                   \
+      }
+#define ZB_DPI_GROUP(ST)                                                                                    \
+      {                                                                                                     \
+        uint32_t ti_s = ti_l, dsx_s = dsx_r + (ST) * 1024, gli_s = gli_r + (ST) * 128, lac_s = lac_r + (ST) * 64; \
+        uint32_t lane_rot = (lane - 3u) & 31u;                                                              \
+        _Pragma("unroll 1")                                                                                 \
+        for (int sb_ = 0; sb_ < 2; sb_++) {                                                                 \
+          ZB_DPI_STEP(0) ZB_DPI_STEP(1) ZB_DPI_STEP(2) ZB_DPI_STEP(3) ZB_DPI_STEP(4) ZB_DPI_STEP(5)         \
+          ZB_DPI_STEP(6) ZB_DPI_STEP(7) ZB_DPI_STEP(8) ZB_DPI_STEP(9) ZB_DPI_STEP(10) ZB_DPI_STEP(11)       \
+          ZB_DPI_STEP(12) ZB_DPI_STEP(13) ZB_DPI_STEP(14) ZB_DPI_STEP(15)                                   \
+          ti_s -= 64; dsx_s += 512; gli_s += 64; lac_s += 32;                                               \
+          lane_rot = (lane_rot - 16u) & 31u;                                                                \
+        }                                                                                                   \
+      }
+      uint32_t ti_l = smem_u32(&dyn.ti[0]) + (((lane - 3u) & 31u) + 33u) * 4u;   // this lane's column, as t0_l
+      uint32_t gli_r = smem_u32(&dyn.gli[0]), xchi_r = smem_u32(&dyn.xchi[0]), tag_r = smem_u32(&dyn.tag[0]);
+      asm volatile("" : "+r"(ti_l), "+r"(gli_r), "+r"(xchi_r), "+r"(tag_r));
+      bool imode = false, i_ok = false;   // window currently held as integers; tables of i_lowb usable
+      long long i_lowb = -1;              // exponent bits of the binade the tables were (or could not be) built for
+      uint32_t i_base = 0, i_hi = 0;      // float bits of 2^e; upper end of the interval of CJ the mode is valid in
+      double i_lo_d = 1.0, i_hi_d = 0.0, i_top = 0.0;
+      uint32_t wI = kIntInf, e2I = kIntInf, CJ = 0, tvI = 0, tv1I = 0, llbI = 0, llb1I = 0;
+      // fp64 value + length code <-> packed word (entries carried over lose their `up` bit, which only matters
+      // against EARLIER sources: 64 + o loses to every later source that rounds up and beats every later one that does not)
+      auto d2i = [&](double c, uint32_t code, uint32_t target) -> uint32_t {
+        if (!(c < i_top)) return kIntInf;   // beyond the binade: cannot be the minimum of a target finished in this group
+        const uint32_t o = (code & kCodeLong) ? 0u : 35u - decode_len(code, target);
+        return ((__float_as_uint(__double2float_rn(c)) - i_base) << 7) | (64u + o);
+      };
+      auto i2d = [&](uint32_t pw, uint32_t target, double& c, uint32_t& code) {
+        if (pw >= kIntNoEdge) { c = kInfD; code = 0; return; }
+        c = (double)__uint_as_float((pw >> 7) + i_base);
+        const uint32_t tb = pw & 127u, o = tb < 64u ? 63u - tb : tb - 64u;
+        code = o == 0u ? s.u.dp.ring[(target - 3u) & 511u].code : ((target - (35u - o)) & 31u) + 3u;
+      };
+
       uint32_t flag_pref = lds_u32(flag_r + (seq_base & 3u) * 4);  // flags of a group are fetched one group ahead
-      for (uint32_t g = 0; g < ngroups; g++) {
+      long long tg = clock64();
+      uint32_t nslow = 0;
+#ifdef ZB_DP_KINDS   /* developer build: DP cycles by kind of group (tools/one_block.py prints them) */
+#define ZB_KIND_TICK(K) if (lane == 0) { const long long t_ = clock64(); s.dpc[K] += (unsigned long long)(t_ - tg); s.dpn[K]++; tg = t_; }
+#else
+#define ZB_KIND_TICK(K)
+#endif
+      for (uint32_t g = 0; g < ngroups;) {
+        uint32_t kind = 4;
         const uint32_t j0 = g * 32, q = seq_base + g, st = q & 3u, stn = (q + 1) & 3u;
         if (g + 1 < ngroups) mbar_wait_a(full_r + stn * 8, ((q + 1) >> 2) & 1u);  // the operand pipeline runs into the next group
         const uint32_t flag_cur = flag_pref;
@@ -699,7 +820,112 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         const uint32_t lac_c = lac_r + st * 64;
         const uint32_t ring_c = ring_r + ((j0 + 32) & 511u) * 16;  // slot of target j0 + 35
         const bool fast = skip_noop && flag_cur == 0 && skip_left == 0 && !just_finished && j0 + 32 <= nb;
-        if (fast) {
+        const uint32_t gli_c = gli_r + st * 128;
+        // ---- integer window: stay / enter / leave ----
+        bool want_int = false;
+        if (fast && int_on && j0 + 35 > dirty_until && j0 >= guard_until) {
+          if (imode) {
+            want_int = CJ < i_hi;   // words only grow by positive edges: nothing falls below the binade once inside
+          } else {
+            const long long lowb = __double_as_longlong(cj) & 0x7ff0000000000000LL;
+            if (lowb != i_lowb) {  // a binade not looked at yet: build its tables (k1, up per edge), or rule it out
+              i_lowb = lowb; i_ok = false;
+              const double B = __longlong_as_double(lowb);
+              i_top = B + B; i_lo_d = B; i_hi_d = i_top - margin_up;
+              if (lowb > 0 && i_lo_d < i_hi_d) {
+                const uint32_t base = __float_as_uint(__double2float_rn(B));
+                const double half_ulp = __longlong_as_double(lowb - (24LL << 52));
+                bool tie = false;
+                i_gen++;
+                uint32_t* lt = dyn.liti[i_gen & 1u];
+                for (int i = lane; i < 31 * 64; i += 32) {
+                  const uint32_t o = 35u - (3u + (((uint32_t)i + 31u) & 31u));   // order of this length among a target's sources
+                  uint32_t E = kIntNoEdge | (64u + o);
+                  if (i < 30 * 64) {
+                    const double s0 = B + s.t0[i];          // the edge cost on the binade's double grid
+                    const float f = __double2float_rn(s0);
+                    const double df = (double)f;
+                    tie |= fabs(df - s0) == half_ulp;
+                    E = ((__float_as_uint(f) - base) << 7) | (df > s0 ? 63u - o : 64u + o);
+                  }
+                  dyn.ti[i] = E;
+                }
+                for (int i = lane; i < 256; i += 32) {
+                  const double s0 = B + s.llcost[i];
+                  const float f = __double2float_rn(s0);
+                  const double df = (double)f;
+                  tie |= fabs(df - s0) == half_ulp;
+                  lt[i] = ((__float_as_uint(f) - base) << 7) | (df > s0 ? 63u - 33u : 64u + 33u);
+                }
+                tie = __any_sync(0xffffffffu, tie);
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) *(volatile uint32_t*)&dyn.gen = i_gen;
+                i_base = base; i_ok = !tie;
+                i_hi = (__float_as_uint(__double2float_rd(i_hi_d)) - base) << 7;
+              }
+            }
+            want_int = i_ok && cj >= i_lo_d && cj < i_hi_d;
+          }
+          if (want_int) {  // the staged literal edges must come from the current tables (this stage and the one the pipeline runs into)
+            const uint32_t tag0 = lds_u32(tag_r + st * 4), tag1 = g + 1 < ngroups ? lds_u32(tag_r + stn * 4) : i_gen;
+            want_int = tag0 == i_gen && tag1 == i_gen;
+          }
+          if (want_int && !imode) {  // every pending value the window holds must lie in the binade (or be infinite) to be carried over
+            double xc; uint32_t xl;
+            ZB_XCH_LOAD(xch_r + ((j0 + 3u) & 3u) * 16, xc, xl);
+            (void)xl;
+            want_int = __all_sync(0xffffffffu, !(w < i_lo_d) && !(e2c < i_lo_d) && !(xc < i_lo_d));
+          }
+        }
+        if (imode != want_int) {
+          const uint32_t t_l = j0 + 3u + ((lane - 3u) & 31u), xs = (j0 + 3u) & 3u;   // this lane's target; slot of pending(j0+2)
+          if (want_int) {
+            wI = d2i(w, wl, t_l);
+            e2I = d2i(e2c, e2l, j0 + 1u);
+            { double xc; uint32_t xl; ZB_XCH_LOAD(xch_r + xs * 16, xc, xl); const uint32_t xp = d2i(xc, xl, j0 + 2u); if (is_l0) dyn.xchi[xs] = xp; }
+            CJ = (__float_as_uint(__double2float_rn(cj)) - i_base) << 7;
+            __syncwarp();
+            tvI = lds_u32(ti_l + lds_u8(dsx_c) * 256 - 32 * 4);
+            tv1I = lds_u32(ti_l + lds_u8(dsx_c + 32) * 256 - 33 * 4);
+            llbI = lds_u32(gli_c);
+            llb1I = lds_u32(gli_c + 4);
+          } else {
+            i2d(wI, t_l, w, wl);
+            i2d(e2I, j0 + 1u, e2c, e2l);
+            { double xc; uint32_t xl; i2d(lds_u32(xchi_r + xs * 4), j0 + 2u, xc, xl); ZB_XCH_STORE(xch_r + xs * 16, xc, xl, is_l0); }
+            cj = (double)__uint_as_float((CJ >> 7) + i_base);
+            __syncwarp();
+            tv = lds_f64(t0_l + lds_u8(dsx_c) * 512 - 32 * 8);
+            tv1 = lds_f64(t0_l + lds_u8(dsx_c + 32) * 512 - 33 * 8);
+            llb = lds_f64(gl_c);
+            llb1 = lds_f64(gl_c + 8);
+          }
+          imode = want_int;
+        }
+        if (imode) {
+          // Integer groups run back to back in a loop of their own: the conditions that can change from one
+          // group to the next (flags of the next group, the interval, the block end, the tag of the stage the
+          // pipeline runs into) cost a dozen instructions; everything else (ring clean, no shortcut zone nearby)
+          // cannot change while no long edge is pushed.  Anything else goes back to the top of the outer loop.
+          uint32_t stc = st;
+          for (;;) {
+            ZB_DPI_GROUP(stc)
+            igroups++;
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(empty_r + stc * 8);
+            ZB_KIND_TICK(0)
+            g++;
+            if (g + 1 >= ngroups) break;
+            const uint32_t qn = seq_base + g + 1u, st2 = qn & 3u;
+            mbar_wait_a(full_r + st2 * 8, (qn >> 2) & 1u);
+            const uint32_t fl2 = lds_u32(flag_r + st2 * 4), tg2 = lds_u32(tag_r + st2 * 4);
+            if (flag_pref != 0 || !(CJ < i_hi) || (g + 1u) * 32u > nb || tg2 != i_gen) break;
+            flag_pref = fl2;
+            stc = (seq_base + g) & 3u;
+          }
+          continue;
+        } else if (fast) {
           // "magic" rounding: while every cost of the group provably stays inside one binade
           // [2^k, 2^(k+1)), round-to-float is (x + C) - C with C = 1.5 * 2^(k+29) (the double grid at
           // C is the float grid of the binade, ties to even alike) -- two DADDs instead of five
@@ -718,9 +944,9 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
             }
             magic = cj >= mg_lo && cj < mg_hi;
           }
-          if (magic) ZB_DP_FAST_GROUP(false, true)
-          else if (j0 + 35 > dirty_until) ZB_DP_FAST_GROUP(false, false)
-          else ZB_DP_FAST_GROUP(true, false)
+          if (magic) { kind = 1; ZB_DP_FAST_GROUP(false, true) }
+          else if (j0 + 35 > dirty_until) { kind = 2; ZB_DP_FAST_GROUP(false, false) }
+          else { kind = 3; ZB_DP_FAST_GROUP(true, false) }
         } else {
           // ---- general group, in half-blocks of four steps: a half without a flagged position still
           // runs the straight-line code (ring-joining variant); only the others check per step.  (Halves
@@ -737,6 +963,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
             continue;
           }
           const uint32_t jend = jb + 4 < nb ? jb + 4 : nb;
+          nslow += jend - jb;
           for (uint32_t j = jb; j < jend; j++) {
             const uint32_t jl = j & 31u;
             const double tv2 = lds_f64(t0_l + ds2 * 512 - (jl + 2) * 8);
@@ -831,13 +1058,20 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_a(empty_r + st * 8);  // the feeder may write back lac[st] and refill the stage
+        ZB_KIND_TICK(kind)
+        (void)kind;
+        g++;
       }
+      if (lane == 0) s.dpn[5] += nslow;
+#undef ZB_KIND_TICK
+#undef ZB_DPI_GROUP
+#undef ZB_DPI_STEP
 #undef ZB_DP_FAST_GROUP
 #undef ZB_DP_FAST_8
 #undef ZB_DP_FAST_4A
 #undef ZB_DP_FAST_4B
 #undef ZB_DP_FAST_STEP
-      if (lane == 0) la[nb] = (uint16_t)decode_len(lfin_prev, nb);
+      if (lane == 0) la[nb] = (uint16_t)decode_code(lfin_prev, nb, s.u.dp.ring);
       seq_base += ngroups;
     }
     cta_sync64();  // (B) the feeder has written length_array[0 .. nb)
@@ -1076,6 +1310,9 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
     js->best_cost = bestcost;
     js->flags = flags;
     js->iters_done = (uint32_t)it;
+    js->int_groups = igroups;
+    for (int i = 0; i < 5; i++) js->dpc[i] = s.dpc[i];
+    for (int i = 0; i < 6; i++) js->dpn[i] = s.dpn[i];
   }
 }
 

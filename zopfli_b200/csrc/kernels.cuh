@@ -60,8 +60,12 @@ struct JobState {   // per segment, written by k_greedy / k_iterate
   uint32_t out_off;      // offset of the packed result (k_pack)
   uint32_t flags;        // bit0: log table overflow (needs host assistance)
   uint32_t iters_done;
+  uint32_t int_groups;   // groups of 32 DP steps that ran in the integer window (all iterations)
+  uint32_t pad_;
   uint64_t best_cost;
   uint64_t cyc[6];       // SM cycles spent in: model, DP, trace, follow, block cost, statistics
+  uint64_t dpc[5];       // DP cycles by kind of group: integer window, fp64 fast (magic / plain / ring-joining), general
+  uint32_t dpn[6];       // groups of each kind; [5] = positions that went through the per-step general loop
 };
 
 struct Batch {
@@ -105,6 +109,7 @@ struct Batch {
   // verbose: cost of every iteration of every block (squeeze.c:492-495), [nsegs][iter_stride]; null otherwise
   uint64_t* iter_cost;
   uint32_t iter_stride;
+  uint32_t dp_flags;   // bit 0: integer window of the forward DP enabled (ZOPFLI_B200_INTDP, default on)
 };
 
 
