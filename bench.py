@@ -382,7 +382,9 @@ def run_product(args, rank, world):
                              "chain_bound_ms": sum(cyc) / sm_mhz / 1e3,
                              "chain": {"max_block_positions": maxpos, "iterations": NUMITER,
                                        "dp_cycles_per_step": cyc[1] / max(1, maxpos * NUMITER),
-                                       "all_cycles_per_step": sum(cyc) / max(1, maxpos * NUMITER)},
+                                       "all_cycles_per_step": sum(cyc) / max(1, maxpos * NUMITER),
+                                       # share of all DP steps of the step that ran in the integer window (iterate.cuh)
+                                       "integer_window_share": st_res.get("int_steps", 0) / max(1, st_res["iterate_steps"])},
                              "note": "DP dependency chain, not bandwidth, bounds this kernel (SURVEY 7.2 #5): "
                                      "chain_bound_ms = cycles of the critical block / SM clock"},
                 "cpu_baseline": cpu,

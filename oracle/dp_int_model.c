@@ -39,6 +39,7 @@ typedef struct {
   uint32_t base;           /* float bits of 2^e */
   uint32_t te[31][35];     /* [dsym][len]; row 30: no edge */
   uint32_t lit[256];
+  uint32_t tl[29][30];     /* long edges: (k1 << 1) | up per (length symbol - 257, distance symbol) */
 } BinadeTab;
 
 /* k1 / up / tie of one edge cost c in binade e; order o */
@@ -65,6 +66,13 @@ static void build_tab(BinadeTab* bt, int e, const ZoStats* st) {
     }
   for (len = 3; len <= 34; len++) bt->te[30][len] = NOEDGE | (uint32_t)(64 + 35 - len);
   for (i = 0; i < 256; i++) bt->lit[i] = pack_edge(st->ll_symbols[i], e, 33, &bt->tie);
+  for (i = 0; i < 29; i++)
+    for (ds = 0; ds < 30; ds++) {
+      /* the cost of a length depends on it only through its symbol (extra bits are a function of the symbol) */
+      const double c = length_symbol_extra_bits(257 + i) + dist_symbol_extra_bits(ds) + st->ll_symbols[257 + i] + st->d_symbols[ds];
+      const uint32_t w = pack_edge(c, e, 0, &bt->tie); /* o = 0: tiebreak 63 (up) or 64 */
+      bt->tl[i][ds] = ((w >> 7) << 1) | ((w & 127u) == 63u ? 1u : 0u);
+    }
   g_ids.builds++;
 }
 
@@ -107,7 +115,7 @@ static void int_model(const ZoSegment* seg, const ZoTable* t, const ZoStats* st,
     const size_t j0 = g * 32, jend = j0 + 32 < nb ? j0 + 32 : nb;
     int flagged = 0, want_int = 0, ring_dirty;
     for (j = j0; j < jend; j++)
-      if (t->length[j] > 34 || t->skipped[j] || (j > 0 && t->skipped[j - 1])) flagged = 1;
+      if (t->skipped[j] || (j > 0 && t->skipped[j - 1])) flagged = 1;   /* long-run shortcut: fp64 general path only */
     ring_dirty = j0 + 35 <= dirty_until;
     if (skip_noop && !flagged && j0 + 32 <= nb && j0 >= guard_until) {
       const double cj = costs[j0];
@@ -128,11 +136,16 @@ static void int_model(const ZoSegment* seg, const ZoTable* t, const ZoStats* st,
         }
         /* no lower margin: words only grow by positive edges, so it is enough that every pending value
          * carried into the window lies in the binade (checked below when the mode is entered) */
-        if (!bt.tie && !ring_dirty && ldexp(1.0, e) > margin_up && cj < ldexp(1.0, e + 1) - margin_up)
+        if (!bt.tie && ldexp(1.0, e) > margin_up && cj < ldexp(1.0, e + 1) - margin_up)
           want_int = 1;
-        if (want_int && !imode)
+        if (want_int && !imode) {
           for (k = j0 + 1; k <= j0 + 34; k++)
             if (costs[k] < (float)ldexp(1.0, e)) want_int = 0;
+          /* every finite ring entry (targets beyond the window) must lie in the binade: it joins as an integer */
+          if (ring_dirty)
+            for (k = j0 + 35; k <= dirty_until; k++)
+              if (costs[k] != (float)ZO_LARGE && !(costs[k] >= (float)ldexp(1.0, e) && costs[k] < (float)ldexp(1.0, e + 1))) want_int = 0;
+        }
       }
     }
     if (want_int) {
@@ -153,18 +166,6 @@ static void int_model(const ZoSegment* seg, const ZoTable* t, const ZoStats* st,
       for (j = j0; j < j0 + 32; j++) {
         const size_t tj = j + 35;
         uint32_t X;
-        /* the lane that just handed over target j+3 takes on target j+35: the ring entry joins */
-        if (ring_dirty) {
-          const float v = costs[tj];
-          if (v == (float)ZO_LARGE) P[tj] = INFP;
-          else {
-            if (!(v >= lo && v < hi)) { g_ids.mismatches++; fprintf(stderr, "int model: ring value outside the binade at %zu\n", tj); }
-            P[tj] = ((fbits(v) - bt.base) << 7) | 64u;
-          }
-        } else {
-          if (costs[tj] != (float)ZO_LARGE) { g_ids.mismatches++; fprintf(stderr, "int model: clean ring expected at %zu\n", tj); }
-          P[tj] = INFP;
-        }
         /* literal */
         X = CJ + bt.lit[in[seg->instart + j]];
         if (P[j + 1] < X) X = P[j + 1];
@@ -182,6 +183,35 @@ static void int_model(const ZoSegment* seg, const ZoTable* t, const ZoStats* st,
             }
             if (cand < P[j + k]) P[j + k] = cand;
           }
+        }
+        /* lengths 35..: straight into the ring (absolute float bits), first strict improvement wins */
+        {
+          const unsigned leng = t->length[j];
+          const size_t kend = leng < nb - j ? leng : nb - j;
+          const uint32_t cjb = bt.base + (CJ >> 7);
+          uint32_t r = t->runoff[j];
+          for (k = 35; k <= kend; k++) {
+            uint32_t e2, rl;
+            while ((t->runs[r] >> 16) < k) r++;
+            e2 = bt.tl[length_symbol((int)k) - 257][dist_symbol((int)(t->runs[r] & 0xffff))];
+            rl = cjb + (e2 >> 1);
+            if (rl >= fbits((float)hi)) { g_ids.mismatches++; fprintf(stderr, "int model: long edge beyond the binade at %zu\n", j); }
+            if (rl < fbits(costs[j + k]) || (rl == fbits(costs[j + k]) && (e2 & 1u))) { costs[j + k] = bitsf(rl); la[j + k] = (uint16_t)k; }
+          }
+          if (kend > 34 && j + kend > dirty_until) dirty_until = j + kend;
+        }
+        /* the lane that just handed over target j+3 takes on target j+35: the ring entry joins
+         * (after this step's own length-35 edge has been pushed) */
+        if (tj <= dirty_until) {
+          const float v = costs[tj];
+          if (v == (float)ZO_LARGE) P[tj] = INFP;
+          else {
+            if (!(v >= lo && v < hi)) { g_ids.mismatches++; fprintf(stderr, "int model: ring value outside the binade at %zu\n", tj); }
+            P[tj] = ((fbits(v) - bt.base) << 7) | 64u;
+          }
+        } else {
+          if (costs[tj] != (float)ZO_LARGE) { g_ids.mismatches++; fprintf(stderr, "int model: clean ring expected at %zu\n", tj); }
+          P[tj] = INFP;
         }
         costs[j + 1] = bitsf((X >> 7) + bt.base);
         la[j + 1] = decode_tb(X, la[j + 1]);

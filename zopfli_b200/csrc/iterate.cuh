@@ -22,7 +22,10 @@
 
 namespace zb {
 
-struct RingEnt { double c; uint32_t code; uint32_t pad; };  // cost (float-representable) + length code of the best edge
+struct XchEnt { double c; uint32_t code; uint32_t pad; };   // hand-off slot of the fp64 window: cost (float-representable) + length code
+struct RingEnt { uint32_t fb; uint32_t code; };             // pending cost of a far target as FLOAT BITS (what the reference's costs[] holds)
+                                                             // + length code of the best edge; the same for the fp64 and the integer paths
+constexpr uint32_t kInfBits = 0x7149f2cau;                  // (float)1e30, ZOPFLI_LARGE_FLOAT squeeze.c:243
 // length codes (decoded by decode_len): the window records only WHICH step produced the best edge
 constexpr uint32_t kCodeLit = 0x800u;    // literal
 constexpr uint32_t kCodeLong = 0x400u;   // | length, for edges longer than 34 (shared-memory ring)
@@ -55,6 +58,7 @@ struct IterDyn {                       // dynamic shared memory of k_iterate (en
   uint32_t liti[2][256];               // integer literal edges, double-buffered by generation parity (DP warp -> feeder)
   uint32_t gli[4 * 32 + 4];            // literal edge of each staged position; [128..129] mirror [0..1]   (feeder warp)
   uint32_t tag[4];                     // generation of liti a stage was filled from                        (feeder warp)
+  uint32_t tl[29 * 32];                // long edges (length >= 35): (k1 << 1 | up) per (length symbol - 257, distance symbol)
   uint32_t xchi[4];                    // hand-off slots of the integer window
   uint32_t gen;                        // published generation of liti
 };
@@ -67,7 +71,8 @@ struct DpStage {                       // forward-DP working set; 4 stages of 32
   uint16_t mk[4][32];                  // mlen16 of each position                             (feeder warp)
   uint16_t lac[4][32];                 // length codes of length_array[32g + l]              (DP warp -> feeder)
   uint32_t flag[4];                    // ballot: position needs the general path            (feeder warp)
-  RingEnt xch[4];                      // pending(j+3) handed from its owner lane to all lanes: written at step j,
+  uint32_t flagS[4];                   // ballot: long-run shortcut candidate (fp64 general path only)   (feeder warp)
+  XchEnt xch[4];                       // pending(j+3) handed from its owner lane to all lanes: written at step j,
                                        // loaded at step j+1, used at step j+2.  Shared memory rather than shuffles
                                        // because the order of memory operations is the one thing the assembler keeps:
                                        // a shuffle is sunk to just before its use and its latency lands on the chain.
@@ -198,6 +203,14 @@ __device__ __forceinline__ void lds_ring(uint32_t a, double& c, uint32_t& code) 
   asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "r"(a) : "memory");
   c = __longlong_as_double((long long)x);
   code = (uint32_t)y;
+}
+// ring entry {float bits, code}
+__device__ __forceinline__ void lds_ring8(uint32_t a, uint32_t& fb, uint32_t& code) {
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(fb), "=r"(code) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts_ring8_if(uint32_t a, uint32_t fb, uint32_t code, bool p) {
+  asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q st.shared.v2.u32 [%0], {%1, %2}; }" ::"r"(a), "r"(fb), "r"(code), "r"((uint32_t)p)
+               : "memory");
 }
 __device__ __forceinline__ double warp_min_first(double v, int& idx) {
   // minimum with the smallest index among equals (sequential strict-< scan order)
@@ -445,7 +458,7 @@ __device__ __forceinline__ uint32_t first_dist_of_symbol(int sd) {  // squeeze.c
 // match length, general-path flags) and writes the finished length_array entries back to global
 // memory, three groups of 32 positions ahead of / behind the DP warp (full[] / empty[] mbarriers).
 // Outside the DP phase it is parked at a named barrier.
-__global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restrict__ order) {
+__global__ void __launch_bounds__(64, 4) k_iterate(Batch b, const uint32_t* __restrict__ order) {
   __shared__ IterSmem s;
   extern __shared__ __align__(16) unsigned char zb_iter_dyn[];
   IterDyn& dyn = *reinterpret_cast<IterDyn*>(zb_iter_dyn);
@@ -510,7 +523,8 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
             if (lane == 0) dyn.tag[st] = gn;
           }
           const uint32_t fw = __ballot_sync(0xffffffffu, (m16 & kShortcutFlag) != 0 || (m16 & 0x7fffu) > 34u);
-          if (lane == 0) s.u.dp.flag[st] = fw;
+          const uint32_t fs = __ballot_sync(0xffffffffu, (m16 & kShortcutFlag) != 0);
+          if (lane == 0) { s.u.dp.flag[st] = fw; s.u.dp.flagS[st] = fs; }
           { const uint32_t p = (g + 1) * 32 + lane; pf_m16 = 0; pf_byte = 0; if (p < nb) { pf_m16 = mlen[p]; pf_byte = in[p]; } }
           __syncwarp();
           if (lane == 0) {
@@ -659,7 +673,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
     // is source order, as in the reference, so ties resolve identically.  The window keeps a
     // length CODE (which step produced the edge), decoded when length_array is written.
     const double kInfD = (double)(float)1e30;  // ZOPFLI_LARGE_FLOAT stored to float, squeeze.c:243
-    for (int t = lane; t < 512; t += 32) { s.u.dp.ring[t].c = kInfD; s.u.dp.ring[t].code = 0; }
+    for (int t = lane; t < 512; t += 32) { s.u.dp.ring[t].fb = kInfBits; s.u.dp.ring[t].code = 0; }
     if (lane < 4) { s.u.dp.xch[lane].c = kInfD; s.u.dp.xch[lane].code = 0; }
     i_gen++;  // new cost model: stages tagged with an older generation (or this one, which has no tables) are fp64-only
     if (lane == 0) { s.go = 1; *(volatile uint32_t*)&dyn.gen = i_gen; }
@@ -712,7 +726,8 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         double en_c_; uint32_t en_l_;                                                                       \
         ZB_XCH_LOAD(xch_r + ((((U) + 3) & 3) * 16), en_c_, en_l_);   /* pending(j+2), made at step j-1 */    \
         double inc_ = kInfD; uint32_t inl_ = 0;                                                             \
-        if (RING) { lds_ring(ring_s + (U) * 16, inc_, inl_); sts_f64_if(ring_s + (U) * 16, kInfD, is_l0); } \
+        if (RING) { uint32_t fb_; lds_ring8(ring_s + (U) * 8, fb_, inl_); inc_ = (double)__uint_as_float(fb_);    \
+                    sts_u32_if(ring_s + (U) * 8, kInfBits, is_l0); }                                         \
         sts_u16_if(lac_s + (U) * 2, lfin_prev, is_l0);                                                      \
         const double lit_ = llb + cj;                                                                       \
         double rl_ = (MAGIC) ? (lit_ + Cm) - Cm : round_to_f32(lit_);   /* unconditional: runs beside the compare */ \
@@ -744,45 +759,56 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         _Pragma("unroll 1")                                                                                 \
         for (int sb_ = 0; sb_ < 4; sb_++) {                                                                 \
           ZB_DP_FAST_8(R, M)                                                                                \
-          t0_s -= 64; dsx_s += 256; gl_s += 64; lac_s += 16; ring_s += 128;                                 \
+          t0_s -= 64; dsx_s += 256; gl_s += 64; lac_s += 16; ring_s += 64;                                  \
           lane_rot = (lane_rot - 8u) & 31u;                                                                 \
         }                                                                                                   \
       }
 
       // ---- integer window: one step = two VIADDMNMX (literal edge against pending(j+1); this lane's length
       // edge against its pending target) and one LOP3 (strip the tiebreak bits) on the chain ----
-#define ZB_DPI_STEP(U)                                                                                      \
+#define ZB_DPI_STEP(U, RING)                                                                                \
       {                                                                                                     \
         const uint32_t tv2_ = lds_u32(ti_s + ds2 * 256 - (((U) + 2) * 4));                                  \
         const uint32_t ds3_ = lds_u8(dsx_s + (((U) + 3) * 32));                                             \
         const uint32_t llb2_ = lds_u32(gli_s + (((U) + 2) * 4));                                            \
         const uint32_t en_ = lds_u32(xchi_r + ((((U) + 3) & 3) * 4));   /* pending(j+2), made at step j-1 */ \
+        uint32_t inc_ = kIntInf;                                                                            \
+        if (RING) {   /* the ring entry of target j+35 joins the window (float bits -> packed word, order 0) */ \
+          uint32_t fb_, cd_;                                                                                \
+          lds_ring8(ring_s + (U) * 8, fb_, cd_); (void)cd_;                                                 \
+          inc_ = fb_ == kInfBits ? kIntInf : (((fb_ - i_base) << 7) | 64u);                                 \
+          sts_u32_if(ring_s + (U) * 8, kInfBits, is_l0);                                                    \
+        }                                                                                                   \
         sts_u16_if(lac_s + (U) * 2, lfin_prev, is_l0);                                                      \
         const uint32_t x_ = __viaddmin_u32(CJ, llbI, e2I);   /* literal edge against pending(j+1) */        \
         lfin_prev = (x_ & 127u) | kCodeInt;                                                                 \
         wI = __viaddmin_u32(CJ, tvI, wI);                   /* this lane's length edge */                  \
         const bool mine_ = lane_rot == (uint32_t)(U);   /* this lane's target is j+3: complete now */       \
         sts_u32_if(xchi_r + (((U) & 3) * 4), wI, mine_);                                                    \
-        wI = mine_ ? kIntInf : wI;                                                                          \
+        wI = mine_ ? inc_ : wI;                                                                             \
         e2I = en_; CJ = x_ & ~127u;                                                                         \
         tvI = tv1I; tv1I = tv2_; ds2 = ds3_; llbI = llb1I; llb1I = llb2_;                                   \
       }
+#define ZB_DPI_4A(R) ZB_DPI_STEP(0, R) ZB_DPI_STEP(1, R) ZB_DPI_STEP(2, R) ZB_DPI_STEP(3, R)
+#define ZB_DPI_4B(R) ZB_DPI_STEP(4, R) ZB_DPI_STEP(5, R) ZB_DPI_STEP(6, R) ZB_DPI_STEP(7, R)
 #define ZB_DPI_GROUP(ST)                                                                                    \
       {                                                                                                     \
         uint32_t ti_s = ti_l, dsx_s = dsx_r + (ST) * 1024, gli_s = gli_r + (ST) * 128, lac_s = lac_r + (ST) * 64; \
         uint32_t lane_rot = (lane - 3u) & 31u;                                                              \
+        const uint32_t ring_s = 0; (void)ring_s;                                                            \
         _Pragma("unroll 1")                                                                                 \
         for (int sb_ = 0; sb_ < 2; sb_++) {                                                                 \
-          ZB_DPI_STEP(0) ZB_DPI_STEP(1) ZB_DPI_STEP(2) ZB_DPI_STEP(3) ZB_DPI_STEP(4) ZB_DPI_STEP(5)         \
-          ZB_DPI_STEP(6) ZB_DPI_STEP(7) ZB_DPI_STEP(8) ZB_DPI_STEP(9) ZB_DPI_STEP(10) ZB_DPI_STEP(11)       \
-          ZB_DPI_STEP(12) ZB_DPI_STEP(13) ZB_DPI_STEP(14) ZB_DPI_STEP(15)                                   \
+          ZB_DPI_4A(false) ZB_DPI_4B(false)                                                                 \
+          ZB_DPI_STEP(8, false) ZB_DPI_STEP(9, false) ZB_DPI_STEP(10, false) ZB_DPI_STEP(11, false)         \
+          ZB_DPI_STEP(12, false) ZB_DPI_STEP(13, false) ZB_DPI_STEP(14, false) ZB_DPI_STEP(15, false)       \
           ti_s -= 64; dsx_s += 512; gli_s += 64; lac_s += 32;                                               \
           lane_rot = (lane_rot - 16u) & 31u;                                                                \
         }                                                                                                   \
       }
       uint32_t ti_l = smem_u32(&dyn.ti[0]) + (((lane - 3u) & 31u) + 33u) * 4u;   // this lane's column, as t0_l
       uint32_t gli_r = smem_u32(&dyn.gli[0]), xchi_r = smem_u32(&dyn.xchi[0]), tag_r = smem_u32(&dyn.tag[0]);
-      asm volatile("" : "+r"(ti_l), "+r"(gli_r), "+r"(xchi_r), "+r"(tag_r));
+      uint32_t tl_r = smem_u32(&dyn.tl[0]), flagS_r = smem_u32(&s.u.dp.flagS[0]);
+      asm volatile("" : "+r"(ti_l), "+r"(gli_r), "+r"(xchi_r), "+r"(tag_r), "+r"(tl_r), "+r"(flagS_r));
       bool imode = false, i_ok = false;   // window currently held as integers; tables of i_lowb usable
       long long i_lowb = -1;              // exponent bits of the binade the tables were (or could not be) built for
       uint32_t i_base = 0, i_hi = 0;      // float bits of 2^e; upper end of the interval of CJ the mode is valid in
@@ -818,12 +844,16 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
         if (g + 1 < ngroups) flag_pref = lds_u32(flag_r + stn * 4);
         const uint32_t dsx_c = dsx_r + st * 1024, gl_c = gl_r + st * 256;
         const uint32_t lac_c = lac_r + st * 64;
-        const uint32_t ring_c = ring_r + ((j0 + 32) & 511u) * 16;  // slot of target j0 + 35
+        const uint32_t ring_c = ring_r + ((j0 + 32) & 511u) * 8;   // slot of target j0 + 35
         const bool fast = skip_noop && flag_cur == 0 && skip_left == 0 && !just_finished && j0 + 32 <= nb;
         const uint32_t gli_c = gli_r + st * 128;
         // ---- integer window: stay / enter / leave ----
+        // The integer window takes every group without long-run shortcut activity: plain ones, and ones with
+        // matches longer than 34 / ring entries to join (long edges are priced from dyn.tl, straight into the ring).
         bool want_int = false;
-        if (fast && int_on && j0 + 35 > dirty_until && j0 >= guard_until) {
+        const bool calm = skip_noop && int_on && skip_left == 0 && !just_finished && j0 + 32 <= nb && j0 >= guard_until &&
+                          lds_u32(flagS_r + st * 4) == 0;
+        if (calm) {
           if (imode) {
             want_int = CJ < i_hi;   // words only grow by positive edges: nothing falls below the binade once inside
           } else {
@@ -857,6 +887,18 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
                   tie |= fabs(df - s0) == half_ulp;
                   lt[i] = ((__float_as_uint(f) - base) << 7) | (df > s0 ? 63u - 33u : 64u + 33u);
                 }
+                for (int i = lane; i < 29 * 32; i += 32) {   // the cost of a length depends on it only through its symbol
+                  const int ls = 257 + (i >> 5), ds = i & 31;
+                  uint32_t E = 0;
+                  if (ds < 30) {
+                    const double s0 = B + ((double)(length_symbol_extra_bits(ls) + dist_symbol_extra_bits(ds)) + s.llcost[ls] + s.dcost[ds]);
+                    const float f = __double2float_rn(s0);
+                    const double df = (double)f;
+                    tie |= fabs(df - s0) == half_ulp;
+                    E = ((__float_as_uint(f) - base) << 1) | (df > s0 ? 1u : 0u);
+                  }
+                  dyn.tl[i] = E;
+                }
                 tie = __any_sync(0xffffffffu, tie);
                 __syncwarp();
                 __threadfence_block();
@@ -876,6 +918,11 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
             ZB_XCH_LOAD(xch_r + ((j0 + 3u) & 3u) * 16, xc, xl);
             (void)xl;
             want_int = __all_sync(0xffffffffu, !(w < i_lo_d) && !(e2c < i_lo_d) && !(xc < i_lo_d));
+            if (want_int && j0 + 35 <= dirty_until) {  // so must every finite ring entry: it joins as an integer
+              bool okr = true;
+              for (int t = lane; t < 512; t += 32) { const uint32_t fb = s.u.dp.ring[t].fb; okr &= fb == kInfBits || (fb - i_base) < (1u << 23); }
+              want_int = __all_sync(0xffffffffu, okr);
+            }
           }
         }
         if (imode != want_int) {
@@ -903,7 +950,85 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
           }
           imode = want_int;
         }
-        if (imode) {
+        if (imode && (flag_cur != 0 || j0 + 35 <= dirty_until)) {
+          // ---- integer general group, in halves of four steps like the fp64 one: halves without a long match run
+          // the straight-line step (ring-joining variant), the others go step by step and push their long edges ----
+          for (uint32_t hb = 0; hb < 8; hb++) {
+            const uint32_t sb = hb >> 1, jb = j0 + hb * 4;
+            if (((flag_cur >> (hb * 4)) & 0xfu) == 0) {
+              uint32_t ti_s = ti_l - sb * 32, dsx_s = dsx_c + sb * 256, gli_s = gli_c + sb * 32, lac_s = lac_c + sb * 16;
+              uint32_t ring_s = ring_c + sb * 64, lane_rot = (lane - 3u - sb * 8u) & 31u;
+              if (hb & 1) { ZB_DPI_4B(true) } else { ZB_DPI_4A(true) }
+              continue;
+            }
+            nslow += 4;
+            for (uint32_t j = jb; j < jb + 4; j++) {
+              const uint32_t jl = j & 31u;
+              const uint32_t tv2_ = lds_u32(ti_l + ds2 * 256 - (jl + 2) * 4);
+              const uint32_t ds3_ = lds_u8(dsx_c + (jl + 3) * 32);
+              const uint32_t llb2_ = lds_u32(gli_c + (jl + 2) * 4);
+              const uint32_t en_ = lds_u32(xchi_r + ((j + 3) & 3) * 4);
+              sts_u16_if(lac_c + jl * 2, lfin_prev, is_l0);
+              const bool lng = ((flag_cur >> jl) & 1u) != 0;   // no shortcut candidates in this group: the flag means length > 34
+              const uint32_t x_ = __viaddmin_u32(CJ, llbI, e2I);
+              lfin_prev = (x_ & 127u) | kCodeInt;
+              wI = __viaddmin_u32(CJ, tvI, wI);
+              if (lng) {  // lengths 35..: first strict improvement wins, on float bits (squeeze.c:286-302)
+                const uint32_t ml = lds_u16(mk_r + st * 64 + jl * 2) & 0x7fffu;
+                const uint32_t room = nb - j;
+                const uint32_t kend = ml < room ? ml : room;
+                const uint4* st4 = (const uint4*)&s.u.dp.runs[st][jl * kRunSlots];
+                const uint4 ea = st4[0], eb = st4[1];
+                const bool ovf = (eb.w & kOverflowBit) != 0;
+                const uint32_t cjb = i_base + (CJ >> 7);
+                // distance symbol of length k: first run whose end reaches k (overflow arena beyond eight runs)
+                auto run_of = [&](uint32_t k) -> uint32_t {
+                  uint32_t e = eb.w;
+                  if (ovf) {
+                    e = 0;
+                    if (k > run_len(eb.z)) {
+                      uint32_t off = eb.w & ~kOverflowBit, cnt = b.ovf[off];
+                      for (uint32_t r = 0; r < cnt; r++) { uint32_t x = b.ovf[off + 1 + r]; if (run_len(x) >= k) { e = x; break; } }
+                    }
+                  }
+                  if (k <= run_len(eb.z)) e = eb.z;
+                  if (k <= run_len(eb.y)) e = eb.y;
+                  if (k <= run_len(eb.x)) e = eb.x;
+                  if (k <= run_len(ea.w)) e = ea.w;
+                  if (k <= run_len(ea.z)) e = ea.z;
+                  if (k <= run_len(ea.y)) e = ea.y;
+                  if (k <= run_len(ea.x)) e = ea.x;
+                  return e;
+                };
+                for (uint32_t k = 35 + lane; k <= kend; k += 32) {
+                  const uint32_t tga = ring_r + ((j + k - 3) & 511) * 8;
+                  const uint32_t pendb = lds_u32(tga);
+                  const uint32_t E = lds_u32(tl_r + (((uint32_t)length_symbol((int)k) - 257u) * 32u + run_dsym(run_of(k))) * 4u);
+                  const uint32_t rl = cjb + (E >> 1);
+                  sts_ring8_if(tga, rl, kCodeLong | k, rl < pendb || (rl == pendb && (E & 1u) != 0));
+                }
+                if (j + kend > dirty_until) dirty_until = j + kend;
+              }
+              const uint32_t src = (j + 3) & 31;
+              sts_u32_if(xchi_r + (j & 3) * 4, wI, lane == src);
+              uint32_t inc = kIntInf;
+              if (lng) __syncwarp();   // this step's own length-35 edge lands in the slot that joins now
+              if (j + 35 <= dirty_until) {
+                const uint32_t ra = ring_r + ((j + 32) & 511) * 8;
+                uint32_t fbj, cdj;
+                lds_ring8(ra, fbj, cdj);
+                (void)cdj;
+                inc = fbj == kInfBits ? kIntInf : (((fbj - i_base) << 7) | 64u);
+                sts_u32_if(ra, kInfBits, lane == 0);   // free the slot for target j+35+512 (first written 254 steps from now)
+              }
+              if (lane == src) wI = inc;
+              e2I = en_; CJ = x_ & ~127u;
+              tvI = tv1I; tv1I = tv2_; ds2 = ds3_; llbI = llb1I; llb1I = llb2_;
+            }
+          }
+          igroups++;
+          kind = 3;
+        } else if (imode) {
           // Integer groups run back to back in a loop of their own: the conditions that can change from one
           // group to the next (flags of the next group, the interval, the block end, the tag of the stage the
           // pipeline runs into) cost a dozen instructions; everything else (ring clean, no shortcut zone nearby)
@@ -957,7 +1082,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
           if (jb >= nb) break;
           if (skip_noop && ((flag_cur >> (hb * 4)) & 0xfu) == 0 && skip_left == 0 && !just_finished && jb + 4 <= nb) {
             uint32_t t0_s = t0_l - sb * 64, dsx_s = dsx_c + sb * 256, gl_s = gl_c + sb * 64, lac_s = lac_c + sb * 16;
-            uint32_t ring_s = ring_c + sb * 128, lane_rot = (lane - 3u - sb * 8u) & 31u, sidx = 3u + hb * 4u;
+            uint32_t ring_s = ring_c + sb * 64, lane_rot = (lane - 3u - sb * 8u) & 31u, sidx = 3u + hb * 4u;
             if (hb & 1) { ZB_DP_FAST_4B(true, false) } else { ZB_DP_FAST_4A(true, false) }
             (void)lane_rot;
             continue;
@@ -980,7 +1105,7 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
             if ((m16 & kShortcutFlag) && skip_left == 0 && !just_finished) skip_left = kMaxMatch;
             if (skip_left > 0) {
               // costs[j+258] = costs[j] + cost(258,1), unconditionally; no literal, no other edge
-              sts_ring_if(ring_r + ((j + kMaxMatch - 3) & 511) * 16, round_to_f32(cj + cost258), kCodeLong | (uint32_t)kMaxMatch, lane == 0);
+              sts_ring8_if(ring_r + ((j + kMaxMatch - 3) & 511) * 8, __float_as_uint(__double2float_rn(cj + cost258)), kCodeLong | (uint32_t)kMaxMatch, lane == 0);
               if (j + kMaxMatch > dirty_until) dirty_until = j + kMaxMatch;
               skip_left--;
               guard_until = j + 600;
@@ -1023,13 +1148,13 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
                   if (k <= run_len(ea.z)) e = ea.z;
                   if (k <= run_len(ea.y)) e = ea.y;
                   if (k <= run_len(ea.x)) e = ea.x;
-                  const uint32_t tga = ring_r + ((j + k - 3) & 511) * 16;
-                  const double pend = lds_f64(tga);
+                  const uint32_t tga = ring_r + ((j + k - 3) & 511) * 8;
+                  const double pend = (double)__uint_as_float(lds_u32(tga));
                   if (pend <= mc) continue;  // squeeze.c:293
                   const int dsym = (int)run_dsym(e);
                   double nc2 = (double)(length_extra_bits((int)k) + dist_symbol_extra_bits(dsym)) + s.lencost[k] + s.dcost[dsym];
                   nc2 = nc2 + cj;
-                  sts_ring_if(tga, round_to_f32(nc2), kCodeLong | k, nc2 < pend);
+                  sts_ring8_if(tga, __float_as_uint(__double2float_rn(nc2)), kCodeLong | k, nc2 < pend);
                 }
                 if (j + kend > dirty_until) dirty_until = j + kend;
               }
@@ -1044,9 +1169,11 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
             double inc = kInfD; uint32_t inl = 0;
             __syncwarp();
             if (j + 35 <= dirty_until) {
-              const uint32_t ra = ring_r + ((j + 32) & 511) * 16;
-              lds_ring(ra, inc, inl);
-              sts_f64_if(ra, kInfD, lane == 0);  // free the slot for target j+35+512
+              const uint32_t ra = ring_r + ((j + 32) & 511) * 8;
+              uint32_t fbj;
+              lds_ring8(ra, fbj, inl);
+              inc = (double)__uint_as_float(fbj);
+              sts_u32_if(ra, kInfBits, lane == 0);  // free the slot for target j+35+512
               __syncwarp();
             }
             if (lane == src) { w = inc; wl = inl; }
@@ -1065,6 +1192,8 @@ __global__ void __launch_bounds__(64) k_iterate(Batch b, const uint32_t* __restr
       if (lane == 0) s.dpn[5] += nslow;
 #undef ZB_KIND_TICK
 #undef ZB_DPI_GROUP
+#undef ZB_DPI_4A
+#undef ZB_DPI_4B
 #undef ZB_DPI_STEP
 #undef ZB_DP_FAST_GROUP
 #undef ZB_DP_FAST_8
