@@ -5,7 +5,9 @@
 //   per iteration:  cost model constants (GetCostModelMinCost squeeze.c:163-198)
 //                   forward DP          (GetBestLengths squeeze.c:217-309)   push form, pending costs
 //                                        of the next 32 targets in a register window, longer edges
-//                                        in a 512-entry shared-memory ring, fp64 add / fp32 store
+//                                        in a 512-entry shared-memory ring; the reference's fp64 add /
+//                                        fp32 store arithmetic, carried out in integers while a group's
+//                                        costs stay inside one float binade ("integer window" below)
 //                   trace-back          (TraceBackwards squeeze.c:317-336)   speculative multi-start
 //                                        chase in shared-memory windows
 //                   follow + histogram  (FollowPath squeeze.c:338-389)       table lookups, 32 wide
@@ -128,11 +130,6 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
   return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
