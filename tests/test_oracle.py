@@ -151,3 +151,19 @@ def test_integer_dp_model_equals_reference_dp(name, data, s, e, iters):
     assert steps_total > 0
     if name in ("text", "random"):
         assert steps_int > 0.8 * steps_total   # the model really ran in the integer representation
+
+
+def test_integer_dp_model_on_the_bench_giant_master_block():
+    """master block 85 of the C2 bench text holds the 969,128-position block (costs beyond 2^21, float ulp 0.25):
+    15 DP passes of the model against the reference arithmetic, one block (no splitting)"""
+    import ctypes as C
+    zref.ensure_built()
+    lib = C.CDLL(os.path.join(zref.ORACLE_DIR, "_build", "libdp_int_model.so"))
+    lib.zo_dp_int_check.restype = C.c_uint64
+    lib.zo_dp_int_check.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
+    text = corpus.synth_text(86_000_000, 2)      # a prefix of the bench text (the generator is prefix-stable)
+    a = 85 * 1_000_000
+    buf = np.frombuffer(text[a - 32768:a + 1_000_000], dtype=np.uint8).copy()
+    out = np.zeros(8, dtype=np.uint64)
+    assert lib.zo_dp_int_check(buf.ctypes.data, 32768, 32768 + 1_000_000, 15, out.ctypes.data) == 0
+    assert int(out[1]) > 0.95 * int(out[0])
