@@ -153,6 +153,7 @@ def test_integer_dp_model_equals_reference_dp(name, data, s, e, iters):
         assert steps_int > 0.8 * steps_total   # the model really ran in the integer representation
 
 
+@pytest.mark.slow
 def test_integer_dp_model_on_the_bench_giant_master_block():
     """master block 85 of the C2 bench text holds the 969,128-position block (costs beyond 2^21, float ulp 0.25):
     15 DP passes of the model against the reference arithmetic, one block (no splitting)"""
