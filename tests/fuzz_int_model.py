@@ -1,9 +1,9 @@
-"""CPU developer tool: random inputs (small alphabets, noisy periods, text-like, binary-like, byte runs, repeated
+"""Test infrastructure (not collected by pytest): random inputs (small alphabets, noisy periods, text-like, binary-like, byte runs, repeated
 phrases) x random ranges x {fixed tree, 1..16 iterations} through oracle/dp_int_model.c, which checks the integer
-formulation of the forward DP against the reference arithmetic on every pass.  usage: fuzz_int_model.py [seed] [seconds]"""
+formulation of the forward DP against the reference arithmetic on every pass.  usage: tests/fuzz_int_model.py [seed] [seconds]"""
 import sys, ctypes as C, numpy as np, time
 import os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from zopfli_b200 import corpus
 lib = C.CDLL(os.path.join(ROOT, 'oracle', '_build', 'libdp_int_model.so'))
